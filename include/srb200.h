@@ -1,0 +1,180 @@
+/*
+ * srb200.h -- C ABI of the B200-native MAP super-resolution gradient engine (libsrb200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of rteammco/super-resolution: one evaluation
+ * of cost + gradient of the MAP objective.  The reference has no FFI layer; its seams are C++
+ * virtual interfaces.  Each entry point below names the reference interface it stands behind
+ * (paths relative to the reference root); INTEGRATION.md shows the adapter subclasses a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns an srb_status (0 = SRB_OK) and never
+ *     throws; srb_last_error() gives the message of the last failure on a context.  The
+ *     reference aborts through glog CHECK on the same conditions (e.g. objective_data_term.cpp:
+ *     91-95, image_model.cpp:66-67); adapters CHECK on the status.
+ *   - images are planar row-major fp64, index c*H*W + row*W + col (src/util/util.cpp:81-89),
+ *     exactly the layout ALGLIB's real_1d_array holds (irls_map_solver.cpp:232-239).
+ *   - "host" pointers are caller-owned CPU memory; "dev" pointers are CUDA device memory on the
+ *     context's device.  Host buffers may be pinned with srb_pin_host for full PCIe rate.
+ *   - a context is bound to one CUDA device and one stream; it is not thread-safe (the reference
+ *     calls every interface from one thread).
+ *   - there is NO CPU fallback: every entry point that computes needs a CUDA device and fails
+ *     with SRB_ERR_CUDA otherwise.
+ */
+#ifndef SRB200_H_
+#define SRB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct srb_ctx srb_ctx;
+
+typedef enum {
+  SRB_OK = 0,
+  SRB_ERR_INVALID = 1,   /* bad argument (the reference would CHECK-fail) */
+  SRB_ERR_CUDA = 2,      /* CUDA runtime error / no device */
+  SRB_ERR_GEOMETRY = 3,  /* (size, scale) for which cv::resize's index map is not block-regular */
+  SRB_ERR_STATE = 4,     /* call order (e.g. evaluation before srb_set_observations) */
+  SRB_ERR_NOMEM = 5
+} srb_status;
+
+/* Regularizer kinds (src/optimization/tv_regularizer.h, btv_regularizer.h). */
+enum { SRB_REG_NONE = -1, SRB_REG_TV = 0, SRB_REG_TV3D = 1, SRB_REG_BTV = 2 };
+
+/* Kernel path selection.  AUTO takes the fused tile kernel whenever the model qualifies and the
+ * reference-order kernels otherwise; both run on the GPU. */
+enum { SRB_PATH_AUTO = 0, SRB_PATH_REFERENCE_ORDER = 1, SRB_PATH_FUSED = 2 };
+
+/*
+ * The image formation model A_k = D * B * M_k, what ImageModel::CreateImageModel builds
+ * (src/image_model/image_model.cpp:17-61; ImageModelParameters image_model.h:26-44) plus the
+ * shape of the observations MapSolver is constructed with (src/optimization/map_solver.cpp:52-86:
+ * HR size = LR size * scale).
+ */
+typedef struct {
+  int lr_height, lr_width; /* size of every low-resolution observation */
+  int num_channels;        /* channels per observation */
+  int num_frames;          /* observations held by THIS context (a rank's frame shard) */
+  int scale;               /* downsampling scale s >= 1 (DownsamplingModule) */
+  int psf_size;            /* K, odd: blur_kernel_ is K x K; 0 = no BlurModule */
+  const double* psf;       /* K*K row-major correlation kernel (blur_module.cpp:20-22), host */
+  const double* shifts;    /* 2*num_frames doubles dx_0,dy_0,dx_1,... (motion_shift.h:14-18);
+                              NULL = no MotionModule */
+} srb_model_desc;
+
+/* Library version string. */
+const char* srb_version(void);
+/* Number of CUDA devices visible (0 if none / no driver). */
+int srb_device_count(void);
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* Builds a context on CUDA device `device`.  Replaces: ImageModel::CreateImageModel +
+ * MapSolver::MapSolver (map_solver.cpp:52-86).  Fails with SRB_ERR_GEOMETRY when cv::resize
+ * (INTER_NEAREST) would not map LR<->HR block-regularly for this size/scale. */
+srb_status srb_create(const srb_model_desc* desc, int device, srb_ctx** out);
+void srb_destroy(srb_ctx* ctx);
+const char* srb_last_error(const srb_ctx* ctx);
+
+/* Uploads the observations once, at LR resolution: lr is [num_frames][num_channels][h][w].
+ * Replaces the observation copies MapSolver keeps (map_solver.cpp:81-85; the nearest-neighbour
+ * upsampling done there is a pure index map and is folded into the kernels). */
+srb_status srb_set_observations(srb_ctx* ctx, const double* lr_host);
+/* Same, from device memory (layout identical). */
+srb_status srb_set_observations_dev(srb_ctx* ctx, const double* lr_dev);
+
+/* Channel sub-range [c0, c1) the following evaluations work on -- IRLSMapSolver's
+ * split_channels (irls_map_solver.cpp:200-206; ObjectiveDataTerm channel_start/channel_end,
+ * objective_data_term.h:24-31).  Default: all channels.  Resets the IRLS weights to 1. */
+srb_status srb_set_channel_range(srb_ctx* ctx, int c0, int c1);
+
+/* Regularizer + regularization parameter: MapSolver::AddRegularizer (map_solver.h:92-93) with a
+ * TotalVariationRegularizer (SetUse3dTotalVariation for SRB_REG_TV3D) or a
+ * BilateralTotalVariationRegularizer(scale_range, spatial_decay) (btv_regularizer.cpp:48-65).
+ * kind = SRB_REG_NONE or lambda <= 0 removes it.  Resets the IRLS weights to 1
+ * (irls_map_solver.cpp:66-74). */
+srb_status srb_set_regularizer(srb_ctx* ctx, int kind, double lambda, int btv_range,
+                               double btv_decay);
+
+/* IRLS weights for the active channel range, (c1-c0)*H*W doubles; NULL = all ones.  This is the
+ * upload done where the reference constructs ObjectiveIRLSRegularizationTerm per outer iteration
+ * (irls_map_solver.cpp:83-93). */
+srb_status srb_set_irls_weights(srb_ctx* ctx, const double* weights_host);
+/* IRLS re-weighting on device (irls_map_solver.cpp:128-143): w = 1 / max(1e-5, reg(x)).
+ * x_host = NULL re-uses the estimate of the last evaluation; weights_out_host may be NULL. */
+srb_status srb_reweight(srb_ctx* ctx, const double* x_host, double* weights_out_host);
+
+/* Which kernel path evaluations take (default SRB_PATH_AUTO); srb_active_path reports the one
+ * the current configuration resolves to. */
+srb_status srb_set_path(srb_ctx* ctx, int path);
+int srb_active_path(const srb_ctx* ctx);
+/* Multi-GPU frame sharding: this context holds the frames of one rank.  The data
+ * term covers the context's frames; the regularizer term is computed only for HR rows
+ * [row_begin, row_end) so that the sum over ranks is the full objective.  Default: all rows. */
+srb_status srb_set_regularizer_rows(srb_ctx* ctx, int row_begin, int row_end);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* ObjectiveFunction::ComputeAllTerms (objective_function.cpp:5-20), the body of
+ * AlglibObjectiveFunction (alglib_objective.cpp:142-152): cost = data term + IRLS regularization
+ * term, gradient OVERWRITTEN with the full sum (gradient_host may be NULL: cost only).
+ * x and gradient: (c1-c0)*H*W doubles on the host. */
+srb_status srb_eval(srb_ctx* ctx, const double* x_host, double* gradient_host, double* cost);
+/* Same with device-resident x / gradient (no PCIe traffic except the cost scalar). */
+srb_status srb_eval_dev(srb_ctx* ctx, const double* x_dev, double* gradient_dev, double* cost);
+/* Multi-GPU form: writes this rank's partial gradient to gradient_cost_dev[0..n) and its partial
+ * cost to gradient_cost_dev[n] (n = (c1-c0)*H*W), all on the context's stream, without any host
+ * synchronisation -- ready for ONE allreduce(sum) over n+1 doubles. */
+srb_status srb_eval_partial_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev);
+
+/* ObjectiveDataTerm::Compute (objective_data_term.cpp:98-116): returns the data cost and ADDS the
+ * data gradient into gradient_host (may be NULL). */
+srb_status srb_data_term(srb_ctx* ctx, const double* x_host, double* gradient_host_accum,
+                         double* cost);
+/* ObjectiveIRLSRegularizationTerm::Compute (objective_irls_regularization_term.cpp:10-58):
+ * cost = sum lambda*w*r^2, gradient ADDED into gradient_host (may be NULL). */
+srb_status srb_irls_term(srb_ctx* ctx, const double* x_host, double* gradient_host_accum,
+                         double* cost);
+
+/* Regularizer::ApplyToImage (regularizer.h:26-28; tv_regularizer.cpp:110-132,
+ * btv_regularizer.cpp:67-90) for the configured regularizer: values_out[num_channels*H*W]. */
+srb_status srb_reg_apply(srb_ctx* ctx, const double* x_host, int num_channels,
+                         double* values_out);
+/* Regularizer::ApplyToImageWithDifferentiation (regularizer.h:41-45; tv_regularizer.cpp:134-227,
+ * btv_regularizer.cpp:92-170): values and partial derivatives of sum_j c_j r_j^2. */
+srb_status srb_reg_apply_diff(srb_ctx* ctx, const double* x_host, const double* constants_host,
+                              int num_channels, double* values_out, double* partials_out);
+
+/* ImageModel::ApplyToImage(ImageData*, index) for one channel (image_model.cpp:86-91): M_k, B, D
+ * applied to an H x W image (any size); lr_out must hold int(H*(1/s)) * int(W*(1/s)) doubles
+ * (image_data.cpp:353-364); the decimation index map is cv::resize's, bit-exact. */
+srb_status srb_forward(srb_ctx* ctx, int frame, const double* hr_host, int H, int W,
+                       double* lr_out_host);
+/* ImageModel::ApplyTransposeToImage for one channel (image_model.cpp:93-101): D^T (zero insert),
+ * B^T (correlation with blur_kernel_.t()), M_k^T (warp by the negated shift); input h x w,
+ * output (h*s) x (w*s). */
+srb_status srb_transpose(srb_ctx* ctx, int frame, const double* lr_host, int h, int w,
+                         double* hr_out_host);
+
+/* ---- plumbing --------------------------------------------------------------------------- */
+/* Page-locks a caller buffer (e.g. ALGLIB's x / g arrays) so H2D/D2H run at full PCIe rate. */
+srb_status srb_pin_host(void* ptr, unsigned long long bytes);
+srb_status srb_unpin_host(void* ptr);
+/* The context's CUDA stream (a cudaStream_t) and device scratch the host layer may use. */
+void* srb_stream(srb_ctx* ctx);
+double* srb_dev_x(srb_ctx* ctx);         /* (c1-c0)*H*W estimate buffer */
+double* srb_dev_gradient(srb_ctx* ctx);  /* (c1-c0)*H*W + 1 gradient (+cost) buffer */
+srb_status srb_synchronize(srb_ctx* ctx);
+
+typedef struct {
+  double last_eval_kernel_ms;   /* device time of the kernels of the last evaluation */
+  double last_eval_h2d_ms, last_eval_d2h_ms;
+  unsigned long long num_evals; /* evaluations so far */
+  unsigned long long kernel_launches; /* CUDA kernels launched by this context so far */
+  unsigned long long algorithmic_bytes_per_eval; /* 8*C*P*(2|3 + N/s^2) */
+} srb_timing;
+srb_status srb_get_timing(srb_ctx* ctx, srb_timing* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H_ */

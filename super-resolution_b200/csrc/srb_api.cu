@@ -1,0 +1,659 @@
+// srb_api.cu -- C ABI (include/srb200.h) of the B200-native MAP super-resolution gradient engine.
+//
+// Host-side orchestration only: geometry tables, buffer management, kernel launches, timing.
+// All arithmetic of the hot path runs in the CUDA kernels of srb_kernels_*.cuh; there is no CPU
+// fallback anywhere in this library.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "srb_common.cuh"
+#include "srb_kernels_fused.cuh"
+#include "srb_kernels_generic.cuh"
+#include "srb_kernels_reg.cuh"
+
+using namespace srb;
+
+namespace {
+
+// ---- geometry (host) ---------------------------------------------------------------------------
+// cv::resize INTER_NEAREST index map (reference call: image_data.cpp:341-347): bit-exact fp64.
+int nearest_index(int q, int n_src, int n_dst) {
+  const double inv_scale = (double)n_dst / (double)n_src;
+  const double ifx = 1.0 / inv_scale;
+  int s = (int)std::floor(q * ifx);
+  if (s > n_src - 1) s = n_src - 1;
+  return s;
+}
+// ImageData::ResizeImage(scale factor) output size (image_data.cpp:353-364).
+void lr_size(int s, int H, int W, int* h, int* w) {
+  const double f = 1.0 / (double)s;
+  *w = (int)(W * f);
+  *h = (int)(H * f);
+}
+// Fixed-point translation of cv::warpAffine for the matrix [1 0 dx; 0 1 dy] (motion_module.cpp:
+// 18-24): AB_BITS = 10, round_delta = 16, INTER_BITS = 5.
+WarpQ quantize_warp(double dx, double dy, int H, int* rowY) {
+  WarpQ q;
+  const double m2 = -dx, m5 = -dy;
+  const long X0 = std::lrint(m2 * 1024.0) + 16;
+  q.nX = (int)(X0 >> 5);
+  q.uniform = true;
+  q.nY = 0;
+  for (int y = 0; y < H; ++y) {
+    const long Y0 = std::lrint((1.0 * y + m5) * 1024.0) + 16;
+    const int Y = (int)(Y0 >> 5);
+    if (y == 0) q.nY = Y;
+    if (Y != 32 * y + q.nY) q.uniform = false;
+    if (rowY) rowY[y] = Y;
+  }
+  return q;
+}
+
+template <class T>
+srb_status dev_alloc(srb_ctx* ctx, T** ptr, size_t count) {
+  if (*ptr) return SRB_OK;
+  cudaError_t e = cudaMalloc((void**)ptr, (count ? count : 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    *ptr = nullptr;
+    (void)cudaGetLastError();
+    return ctx->fail(SRB_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  }
+  return SRB_OK;
+}
+template <class T>
+void dev_free(T** ptr) {
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+}
+
+struct TempBuf {  // RAII device scratch for the one-off forward / transpose entry points
+  void* p = nullptr;
+  ~TempBuf() {
+    if (p) cudaFree(p);
+  }
+  template <class T>
+  T* get() { return (T*)p; }
+};
+
+inline dim3 grid2d(int W, int H, int Z) { return dim3((W + 31) / 32, (H + 7) / 8, Z); }
+inline int fill_blocks(size_t n) {
+  size_t b = (n + 255) / 256;
+  return (int)(b > 148 * 16 ? 148 * 16 : (b ? b : 1));
+}
+
+GenericParams make_params(const srb_ctx* c, bool transpose_warp) {
+  GenericParams P;
+  P.H = c->g.H; P.W = c->g.W; P.h = c->g.h; P.w = c->g.w; P.s = c->g.s; P.K = c->g.K; P.hk = c->g.hk;
+  P.N = c->g.N; P.Ca = c->Ca(); P.Ct = c->g.Ct; P.c0 = c->c0;
+  P.src_r = c->d_src_r; P.src_c = c->d_src_c; P.psf = c->d_psf;
+  P.rowY = transpose_warp ? c->d_rowY_tr : c->d_rowY_fwd;
+  P.nX = transpose_warp ? c->d_nX_tr : c->d_nX_fwd;
+  return P;
+}
+RegParams make_reg_params(const srb_ctx* c, int C) {
+  RegParams R;
+  R.H = c->g.H; R.W = c->g.W; R.C = C; R.kind = c->reg_kind; R.R = c->btv_R; R.decay = c->d_decay;
+  return R;
+}
+
+srb_status ensure_partials(srb_ctx* c, size_t n) {
+  if (n <= c->partial_capacity) return SRB_OK;
+  dev_free(&c->d_partial);
+  srb_status st = dev_alloc(c, &c->d_partial, n);
+  if (st == SRB_OK) c->partial_capacity = n;
+  return st;
+}
+
+bool reg_active(const srb_ctx* c) { return c->reg_kind != SRB_REG_NONE && c->lambda > 0.0; }
+
+int resolve_path(const srb_ctx* c) {
+  if (c->path == SRB_PATH_REFERENCE_ORDER) return SRB_PATH_REFERENCE_ORDER;
+  return fused_supported(c) ? SRB_PATH_FUSED : SRB_PATH_REFERENCE_ORDER;
+}
+
+// ---- evaluation core ---------------------------------------------------------------------------
+// ObjectiveFunction::ComputeAllTerms on device buffers.  d_g may be NULL (cost only).  On return
+// (stream-ordered) c->d_cost[0..2] hold data cost, regularization cost and their sum; if `tail` is
+// non-NULL the sum is also written there.
+srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, bool data_term,
+                     bool reg_term, bool accumulate) {
+  if (data_term && !c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
+  const Geometry& G = c->g;
+  const int Ca = c->Ca();
+  SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_cost, 0, 4 * sizeof(double), c->stream));
+  const bool do_reg = reg_term && reg_active(c) && c->reg_row1 > c->reg_row0;
+
+  if (resolve_path(c) == SRB_PATH_FUSED && data_term && !accumulate && (reg_term || !reg_active(c))) {
+    srb_status st = fused_eval(c, d_x, d_g, do_reg);
+    if (st != SRB_OK) return st;
+  } else {
+    if (data_term) {
+      srb_status st = dev_alloc(c, &c->d_pooled, (size_t)G.N * G.Ct * c->p);
+      if (st != SRB_OK) return st;
+      const dim3 grid = grid2d(G.w, G.h, G.N * Ca);
+      const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+      if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
+      k_forward_generic<1><<<grid, dim3(32, 8), 0, c->stream>>>(make_params(c, false), d_x, c->d_y,
+                                                               c->d_pooled, c->d_partial);
+      k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 0);
+      c->timing.kernel_launches += 2;
+      if (d_g) {
+        k_adjoint_generic<<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(
+            make_params(c, true), c->d_pooled, d_g, 2.0, accumulate ? 1 : 0);
+        c->timing.kernel_launches += 1;
+      }
+    } else if (d_g && !accumulate) {
+      SRB_CUDA_CHECK(c, cudaMemsetAsync(d_g, 0, c->n_active() * sizeof(double), c->stream));
+    }
+    if (do_reg) {
+      srb_status st = dev_alloc(c, &c->d_vals, (size_t)G.Ct * c->P);
+      if (st != SRB_OK) return st;
+      const RegParams R = make_reg_params(c, Ca);
+      k_reg_values<0><<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals);
+      const int rows = c->reg_row1 - c->reg_row0;
+      const dim3 grid = grid2d(G.W, rows, Ca);
+      const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+      if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
+      k_reg_partials<1><<<grid, dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals, c->d_w, c->lambda,
+                                                            c->reg_row0, c->reg_row1, d_g, c->d_partial);
+      k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 1);
+      c->timing.kernel_launches += 3;
+    }
+  }
+  k_finish_cost<<<1, 1, 0, c->stream>>>(c->d_cost, tail);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  c->timing.num_evals += 1;
+  return SRB_OK;
+}
+
+srb_status fetch_cost(srb_ctx* c, int slot, double* cost) {
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_cost, c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost,
+                                    c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (cost) *cost = c->h_cost[slot];
+  return SRB_OK;
+}
+
+void update_timing(srb_ctx* c) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->timing.last_eval_h2d_ms = ms;
+  if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->timing.last_eval_kernel_ms = ms;
+  if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->timing.last_eval_d2h_ms = ms;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* srb_version(void) { return "srb200 0.1 (sm_100a)"; }
+
+int srb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* srb_last_error(const srb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
+  if (!out) return SRB_ERR_INVALID;
+  *out = nullptr;
+  srb_ctx* c = new (std::nothrow) srb_ctx();
+  if (!c) return SRB_ERR_NOMEM;
+  *out = c;  // returned even on failure so the caller can read srb_last_error, then srb_destroy
+  if (!d) return c->fail(SRB_ERR_INVALID, "null model description");
+  // The reference CHECK-fails on these (map_solver.cpp:52-76, blur_module.cpp:13-18,
+  // downsampling_module.cpp:13-17, objective_data_term.cpp:91-95).
+  if (d->lr_height <= 0 || d->lr_width <= 0 || d->num_channels <= 0)
+    return c->fail(SRB_ERR_INVALID, "observation size and channel count must be positive");
+  if (d->num_frames <= 0) return c->fail(SRB_ERR_INVALID, "cannot solve with 0 observations");
+  if (d->scale < 1) return c->fail(SRB_ERR_INVALID, "downsampling scale must be >= 1");
+  if (d->psf_size < 0 || (d->psf_size > 0 && (d->psf_size % 2 == 0 || !d->psf)))
+    return c->fail(SRB_ERR_INVALID, "blur kernel size must be odd and the kernel non-null");
+  if (d->psf_size > 63) return c->fail(SRB_ERR_INVALID, "blur kernel larger than 63x63 is not supported");
+
+  Geometry& G = c->g;
+  G.h = d->lr_height; G.w = d->lr_width; G.s = d->scale; G.N = d->num_frames; G.Ct = d->num_channels;
+  const long long Hl = (long long)G.h * G.s, Wl = (long long)G.w * G.s;
+  // map_solver.cpp:96-101 guards C*H*W <= INT_MAX
+  if (Hl * Wl * G.Ct > 2147483647LL) return c->fail(SRB_ERR_INVALID, "C*H*W exceeds INT_MAX");
+  G.H = (int)Hl; G.W = (int)Wl;
+  c->has_blur = d->psf_size > 0;
+  G.K = c->has_blur ? d->psf_size : 1;
+  G.hk = G.K / 2;
+  c->P = (size_t)G.H * G.W;
+  c->p = (size_t)G.h * G.w;
+  c->psf_h.assign(1, 1.0);
+  if (c->has_blur) c->psf_h.assign(d->psf, d->psf + (size_t)G.K * G.K);
+  c->has_motion = d->shifts != nullptr;
+  c->shifts_h.assign((size_t)2 * G.N, 0.0);
+  if (c->has_motion) c->shifts_h.assign(d->shifts, d->shifts + (size_t)2 * G.N);
+  for (double v : c->shifts_h)
+    if (!(std::fabs(v) < 1.0e6)) return c->fail(SRB_ERR_INVALID, "motion shift out of range");
+
+  // cv::resize must act block-regularly between LR and HR, which is what the fused residual /
+  // sum-pool / zero-insert chain of the reference (objective_data_term.cpp:29,57-59) assumes.
+  {
+    int h2, w2;
+    lr_size(G.s, G.H, G.W, &h2, &w2);
+    bool ok = (h2 == G.h && w2 == G.w);
+    for (int q = 0; ok && q < G.h; ++q) ok = nearest_index(q, G.H, G.h) == q * G.s;
+    for (int q = 0; ok && q < G.w; ++q) ok = nearest_index(q, G.W, G.w) == q * G.s;
+    for (int r = 0; ok && r < G.H; ++r) ok = nearest_index(r, G.h, G.H) == r / G.s;
+    for (int r = 0; ok && r < G.W; ++r) ok = nearest_index(r, G.w, G.W) == r / G.s;
+    if (!ok) return c->fail(SRB_ERR_GEOMETRY, "cv::resize nearest index map is not block-regular for this size/scale");
+  }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return c->fail(SRB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return c->fail(SRB_ERR_INVALID, "invalid CUDA device index");
+  c->device = device;
+  SRB_CUDA_CHECK(c, cudaSetDevice(device));
+  SRB_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) SRB_CUDA_CHECK(c, cudaEventCreate(&e));
+
+  // tables
+  std::vector<int> src_r(G.h), src_c(G.w);
+  for (int q = 0; q < G.h; ++q) src_r[q] = nearest_index(q, G.H, G.h);
+  for (int q = 0; q < G.w; ++q) src_c[q] = nearest_index(q, G.W, G.w);
+  std::vector<int> rowY_f((size_t)G.N * G.H), rowY_t((size_t)G.N * G.H), nX_f(G.N), nX_t(G.N);
+  c->warp_fwd.resize(G.N);
+  c->warp_tr.resize(G.N);
+  c->warps_uniform = true;
+  c->warps_integer = true;
+  for (int k = 0; k < G.N; ++k) {
+    const double dx = c->shifts_h[2 * k], dy = c->shifts_h[2 * k + 1];
+    c->warp_fwd[k] = quantize_warp(dx, dy, G.H, &rowY_f[(size_t)k * G.H]);
+    c->warp_tr[k] = quantize_warp(-dx, -dy, G.H, &rowY_t[(size_t)k * G.H]);
+    nX_f[k] = c->warp_fwd[k].nX;
+    nX_t[k] = c->warp_tr[k].nX;
+    c->warps_uniform = c->warps_uniform && c->warp_fwd[k].uniform && c->warp_tr[k].uniform;
+    const int frac = (c->warp_fwd[k].nX | c->warp_fwd[k].nY | c->warp_tr[k].nX | c->warp_tr[k].nY) & 31;
+    c->warps_integer = c->warps_integer && frac == 0;
+  }
+  srb_status st;
+#define ALLOC_COPY(dptr, hvec)                                                                   \
+  if ((st = dev_alloc(c, &dptr, hvec.size())) != SRB_OK) return st;                              \
+  SRB_CUDA_CHECK(c, cudaMemcpy(dptr, hvec.data(), hvec.size() * sizeof(hvec[0]), cudaMemcpyHostToDevice));
+  ALLOC_COPY(c->d_psf, c->psf_h)
+  ALLOC_COPY(c->d_src_r, src_r)
+  ALLOC_COPY(c->d_src_c, src_c)
+  ALLOC_COPY(c->d_rowY_fwd, rowY_f)
+  ALLOC_COPY(c->d_rowY_tr, rowY_t)
+  ALLOC_COPY(c->d_nX_fwd, nX_f)
+  ALLOC_COPY(c->d_nX_tr, nX_t)
+#undef ALLOC_COPY
+
+  const size_t n_all = (size_t)G.Ct * c->P;
+  if ((st = dev_alloc(c, &c->d_y, (size_t)G.N * G.Ct * c->p)) != SRB_OK) return st;
+  if ((st = dev_alloc(c, &c->d_x, n_all)) != SRB_OK) return st;
+  if ((st = dev_alloc(c, &c->d_grad, n_all + 1)) != SRB_OK) return st;
+  if ((st = dev_alloc(c, &c->d_w, n_all)) != SRB_OK) return st;
+  if ((st = dev_alloc(c, &c->d_cost, 4)) != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaMallocHost((void**)&c->h_cost, 4 * sizeof(double)));
+  k_fill<<<fill_blocks(n_all), 256, 0, c->stream>>>(c->d_w, n_all, 1.0);
+  c->c0 = 0;
+  c->c1 = G.Ct;
+  c->reg_row0 = 0;
+  c->reg_row1 = G.H;
+  if ((st = fused_setup(c)) != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+void srb_destroy(srb_ctx* c) {
+  if (!c) return;
+  if (c->stream) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  fused_teardown(c);
+  dev_free(&c->d_psf); dev_free(&c->d_src_r); dev_free(&c->d_src_c);
+  dev_free(&c->d_rowY_fwd); dev_free(&c->d_rowY_tr); dev_free(&c->d_nX_fwd); dev_free(&c->d_nX_tr);
+  dev_free(&c->d_y); dev_free(&c->d_decay); dev_free(&c->d_w); dev_free(&c->d_x); dev_free(&c->d_grad);
+  dev_free(&c->d_pooled); dev_free(&c->d_vals); dev_free(&c->d_aux); dev_free(&c->d_partial);
+  dev_free(&c->d_cost);
+  if (c->h_cost) cudaFreeHost(c->h_cost);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+srb_status srb_set_observations(srb_ctx* c, const double* lr_host) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!lr_host) return c->fail(SRB_ERR_INVALID, "null observations");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_y, lr_host, (size_t)c->g.N * c->g.Ct * c->p * sizeof(double),
+                                    cudaMemcpyHostToDevice, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  c->have_obs = true;
+  return SRB_OK;
+}
+
+srb_status srb_set_observations_dev(srb_ctx* c, const double* lr_dev) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!lr_dev) return c->fail(SRB_ERR_INVALID, "null observations");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_y, lr_dev, (size_t)c->g.N * c->g.Ct * c->p * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  c->have_obs = true;
+  return SRB_OK;
+}
+
+static srb_status reset_weights(srb_ctx* c) {
+  const size_t n = (size_t)c->g.Ct * c->P;
+  k_fill<<<fill_blocks(n), 256, 0, c->stream>>>(c->d_w, n, 1.0);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  return SRB_OK;
+}
+
+srb_status srb_set_channel_range(srb_ctx* c, int c0, int c1) {
+  if (!c) return SRB_ERR_INVALID;
+  // objective_data_term.cpp:91-95
+  if (c0 < 0 || c1 > c->g.Ct || c1 <= c0) return c->fail(SRB_ERR_INVALID, "invalid channel range");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  c->c0 = c0;
+  c->c1 = c1;
+  return reset_weights(c);
+}
+
+srb_status srb_set_regularizer(srb_ctx* c, int kind, double lambda, int btv_range, double btv_decay) {
+  if (!c) return SRB_ERR_INVALID;
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (kind == SRB_REG_NONE || !(lambda > 0.0)) {
+    c->reg_kind = SRB_REG_NONE;
+    c->lambda = 0.0;
+    return reset_weights(c);
+  }
+  if (kind != SRB_REG_TV && kind != SRB_REG_TV3D && kind != SRB_REG_BTV)
+    return c->fail(SRB_ERR_INVALID, "unknown regularizer kind");
+  if (kind == SRB_REG_BTV) {
+    // btv_regularizer.cpp:58-61
+    if (btv_range < 1) return c->fail(SRB_ERR_INVALID, "BTV scale range must be at least 1");
+    if (!(btv_decay > 0.0 && btv_decay <= 1.0))
+      return c->fail(SRB_ERR_INVALID, "BTV spatial decay must be in (0, 1]");
+    if (btv_range > 16) return c->fail(SRB_ERR_INVALID, "BTV scale range larger than 16 is not supported");
+    std::vector<double> tab(2 * btv_range + 1);
+    for (int t = 0; t <= 2 * btv_range; ++t) tab[t] = std::pow(btv_decay, t);  // btv_regularizer.cpp:39
+    dev_free(&c->d_decay);
+    srb_status st = dev_alloc(c, &c->d_decay, tab.size());
+    if (st != SRB_OK) return st;
+    SRB_CUDA_CHECK(c, cudaMemcpy(c->d_decay, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->btv_R = btv_range;
+    c->btv_decay = btv_decay;
+  }
+  c->reg_kind = kind;
+  c->lambda = lambda;
+  fused_reg_changed(c);
+  return reset_weights(c);
+}
+
+srb_status srb_set_irls_weights(srb_ctx* c, const double* w) {
+  if (!c) return SRB_ERR_INVALID;
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (!w) return reset_weights(c);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_w, w, c->n_active() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+srb_status srb_reweight(srb_ctx* c, const double* x_host, double* w_out) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!reg_active(c)) return c->fail(SRB_ERR_STATE, "no regularizer configured");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (x_host)
+    SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, c->n_active() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_reg_values<1><<<grid2d(c->g.W, c->g.H, c->Ca()), dim3(32, 8), 0, c->stream>>>(
+      make_reg_params(c, c->Ca()), c->d_x, c->d_w);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  if (w_out)
+    SRB_CUDA_CHECK(c, cudaMemcpyAsync(w_out, c->d_w, c->n_active() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+srb_status srb_set_path(srb_ctx* c, int path) {
+  if (!c) return SRB_ERR_INVALID;
+  if (path != SRB_PATH_AUTO && path != SRB_PATH_REFERENCE_ORDER && path != SRB_PATH_FUSED)
+    return c->fail(SRB_ERR_INVALID, "unknown path");
+  if (path == SRB_PATH_FUSED && !fused_supported(c))
+    return c->fail(SRB_ERR_INVALID, "the fused kernel does not cover this model (see srb_active_path)");
+  c->path = path;
+  return SRB_OK;
+}
+int srb_active_path(const srb_ctx* c) { return c ? resolve_path(c) : -1; }
+
+srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {
+  if (!c) return SRB_ERR_INVALID;
+  if (row_begin < 0 || row_end > c->g.H || row_end < row_begin)
+    return c->fail(SRB_ERR_INVALID, "invalid regularizer row band");
+  c->reg_row0 = row_begin;
+  c->reg_row1 = row_end;
+  return SRB_OK;
+}
+
+// ---- hot path -----------------------------------------------------------------------------------
+srb_status srb_eval(srb_ctx* c, const double* x_host, double* g_host, double* cost) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t bytes = c->n_active() * sizeof(double);
+  cudaEventRecord(c->ev[0], c->stream);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  cudaEventRecord(c->ev[1], c->stream);
+  srb_status st = eval_core(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr, true, true, false);
+  if (st != SRB_OK) return st;
+  cudaEventRecord(c->ev[2], c->stream);
+  if (g_host) SRB_CUDA_CHECK(c, cudaMemcpyAsync(g_host, c->d_grad, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_cost, c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  cudaEventRecord(c->ev[3], c->stream);
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (cost) *cost = c->h_cost[2];
+  update_timing(c);
+  return SRB_OK;
+}
+
+srb_status srb_eval_dev(srb_ctx* c, const double* x_dev, double* g_dev, double* cost) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev) return c->fail(SRB_ERR_INVALID, "null estimate");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  cudaEventRecord(c->ev[0], c->stream);
+  cudaEventRecord(c->ev[1], c->stream);
+  srb_status st = eval_core(c, x_dev, g_dev, nullptr, true, true, false);
+  if (st != SRB_OK) return st;
+  cudaEventRecord(c->ev[2], c->stream);
+  cudaEventRecord(c->ev[3], c->stream);
+  if (cost) {
+    st = fetch_cost(c, 2, cost);
+    if (st != SRB_OK) return st;
+    update_timing(c);
+  }
+  return SRB_OK;
+}
+
+srb_status srb_eval_partial_dev(srb_ctx* c, const double* x_dev, double* gc_dev) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev || !gc_dev) return c->fail(SRB_ERR_INVALID, "null buffer");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  return eval_core(c, x_dev, gc_dev, gc_dev + c->n_active(), true, true, false);
+}
+
+static srb_status term_host(srb_ctx* c, const double* x_host, double* g_accum, double* cost, bool data) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t bytes = c->n_active() * sizeof(double);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (g_accum) SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_grad, g_accum, bytes, cudaMemcpyHostToDevice, c->stream));
+  // single terms always run the reference-order kernels (they ADD into the caller's gradient in
+  // the reference's operation order)
+  const int saved = c->path;
+  c->path = SRB_PATH_REFERENCE_ORDER;
+  srb_status st = eval_core(c, c->d_x, g_accum ? c->d_grad : nullptr, nullptr, data, !data, true);
+  c->path = saved;
+  if (st != SRB_OK) return st;
+  if (g_accum) SRB_CUDA_CHECK(c, cudaMemcpyAsync(g_accum, c->d_grad, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return fetch_cost(c, data ? 0 : 1, cost);
+}
+
+srb_status srb_data_term(srb_ctx* c, const double* x_host, double* g_accum, double* cost) {
+  return term_host(c, x_host, g_accum, cost, true);
+}
+srb_status srb_irls_term(srb_ctx* c, const double* x_host, double* g_accum, double* cost) {
+  return term_host(c, x_host, g_accum, cost, false);
+}
+
+srb_status srb_reg_apply(srb_ctx* c, const double* x_host, int C, double* values_out) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host || !values_out) return c->fail(SRB_ERR_INVALID, "null buffer");
+  if (c->reg_kind == SRB_REG_NONE) return c->fail(SRB_ERR_STATE, "no regularizer configured");
+  if (C < 1 || C > c->g.Ct) return c->fail(SRB_ERR_INVALID, "invalid channel count");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  srb_status st = dev_alloc(c, &c->d_vals, (size_t)c->g.Ct * c->P);
+  if (st != SRB_OK) return st;
+  const size_t bytes = (size_t)C * c->P * sizeof(double);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  k_reg_values<0><<<grid2d(c->g.W, c->g.H, C), dim3(32, 8), 0, c->stream>>>(make_reg_params(c, C), c->d_x, c->d_vals);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(values_out, c->d_vals, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+srb_status srb_reg_apply_diff(srb_ctx* c, const double* x_host, const double* cst_host, int C,
+                              double* values_out, double* partials_out) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host || !cst_host || !values_out || !partials_out) return c->fail(SRB_ERR_INVALID, "null buffer");
+  if (c->reg_kind == SRB_REG_NONE) return c->fail(SRB_ERR_STATE, "no regularizer configured");
+  if (C < 1 || C > c->g.Ct) return c->fail(SRB_ERR_INVALID, "invalid channel count");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  srb_status st = dev_alloc(c, &c->d_vals, (size_t)c->g.Ct * c->P);
+  if (st != SRB_OK) return st;
+  if ((st = dev_alloc(c, &c->d_aux, (size_t)c->g.Ct * c->P)) != SRB_OK) return st;
+  const size_t bytes = (size_t)C * c->P * sizeof(double);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_aux, cst_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  const RegParams R = make_reg_params(c, C);
+  k_reg_values<0><<<grid2d(c->g.W, c->g.H, C), dim3(32, 8), 0, c->stream>>>(R, c->d_x, c->d_vals);
+  // partials go to d_grad (scratch here)
+  k_reg_partials<0><<<grid2d(c->g.W, c->g.H, C), dim3(32, 8), 0, c->stream>>>(
+      R, c->d_x, c->d_vals, c->d_aux, 0.0, 0, c->g.H, c->d_grad, nullptr);
+  c->timing.kernel_launches += 2;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(values_out, c->d_vals, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(partials_out, c->d_grad, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+srb_status srb_forward(srb_ctx* c, int frame, const double* hr_host, int H, int W, double* lr_out) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!hr_host || !lr_out || H <= 0 || W <= 0) return c->fail(SRB_ERR_INVALID, "bad image");
+  if (frame < 0 || frame >= c->g.N) return c->fail(SRB_ERR_INVALID, "frame index out of range");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  int h, w;
+  lr_size(c->g.s, H, W, &h, &w);
+  if (h <= 0 || w <= 0) return c->fail(SRB_ERR_INVALID, "image smaller than the downsampling scale");
+  std::vector<int> tab((size_t)h + w + H + 1);
+  int* src_r = tab.data();
+  int* src_c = src_r + h;
+  int* rowY = src_c + w;
+  for (int q = 0; q < h; ++q) src_r[q] = nearest_index(q, H, h);
+  for (int q = 0; q < w; ++q) src_c[q] = nearest_index(q, W, w);
+  const WarpQ wq = quantize_warp(c->shifts_h[2 * frame], c->shifts_h[2 * frame + 1], H, rowY);
+  rowY[H] = wq.nX;
+  TempBuf t_tab, t_in, t_out;
+  SRB_CUDA_CHECK(c, cudaMalloc(&t_tab.p, tab.size() * sizeof(int)));
+  SRB_CUDA_CHECK(c, cudaMalloc(&t_in.p, (size_t)H * W * sizeof(double)));
+  SRB_CUDA_CHECK(c, cudaMalloc(&t_out.p, (size_t)h * w * sizeof(double)));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(t_tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(t_in.p, hr_host, (size_t)H * W * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GenericParams P = make_params(c, false);
+  P.H = H; P.W = W; P.h = h; P.w = w; P.N = 1; P.Ca = 1; P.Ct = 1; P.c0 = 0;
+  P.src_r = t_tab.get<int>(); P.src_c = P.src_r + h; P.rowY = P.src_c + w; P.nX = P.rowY + H;
+  k_forward_generic<0><<<grid2d(w, h, 1), dim3(32, 8), 0, c->stream>>>(P, t_in.get<double>(), nullptr,
+                                                                     t_out.get<double>(), nullptr);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(lr_out, t_out.p, (size_t)h * w * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+srb_status srb_transpose(srb_ctx* c, int frame, const double* lr_host, int h, int w, double* hr_out) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!lr_host || !hr_out || h <= 0 || w <= 0) return c->fail(SRB_ERR_INVALID, "bad image");
+  if (frame < 0 || frame >= c->g.N) return c->fail(SRB_ERR_INVALID, "frame index out of range");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const int H = h * c->g.s, W = w * c->g.s;
+  std::vector<int> tab((size_t)H + 1);
+  const WarpQ wq = quantize_warp(-c->shifts_h[2 * frame], -c->shifts_h[2 * frame + 1], H, tab.data());
+  tab[H] = wq.nX;
+  TempBuf t_tab, t_in, t_out;
+  SRB_CUDA_CHECK(c, cudaMalloc(&t_tab.p, tab.size() * sizeof(int)));
+  SRB_CUDA_CHECK(c, cudaMalloc(&t_in.p, (size_t)h * w * sizeof(double)));
+  SRB_CUDA_CHECK(c, cudaMalloc(&t_out.p, (size_t)H * W * sizeof(double)));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(t_tab.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(t_in.p, lr_host, (size_t)h * w * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GenericParams P = make_params(c, true);
+  P.H = H; P.W = W; P.h = h; P.w = w; P.N = 1; P.Ca = 1; P.Ct = 1; P.c0 = 0;
+  P.src_r = nullptr; P.src_c = nullptr; P.rowY = t_tab.get<int>(); P.nX = P.rowY + H;
+  k_adjoint_generic<<<grid2d(W, H, 1), dim3(32, 8), 0, c->stream>>>(P, t_in.get<double>(), t_out.get<double>(), 1.0, 0);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(hr_out, t_out.p, (size_t)H * W * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+// ---- plumbing -----------------------------------------------------------------------------------
+srb_status srb_pin_host(void* ptr, unsigned long long bytes) {
+  if (!ptr || !bytes) return SRB_ERR_INVALID;
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SRB_ERR_CUDA;
+  }
+  return SRB_OK;
+}
+srb_status srb_unpin_host(void* ptr) {
+  if (!ptr) return SRB_ERR_INVALID;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SRB_ERR_CUDA;
+  }
+  return SRB_OK;
+}
+void* srb_stream(srb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+double* srb_dev_x(srb_ctx* c) { return c ? c->d_x : nullptr; }
+double* srb_dev_gradient(srb_ctx* c) { return c ? c->d_grad : nullptr; }
+srb_status srb_synchronize(srb_ctx* c) {
+  if (!c) return SRB_ERR_INVALID;
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+srb_status srb_get_timing(srb_ctx* c, srb_timing* out) {
+  if (!c || !out) return SRB_ERR_INVALID;
+  const double nf = (double)c->g.N / ((double)c->g.s * c->g.s);
+  c->timing.algorithmic_bytes_per_eval =
+      (unsigned long long)(8.0 * (double)c->n_active() * ((reg_active(c) ? 3.0 : 2.0) + nf));
+  *out = c->timing;
+  return SRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+"""ctypes binding of libsrb200.so (include/srb200.h).
+
+`Engine` is a thin, typed wrapper over one srb_ctx; every method maps 1:1 to a C-ABI entry point
+and raises `SrbError` on a non-zero status (the reference aborts through glog CHECK on the same
+conditions).  There is no CPU fallback: constructing an Engine without a CUDA device fails.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_dp = C.POINTER(C.c_double)
+_ctx_p = C.c_void_p
+
+REG_NONE, REG_TV, REG_TV3D, REG_BTV = -1, 0, 1, 2
+PATH_AUTO, PATH_REFERENCE_ORDER, PATH_FUSED = 0, 1, 2
+_STATUS = {0: "SRB_OK", 1: "SRB_ERR_INVALID", 2: "SRB_ERR_CUDA", 3: "SRB_ERR_GEOMETRY",
+           4: "SRB_ERR_STATE", 5: "SRB_ERR_NOMEM"}
+
+# name -> (restype, argtypes); also the export list tests/test_cabi.py checks against srb200.h
+SIGNATURES = {
+    "srb_version": (C.c_char_p, []),
+    "srb_device_count": (C.c_int, []),
+    "srb_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_ctx_p)]),
+    "srb_destroy": (None, [_ctx_p]),
+    "srb_last_error": (C.c_char_p, [_ctx_p]),
+    "srb_set_observations": (C.c_int, [_ctx_p, C.c_void_p]),
+    "srb_set_observations_dev": (C.c_int, [_ctx_p, C.c_void_p]),
+    "srb_set_channel_range": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    "srb_set_regularizer": (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_double]),
+    "srb_set_irls_weights": (C.c_int, [_ctx_p, C.c_void_p]),
+    "srb_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_set_path": (C.c_int, [_ctx_p, C.c_int]),
+    "srb_active_path": (C.c_int, [_ctx_p]),
+    "srb_set_regularizer_rows": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    "srb_eval": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
+    "srb_eval_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
+    "srb_eval_partial_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_data_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
+    "srb_irls_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
+    "srb_reg_apply": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "srb_reg_apply_diff": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "srb_forward": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "srb_transpose": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "srb_pin_host": (C.c_int, [C.c_void_p, C.c_ulonglong]),
+    "srb_unpin_host": (C.c_int, [C.c_void_p]),
+    "srb_stream": (C.c_void_p, [_ctx_p]),
+    "srb_dev_x": (C.c_void_p, [_ctx_p]),
+    "srb_dev_gradient": (C.c_void_p, [_ctx_p]),
+    "srb_synchronize": (C.c_int, [_ctx_p]),
+    "srb_get_timing": (C.c_int, [_ctx_p, C.c_void_p]),
+}
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("lr_height", C.c_int), ("lr_width", C.c_int), ("num_channels", C.c_int),
+                ("num_frames", C.c_int), ("scale", C.c_int), ("psf_size", C.c_int),
+                ("psf", _dp), ("shifts", _dp)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("last_eval_kernel_ms", C.c_double), ("last_eval_h2d_ms", C.c_double),
+                ("last_eval_d2h_ms", C.c_double), ("num_evals", C.c_ulonglong),
+                ("kernel_launches", C.c_ulonglong), ("algorithmic_bytes_per_eval", C.c_ulonglong)]
+
+
+class SrbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (_STATUS.get(status, status), message))
+        self.status = status
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load_library(rebuild=False):
+    """Loads (building first if needed) libsrb200.so.  Raises if it cannot be built or loaded --
+    the product never substitutes a CPU implementation."""
+    global _lib
+    if _lib is None or rebuild:
+        path = _build.build(force=rebuild) if (rebuild or not os.path.exists(_build.LIB)) else _build.LIB
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def device_count():
+    return load_library().srb_device_count()
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _host_ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t):
+    """Device pointer of a torch CUDA tensor (float64, contiguous) or a raw int address."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous() and t.element_size() == 8
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One srb_ctx: the image formation model A_k = D B M_k plus the observations of this rank's
+    frame shard, on one CUDA device."""
+
+    def __init__(self, lr_shape, scale, psf=None, shifts=None, device=0):
+        """lr_shape = (N, C, h, w); psf: K x K array or None; shifts: (N, 2) (dx, dy) or None."""
+        self._lib = load_library()
+        self._ctx = _ctx_p()
+        N, Cn, h, w = (int(v) for v in lr_shape)
+        self.N, self.C, self.h, self.w, self.scale = N, Cn, h, w, int(scale)
+        self.H, self.W = h * self.scale, w * self.scale
+        self.c0, self.c1 = 0, Cn
+        self._psf = None if psf is None else _f64(psf)
+        self._shifts = None if shifts is None else _f64(shifts).reshape(-1, 2)
+        if self._shifts is not None and len(self._shifts) != N:
+            raise SrbError(1, "need one (dx, dy) shift per frame")
+        desc = ModelDesc(h, w, Cn, N, self.scale, 0 if self._psf is None else self._psf.shape[0],
+                         None if self._psf is None else self._psf.ctypes.data_as(_dp),
+                         None if self._shifts is None else self._shifts.ctypes.data_as(_dp))
+        st = self._lib.srb_create(C.byref(desc), int(device), C.byref(self._ctx))
+        if st != 0:
+            msg = self._lib.srb_last_error(self._ctx).decode() if self._ctx else "allocation failed"
+            if self._ctx:
+                self._lib.srb_destroy(self._ctx)
+            self._ctx = None
+            raise SrbError(st, msg)
+
+    # -- life cycle
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.srb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st):
+        if st != 0:
+            raise SrbError(st, self._lib.srb_last_error(self._ctx).decode())
+
+    @property
+    def num_active(self):
+        return (self.c1 - self.c0) * self.H * self.W
+
+    # -- configuration
+    def set_observations(self, lr):
+        if hasattr(lr, "is_cuda"):
+            assert tuple(lr.shape) == (self.N, self.C, self.h, self.w)
+            self._check(self._lib.srb_set_observations_dev(self._ctx, _dev_ptr(lr)))
+            return
+        lr = _f64(lr)
+        assert lr.shape == (self.N, self.C, self.h, self.w), lr.shape
+        self._check(self._lib.srb_set_observations(self._ctx, _host_ptr(lr)))
+
+    def set_channel_range(self, c0, c1):
+        self._check(self._lib.srb_set_channel_range(self._ctx, int(c0), int(c1)))
+        self.c0, self.c1 = int(c0), int(c1)
+
+    def set_regularizer(self, kind, lam, btv_range=3, btv_decay=0.5):
+        self._check(self._lib.srb_set_regularizer(self._ctx, int(kind), float(lam), int(btv_range),
+                                                  float(btv_decay)))
+
+    def set_irls_weights(self, weights):
+        w = None if weights is None else _f64(weights).reshape(-1)
+        if w is not None:
+            assert w.size == self.num_active
+        self._check(self._lib.srb_set_irls_weights(self._ctx, _host_ptr(w)))
+
+    def reweight(self, x=None, want_weights=True):
+        xa = None if x is None else _f64(x).reshape(-1)
+        out = np.empty(self.num_active) if want_weights else None
+        self._check(self._lib.srb_reweight(self._ctx, _host_ptr(xa), _host_ptr(out)))
+        return None if out is None else out.reshape(self.c1 - self.c0, self.H, self.W)
+
+    def set_path(self, path):
+        self._check(self._lib.srb_set_path(self._ctx, int(path)))
+
+    @property
+    def active_path(self):
+        return self._lib.srb_active_path(self._ctx)
+
+    def set_regularizer_rows(self, r0, r1):
+        self._check(self._lib.srb_set_regularizer_rows(self._ctx, int(r0), int(r1)))
+
+    # -- hot path
+    def eval(self, x, want_grad=True, out=None):
+        """ObjectiveFunction::ComputeAllTerms with host buffers.  Returns (cost, gradient|None)."""
+        xa = _f64(x).reshape(-1)
+        assert xa.size == self.num_active
+        g = None
+        if want_grad:
+            g = out if out is not None else np.empty(self.num_active)
+        cost = C.c_double()
+        self._check(self._lib.srb_eval(self._ctx, _host_ptr(xa), _host_ptr(g), C.byref(cost)))
+        return cost.value, (None if g is None else g.reshape(self.c1 - self.c0, self.H, self.W))
+
+    def eval_dev(self, x_dev, g_dev=None, want_cost=True):
+        cost = C.c_double()
+        self._check(self._lib.srb_eval_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(g_dev),
+                                           C.byref(cost) if want_cost else None))
+        return cost.value if want_cost else None
+
+    def eval_partial_dev(self, x_dev, gc_dev):
+        self._check(self._lib.srb_eval_partial_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(gc_dev)))
+
+    def data_term(self, x, gradient=None):
+        """ObjectiveDataTerm::Compute: returns cost; ADDS into `gradient` (in place) if given."""
+        xa = _f64(x).reshape(-1)
+        if gradient is not None:
+            assert gradient.dtype == np.float64 and gradient.flags.c_contiguous
+        cost = C.c_double()
+        self._check(self._lib.srb_data_term(self._ctx, _host_ptr(xa), _host_ptr(gradient), C.byref(cost)))
+        return cost.value
+
+    def irls_term(self, x, gradient=None):
+        xa = _f64(x).reshape(-1)
+        if gradient is not None:
+            assert gradient.dtype == np.float64 and gradient.flags.c_contiguous
+        cost = C.c_double()
+        self._check(self._lib.srb_irls_term(self._ctx, _host_ptr(xa), _host_ptr(gradient), C.byref(cost)))
+        return cost.value
+
+    def reg_apply(self, x):
+        xa = _f64(x)
+        Cn = xa.shape[0]
+        out = np.empty_like(xa)
+        self._check(self._lib.srb_reg_apply(self._ctx, _host_ptr(xa), Cn, _host_ptr(out)))
+        return out
+
+    def reg_apply_diff(self, x, constants):
+        xa, ca = _f64(x), _f64(constants)
+        Cn = xa.shape[0]
+        v, p = np.empty_like(xa), np.empty_like(xa)
+        self._check(self._lib.srb_reg_apply_diff(self._ctx, _host_ptr(xa), _host_ptr(ca), Cn,
+                                                 _host_ptr(v), _host_ptr(p)))
+        return v, p
+
+    def forward(self, k, hr):
+        hr = _f64(hr)
+        H, W = hr.shape
+        f = 1.0 / float(self.scale)
+        out = np.empty((int(H * f), int(W * f)))
+        self._check(self._lib.srb_forward(self._ctx, int(k), _host_ptr(hr), H, W, _host_ptr(out)))
+        return out
+
+    def transpose(self, k, lr):
+        lr = _f64(lr)
+        h, w = lr.shape
+        out = np.empty((h * self.scale, w * self.scale))
+        self._check(self._lib.srb_transpose(self._ctx, int(k), _host_ptr(lr), h, w, _host_ptr(out)))
+        return out
+
+    # -- plumbing
+    def stream_handle(self):
+        return self._lib.srb_stream(self._ctx)
+
+    def dev_x_ptr(self):
+        return self._lib.srb_dev_x(self._ctx)
+
+    def dev_gradient_ptr(self):
+        return self._lib.srb_dev_gradient(self._ctx)
+
+    def synchronize(self):
+        self._check(self._lib.srb_synchronize(self._ctx))
+
+    def timing(self):
+        t = Timing()
+        self._check(self._lib.srb_get_timing(self._ctx, C.byref(t)))
+        return {name: getattr(t, name) for name, _ in Timing._fields_}
+
+
+def pin_host(array):
+    st = load_library().srb_pin_host(array.ctypes.data_as(C.c_void_p), array.nbytes)
+    if st != 0:
+        raise SrbError(st, "cudaHostRegister failed")
+
+
+def unpin_host(array):
+    load_library().srb_unpin_host(array.ctypes.data_as(C.c_void_p))
