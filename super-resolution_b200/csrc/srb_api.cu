@@ -124,42 +124,41 @@ srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, b
   SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_cost, 0, 4 * sizeof(double), c->stream));
   const bool do_reg = reg_term && reg_active(c) && c->reg_row1 > c->reg_row0;
 
-  if (resolve_path(c) == SRB_PATH_FUSED && data_term && !accumulate && (reg_term || !reg_active(c))) {
-    srb_status st = fused_eval(c, d_x, d_g, do_reg);
+  bool reg_done = false;
+  if (resolve_path(c) == SRB_PATH_FUSED && data_term && !accumulate) {
+    srb_status st = fused_eval(c, d_x, d_g, do_reg, &reg_done);
     if (st != SRB_OK) return st;
-  } else {
-    if (data_term) {
-      srb_status st = dev_alloc(c, &c->d_pooled, (size_t)G.N * G.Ct * c->p);
-      if (st != SRB_OK) return st;
-      const dim3 grid = grid2d(G.w, G.h, G.N * Ca);
-      const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
-      if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
-      k_forward_generic<1><<<grid, dim3(32, 8), 0, c->stream>>>(make_params(c, false), d_x, c->d_y,
-                                                               c->d_pooled, c->d_partial);
-      k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 0);
-      c->timing.kernel_launches += 2;
-      if (d_g) {
-        k_adjoint_generic<<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(
-            make_params(c, true), c->d_pooled, d_g, 2.0, accumulate ? 1 : 0);
-        c->timing.kernel_launches += 1;
-      }
-    } else if (d_g && !accumulate) {
-      SRB_CUDA_CHECK(c, cudaMemsetAsync(d_g, 0, c->n_active() * sizeof(double), c->stream));
+  } else if (data_term) {
+    srb_status st = dev_alloc(c, &c->d_pooled, (size_t)G.N * G.Ct * c->p);
+    if (st != SRB_OK) return st;
+    const dim3 grid = grid2d(G.w, G.h, G.N * Ca);
+    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
+    k_forward_generic<1><<<grid, dim3(32, 8), 0, c->stream>>>(make_params(c, false), d_x, c->d_y,
+                                                             c->d_pooled, c->d_partial);
+    k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 0);
+    c->timing.kernel_launches += 2;
+    if (d_g) {
+      k_adjoint_generic<<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(
+          make_params(c, true), c->d_pooled, d_g, 2.0, accumulate ? 1 : 0);
+      c->timing.kernel_launches += 1;
     }
-    if (do_reg) {
-      srb_status st = dev_alloc(c, &c->d_vals, (size_t)G.Ct * c->P);
-      if (st != SRB_OK) return st;
-      const RegParams R = make_reg_params(c, Ca);
-      k_reg_values<0><<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals);
-      const int rows = c->reg_row1 - c->reg_row0;
-      const dim3 grid = grid2d(G.W, rows, Ca);
-      const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
-      if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
-      k_reg_partials<1><<<grid, dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals, c->d_w, c->lambda,
-                                                            c->reg_row0, c->reg_row1, d_g, c->d_partial);
-      k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 1);
-      c->timing.kernel_launches += 3;
-    }
+  } else if (d_g && !accumulate) {
+    SRB_CUDA_CHECK(c, cudaMemsetAsync(d_g, 0, c->n_active() * sizeof(double), c->stream));
+  }
+  if (do_reg && !reg_done) {
+    srb_status st = dev_alloc(c, &c->d_vals, (size_t)G.Ct * c->P);
+    if (st != SRB_OK) return st;
+    const RegParams R = make_reg_params(c, Ca);
+    k_reg_values<0><<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals);
+    const int rows = c->reg_row1 - c->reg_row0;
+    const dim3 grid = grid2d(G.W, rows, Ca);
+    const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
+    if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
+    k_reg_partials<1><<<grid, dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals, c->d_w, c->lambda,
+                                                          c->reg_row0, c->reg_row1, d_g, c->d_partial);
+    k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 1);
+    c->timing.kernel_launches += 3;
   }
   k_finish_cost<<<1, 1, 0, c->stream>>>(c->d_cost, tail);
   c->timing.kernel_launches += 1;
@@ -430,7 +429,8 @@ srb_status srb_set_path(srb_ctx* c, int path) {
   if (path != SRB_PATH_AUTO && path != SRB_PATH_REFERENCE_ORDER && path != SRB_PATH_FUSED)
     return c->fail(SRB_ERR_INVALID, "unknown path");
   if (path == SRB_PATH_FUSED && !fused_supported(c))
-    return c->fail(SRB_ERR_INVALID, "the fused kernel does not cover this model (see srb_active_path)");
+    return c->fail(SRB_ERR_INVALID, std::string("the fused kernel does not cover this model: ") +
+                                        (fused_state(c) ? fused_state(c)->why : std::string("not initialised")));
   c->path = path;
   return SRB_OK;
 }

@@ -79,6 +79,7 @@ struct srb_ctx {
   double* d_w = nullptr;      // IRLS weights [Ct][H][W]
   int reg_row0 = 0, reg_row1 = 0;
   int path = SRB_PATH_AUTO;
+  void* fused = nullptr;  // srb::FusedState (srb_kernels_fused.cuh)
 
   // work buffers
   double* d_x = nullptr;      // [Ct*P]
