@@ -8,9 +8,9 @@
 #include <new>
 
 #include "srb_common.cuh"
-#include "srb_kernels_fused.cuh"
 #include "srb_kernels_generic.cuh"
 #include "srb_kernels_reg.cuh"
+#include "srb_kernels_tile.cuh"
 
 using namespace srb;
 
@@ -121,14 +121,21 @@ srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, b
   if (data_term && !c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   const Geometry& G = c->g;
   const int Ca = c->Ca();
-  SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_cost, 0, 4 * sizeof(double), c->stream));
   const bool do_reg = reg_term && reg_active(c) && c->reg_row1 > c->reg_row0;
 
   bool reg_done = false;
   if (resolve_path(c) == SRB_PATH_FUSED && data_term && !accumulate) {
-    srb_status st = fused_eval(c, d_x, d_g, do_reg, &reg_done);
+    // the tile kernel's finishing launch also closes the cost when nothing follows it
+    const bool last = !do_reg || c->reg_kind == SRB_REG_TV;
+    srb_status st = fused_eval(c, d_x, d_g, do_reg, last ? tail : nullptr, &reg_done);
     if (st != SRB_OK) return st;
+    if (last) {
+      SRB_CUDA_CHECK(c, cudaGetLastError());
+      c->timing.num_evals += 1;
+      return SRB_OK;
+    }
   } else if (data_term) {
+    SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_cost, 0, 4 * sizeof(double), c->stream));
     srb_status st = dev_alloc(c, &c->d_pooled, (size_t)G.N * G.Ct * c->p);
     if (st != SRB_OK) return st;
     const dim3 grid = grid2d(G.w, G.h, G.N * Ca);
@@ -143,8 +150,10 @@ srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, b
           make_params(c, true), c->d_pooled, d_g, 2.0, accumulate ? 1 : 0);
       c->timing.kernel_launches += 1;
     }
-  } else if (d_g && !accumulate) {
-    SRB_CUDA_CHECK(c, cudaMemsetAsync(d_g, 0, c->n_active() * sizeof(double), c->stream));
+  } else {
+    SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_cost, 0, 4 * sizeof(double), c->stream));
+    if (d_g && !accumulate)
+      SRB_CUDA_CHECK(c, cudaMemsetAsync(d_g, 0, c->n_active() * sizeof(double), c->stream));
   }
   if (do_reg && !reg_done) {
     srb_status st = dev_alloc(c, &c->d_vals, (size_t)G.Ct * c->P);
@@ -395,7 +404,6 @@ srb_status srb_set_regularizer(srb_ctx* c, int kind, double lambda, int btv_rang
   }
   c->reg_kind = kind;
   c->lambda = lambda;
-  fused_reg_changed(c);
   return reset_weights(c);
 }
 
@@ -430,7 +438,7 @@ srb_status srb_set_path(srb_ctx* c, int path) {
     return c->fail(SRB_ERR_INVALID, "unknown path");
   if (path == SRB_PATH_FUSED && !fused_supported(c))
     return c->fail(SRB_ERR_INVALID, std::string("the fused kernel does not cover this model: ") +
-                                        (fused_state(c) ? fused_state(c)->why : std::string("not initialised")));
+                                        (tile_state(c) ? tile_state(c)->why : std::string("not initialised")));
   c->path = path;
   return SRB_OK;
 }
