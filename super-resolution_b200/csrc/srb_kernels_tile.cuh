@@ -138,9 +138,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 }
 
 // sgn(g) * t with sgn(0) = 0 (tv_regularizer.cpp:152-201: the three-way branches on the sign of a
-// forward difference).
+// forward difference), on the integer pipes: the fp64 pipe is the scarce one in this kernel.
 __device__ __forceinline__ double signed_by(double g, double t) {
-  return g > 0.0 ? t : (g < 0.0 ? -t : 0.0);
+  const int ghi = __double2hiint(g), glo = __double2loint(g);
+  const bool nz = ((ghi & 0x7fffffff) | glo) != 0;
+  const int rhi = __double2hiint(t) ^ (ghi & 0x80000000);
+  return nz ? __hiloint2double(rhi, __double2loint(t)) : 0.0;
 }
 
 // Sums two values over the thread block; results valid in thread 0.
@@ -168,20 +171,49 @@ __device__ __forceinline__ int floordiv_scale(int a, int s, int sshift) {
   return sshift >= 0 ? (a >> sshift) : floordiv(a, s);
 }
 
-// Residual pass over the rows r = rho, rho + s, ... of column c of the Z region.  All these HR
-// pixels share one sub-pixel phase, hence one list [e0, e1) of (frame, tap) entries; going down
-// one row of the list's LR cells is one LR row (ycell += w).
+// Residual pass over the rows r = r_begin, r_begin + s, ... (< r_end) of column c of the Z region.
+// All these HR pixels share one sub-pixel phase, hence one list [e0, e1) of (frame, tap) entries;
+// going down one row of the list's LR cells is one LR row (ycell += w).
+//   EDGE: the tile touches the border band -- samples are range / band checked, and the cost of a
+//   sample whose transpose tap lies in the halo outside the image is owned by the border tile.
 template <int KH, bool FRAC, bool EDGE>
 __device__ __forceinline__ double tile_residuals(const TileParams& P, const double* __restrict__ bx,
                                                  double* __restrict__ zs, const TEntry* __restrict__ ents,
                                                  int e0, int e1, const double* __restrict__ ycell, int mr,
-                                                 int mc, int c, int rho, bool own_c) {
+                                                 int mc, int c, int r_begin, int r_end, bool own_c, int ty0) {
   using D = TileDims<KH, FRAC>;
   const int s = P.s;
   double cost = 0.0;
-#pragma unroll 2
-  for (int r = rho; r < D::ZH; r += s) {
-    const bool own = own_c && r >= KH && r < KH + FT_H;
+  if (!FRAC && !EDGE && e1 - e0 == 1) {
+    // the common case (one frame per sub-pixel phase): entry in registers, LR loads batched
+    const int4 head = *reinterpret_cast<const int4*>(ents + e0);
+    const double* __restrict__ yp = ycell + (((long long)head.y << 32) | (unsigned)head.x);
+    const double* __restrict__ bp = bx + c + head.z;
+    const int wstep = P.w;
+    constexpr int B = 5;
+    for (int r = r_begin; r < r_end; r += B * s) {
+      double obs[B];
+#pragma unroll
+      for (int j = 0; j < B; ++j) obs[j] = (r + j * s < r_end) ? __ldg(yp + (size_t)j * wstep) : 0.0;
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const int rr = r + j * s;
+        if (rr < r_end) {
+          const double res = bp[rr * D::BP] - obs[j];
+          zs[rr * D::ZP + c] = res;
+          if (own_c && rr >= KH && rr < KH + FT_H) cost = fma(res, res, cost);
+        }
+      }
+      yp += (size_t)B * wstep;
+    }
+    return cost;
+  }
+  for (int r = r_begin; r < r_end; r += s) {
+    bool own = own_c && r >= KH && r < KH + FT_H;
+    if (EDGE && own_c) {  // halo rows outside the image belong to the first / last tile row
+      const int pr = ty0 - KH + r;
+      own = own || (pr < 0 && ty0 == 0) || (pr >= P.H && ty0 + FT_H >= P.H);
+    }
     double z = 0.0;
 #pragma unroll 1
     for (int e = e0; e < e1; ++e) {
@@ -215,6 +247,54 @@ __device__ __forceinline__ double tile_residuals(const TileParams& P, const doub
   return cost;
 }
 
+// IRLS-weighted 2-D TV gradient + cost of this thread's EL pixels (column ec, rows er0..).
+//   BORDER: the tile touches the right / bottom image border or the edge of the regularizer row
+//   band, so neighbours and outputs are checked per pixel.
+template <int KH, bool FRAC, int EL, bool BORDER>
+__device__ __forceinline__ void tile_tv(const TileParams& P, const double* __restrict__ xs,
+                                        const double* __restrict__ ws, int ty0, int gc, int ec, int er0,
+                                        double (&tvg)[EL], double& cost_reg) {
+  using D = TileDims<KH, FRAC>;
+  const bool has_r = !BORDER || gc + 1 < P.W;
+  const double* __restrict__ xp = xs + (er0 + D::HX) * D::XW + (ec + D::HXC);
+  const double* __restrict__ wp = ws + (er0 + 1) * D::WW + (ec + 2);
+  const double tl2 = P.two_lambda;
+  double b_above;
+  {  // B of the pixel above the first row of this thread's segment
+    const double xa = xp[-D::XW], x0 = xp[0];
+    const double gya = x0 - xa;
+    const double gxa = has_r ? xp[-D::XW + 1] - xa : 0.0;
+    const double ta = (tl2 * wp[-D::WW]) * (fabs(gya) + fabs(gxa));
+    b_above = signed_by(gya, ta);
+  }
+  double x0 = xp[0], xl = xp[-1];
+  double cost = 0.0;
+#pragma unroll
+  for (int l = 0; l < EL; ++l) {
+    const int gr = ty0 + er0 + l;
+    const bool has_b = !BORDER || gr + 1 < P.H;
+    const double xr = xp[l * D::XW + 1];
+    const double xb = xp[(l + 1) * D::XW], xbl = xp[(l + 1) * D::XW - 1];
+    const double gx = has_r ? xr - x0 : 0.0;
+    const double gy = has_b ? xb - x0 : 0.0;
+    const double r = fabs(gy) + fabs(gx);
+    const double t = (tl2 * wp[l * D::WW]) * r;
+    const double a_own = signed_by(gx, t), b_own = signed_by(gy, t);
+    const double gxl = x0 - xl;
+    const double gyl = has_b ? xbl - xl : 0.0;
+    const double tl = (tl2 * wp[l * D::WW - 1]) * (fabs(gyl) + fabs(gxl));
+    const double a_left = signed_by(gxl, tl);
+    if (!BORDER || (gr >= P.row0 && gr < P.row1 && gr < P.H && gc < P.W)) {
+      tvg[l] = (a_left + b_above) - (a_own + b_own);
+      cost = fma(t, r, cost);  // 2 lambda w r^2; halved below
+    }
+    b_above = b_own;
+    x0 = xb;
+    xl = xbl;
+  }
+  cost_reg = 0.5 * cost;
+}
+
 template <int KH, bool FRAC>
 __global__ void __launch_bounds__(FT_NT, KH <= 3 ? 4 : 3)
 k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
@@ -238,24 +318,45 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
   const int ch = blockIdx.z;
   const size_t HW = (size_t)P.H * P.W;
+  const int s = P.s, sh = P.sshift;
+
+  // LR cells under the Z region of this tile, and whether all their samples are regular
+  const int mr_lo = floordiv_scale(ty0 - KH, s, sh), mr_hi = floordiv_scale(ty0 + FT_H + KH - 1, s, sh);
+  const int mc_lo = floordiv_scale(tx0 - KH, s, sh), mc_hi = floordiv_scale(tx0 + FT_W + KH - 1, s, sh);
+  const bool interior = mr_lo + P.qoff_min_r >= P.lo_r && mr_hi + P.qoff_max_r < P.hi_r &&
+                        mc_lo + P.qoff_min_c >= P.lo_c && mc_hi + P.qoff_max_c < P.hi_c &&
+                        ty0 - KH >= 0 && tx0 - KH >= 0 && ty0 + FT_H + KH <= P.H && tx0 + FT_W + KH <= P.W;
+  const double* __restrict__ ych = P.y + (size_t)(P.c0 + ch) * ((size_t)P.h * P.w);
 
   // ---- 0. stage the x tile + halo and the IRLS weights (zero outside the image) ------------------
   if (P.use_tma) {
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
     if (tid == 0) {
+      mbar_init(bar, 1);
       mbar_expect_tx(bar, D::X_BYTES + (P.reg_fused ? D::W_BYTES : 0u));
       tma_load_3d(xs, &map_x, tx0 - D::HXC, ty0 - D::HX, ch, bar);
       if (P.reg_fused) tma_load_3d(ws, &map_w, tx0 - 2, ty0 - 1, ch, bar);
     }
   }
   // phase table and entry list -> smem while the bulk copies are in flight
-  const int nph = P.s * P.s + 1;
+  const int nph = s * s + 1;
   for (int i = tid; i < nph; i += FT_NT) s_pb[i] = P.phase_begin[i];
   {
     const int4* src = reinterpret_cast<const int4*>(P.entries);
     int4* dst = reinterpret_cast<int4*>(s_ents);
     for (int i = tid; i < P.num_entries * 2; i += FT_NT) dst[i] = src[i];
+  }
+  __syncthreads();  // tables visible; mbarrier initialised before anyone waits on it
+  if (interior) {
+    // pull the LR rows this tile will read (one row segment per entry and LR cell row) into L2
+    const int ncr = mr_hi - mr_lo + 1;
+    const size_t row_bytes = (size_t)(mc_hi - mc_lo + 1) * sizeof(double);
+    for (int i = tid; i < P.num_entries * ncr; i += FT_NT) {
+      const int e = i / ncr, j = i - e * ncr;
+      const double* a = ych + s_ents[e].yoff + ((long long)(mr_lo + j) * P.w + mc_lo);
+      const size_t a0 = (size_t)a & ~(size_t)15;
+      const unsigned bytes = (unsigned)((((size_t)a + row_bytes + 15) & ~(size_t)15) - a0);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+    }
   }
   if (P.use_tma) {
     mbar_wait(bar, 0);
@@ -291,47 +392,16 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   static_assert(ESEG * FT_W == FT_NT && EL * ESEG == FT_H, "tile/thread shape");
   const int ec = tid % FT_W, er0 = (tid / FT_W) * EL;
   const int gc = tx0 + ec;
+  const bool tile_inside = tx0 + FT_W < P.W && ty0 + FT_H < P.H;  // strictly: right/bottom neighbours exist
   double tvg[EL];
   double cost_reg = 0.0;
 #pragma unroll
   for (int l = 0; l < EL; ++l) tvg[l] = 0.0;
   if (P.reg_fused) {
-    const bool has_r = gc + 1 < P.W;
-    const double* xp = xs + (er0 + D::HX) * D::XW + (ec + D::HXC);
-    const double* wp = ws + (er0 + 1) * D::WW + (ec + 2);
-    double b_above;
-    {  // B of the pixel above the first row of this thread's segment
-      const double xa = xp[-D::XW], x0 = xp[0];
-      const double gya = x0 - xa;
-      const double gxa = has_r ? xp[-D::XW + 1] - xa : 0.0;
-      const double ta = (P.two_lambda * wp[-D::WW]) * (fabs(gya) + fabs(gxa));
-      b_above = signed_by(gya, ta);
-    }
-    double x0 = xp[0], xl = xp[-1];
-#pragma unroll
-    for (int l = 0; l < EL; ++l) {
-      const int gr = ty0 + er0 + l;
-      const bool has_b = gr + 1 < P.H;
-      const double xr = xp[l * D::XW + 1];
-      const double xb = xp[(l + 1) * D::XW], xbl = xp[(l + 1) * D::XW - 1];
-      const double gx = has_r ? xr - x0 : 0.0;
-      const double gy = has_b ? xb - x0 : 0.0;
-      const double r = fabs(gy) + fabs(gx);
-      const double t = (P.two_lambda * wp[l * D::WW]) * r;
-      const double a_own = signed_by(gx, t), b_own = signed_by(gy, t);
-      const double gxl = x0 - xl;
-      const double gyl = has_b ? xbl - xl : 0.0;
-      const double tl = (P.two_lambda * wp[l * D::WW - 1]) * (fabs(gyl) + fabs(gxl));
-      const double a_left = signed_by(gxl, tl);
-      if (gr >= P.row0 && gr < P.row1 && gr < P.H && gc < P.W) {
-        tvg[l] = (a_left + b_above) - (a_own + b_own);
-        cost_reg = fma(t, r, cost_reg);  // 2 lambda w r^2; halved below
-      }
-      b_above = b_own;
-      x0 = xb;
-      xl = xbl;
-    }
-    cost_reg *= 0.5;
+    if (tile_inside && ty0 >= P.row0 && ty0 + FT_H <= P.row1)
+      tile_tv<KH, FRAC, EL, false>(P, xs, ws, ty0, gc, ec, er0, tvg, cost_reg);
+    else
+      tile_tv<KH, FRAC, EL, true>(P, xs, ws, ty0, gc, ec, er0, tvg, cost_reg);
     __syncthreads();  // ws (bufB) is overwritten by the vertical pass
   }
 
@@ -392,27 +462,40 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   __syncthreads();
 
   // ---- 3. residuals of the regular LR samples landing in the tile (+ halo), per HR pixel --------
-  //         work item = (column c of the Z region, row residue rho mod s): one sub-pixel phase.
+  //   pass A: the FT_W tile columns; work item = (column, row residue mod s) = one sub-pixel phase
+  //   pass B: the 2*KH halo columns, one (column, row) pixel per thread
   double cost_data = 0.0;
   {
-    const int s = P.s, sh = P.sshift;
-    const int mr_lo = floordiv_scale(ty0 - KH, s, sh), mr_hi = floordiv_scale(ty0 + FT_H + KH - 1, s, sh);
-    const int mc_lo = floordiv_scale(tx0 - KH, s, sh), mc_hi = floordiv_scale(tx0 + FT_W + KH - 1, s, sh);
-    const bool interior = mr_lo + P.qoff_min_r >= P.lo_r && mr_hi + P.qoff_max_r < P.hi_r &&
-                          mc_lo + P.qoff_min_c >= P.lo_c && mc_hi + P.qoff_max_c < P.hi_c;
-    const double* __restrict__ ych = P.y + (size_t)(P.c0 + ch) * ((size_t)P.h * P.w);
-    for (int id = tid; id < D::ZW * s; id += FT_NT) {
-      const int rho = id / D::ZW, c = id - rho * D::ZW;
+    for (int id = tid; id < FT_W * s; id += FT_NT) {
+      const int rho = id / FT_W, c = KH + (id - rho * FT_W);
       const int pc = tx0 - KH + c, pr = ty0 - KH + rho;
       const int mc = floordiv_scale(pc, s, sh), mr = floordiv_scale(pr, s, sh);
       const int phase = (pr - mr * s) * s + (pc - mc * s);
       const int e0 = s_pb[phase], e1 = s_pb[phase + 1];
-      const bool own_c = c >= KH && c < KH + FT_W;
       const double* ycell = ych + ((long long)mr * P.w + mc);
       if (interior)
-        cost_data += tile_residuals<KH, FRAC, false>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, rho, own_c);
+        cost_data += tile_residuals<KH, FRAC, false>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, rho, D::ZH, true, ty0);
       else
-        cost_data += tile_residuals<KH, FRAC, true>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, rho, own_c);
+        cost_data += tile_residuals<KH, FRAC, true>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, rho, D::ZH, true, ty0);
+    }
+    if (KH > 0) {
+      const bool first_col = tx0 == 0, last_col = tx0 + FT_W >= P.W;
+      for (int id = tid; id < 2 * KH * D::ZH; id += FT_NT) {
+        const int r = id / (2 * KH), hc = id - r * (2 * KH);
+        const int c = hc < KH ? hc : hc + FT_W;
+        const int pc = tx0 - KH + c, pr = ty0 - KH + r;
+        const int mc = floordiv_scale(pc, s, sh), mr = floordiv_scale(pr, s, sh);
+        const int phase = (pr - mr * s) * s + (pc - mc * s);
+        const int e0 = s_pb[phase], e1 = s_pb[phase + 1];
+        const double* ycell = ych + ((long long)mr * P.w + mc);
+        if (interior) {
+          cost_data += tile_residuals<KH, FRAC, false>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, r, r + 1, false, ty0);
+        } else {
+          // halo columns outside the image belong to the first / last tile column
+          const bool own_c = (pc < 0 && first_col) || (pc >= P.W && last_col);
+          cost_data += tile_residuals<KH, FRAC, true>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, r, r + 1, own_c, ty0);
+        }
+      }
     }
   }
   __syncthreads();
@@ -451,18 +534,18 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
       double win[K];
 #pragma unroll
       for (int i = 0; i < K - 1; ++i) win[i] = t2[(er0 + i) * D::T2P + ec];
-      double* __restrict__ gcn = P.g + (size_t)ch * HW;
+      double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
+      const bool all_in = tx0 + FT_W <= P.W && ty0 + FT_H <= P.H;
 #pragma unroll
       for (int l = 0; l < EL; ++l) {
         const int r = er0 + l;
-        const int gr = ty0 + r;
         win[K - 1] = t2[(r + K - 1) * D::T2P + ec];
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
 #pragma unroll
         for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
-        if (gr < P.H && gc < P.W) gcn[(size_t)gr * P.W + gc] = fma(P.two_s2, acc, tvg[l]);
+        if (all_in || (ty0 + r < P.H && gc < P.W)) gp[(size_t)l * P.W] = fma(P.two_s2, acc, tvg[l]);
       }
     }
   }
@@ -690,14 +773,14 @@ inline int pydiv(int a, int b) { return (a - pymod(a, b)) / b; }
 // Is LR sample q (one dimension; HR size L, half PSF width hk, scale s) "special" for a frame whose
 // quantised forward / transpose warps are n32 / t32 (1/32 px)?  Regular means: commuting the PSF
 // with the shift changes neither the LR prediction nor the back-projected gradient, and every
-// transpose tap lands inside the image.
+// transpose tap lands inside the image or in the Z halo (PSF half width) of a border tile.
 inline bool sample_is_special(int q, int L, int hk, int s, int n32, int t32) {
   const int n = n32 >> 5, fa = (n32 & 31) ? 1 : 0;
   const int nt = t32 >> 5, fb = (t32 & 31) ? 1 : 0;
   const int p0 = s * q;
   auto in = [L](int p) { return p >= 0 && p < L; };
   for (int b = 0; b <= fb; ++b)
-    if (!in(p0 - nt - b)) return true;
+    if (p0 - nt - b < -hk || p0 - nt - b >= L + hk) return true;  // beyond the Z halo of the border tiles
   for (int i = -hk; i <= hk; ++i) {
     if (in(p0 + i)) continue;
     for (int a = 0; a <= fa; ++a)
