@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "srb_common.cuh"
 #include "srb_kernels_generic.cuh"
@@ -49,7 +50,7 @@ struct __align__(16) TEntry {
 static_assert(sizeof(TEntry) == 32, "TEntry layout");
 
 struct TileParams {
-  int H, W, h, w, s, sshift, Ct, c0;  // sshift = log2(s) when s is a power of two, else -1
+  int H, W, h, w, s, sshift, Ct, c0, Ca;  // sshift = log2(s) when s is a power of two, else -1
   const double* x;
   const double* y;
   double* g;           // may be NULL (cost only)
@@ -70,8 +71,9 @@ struct TileParams {
   double* part_reg;    // per-CTA partial sums of the regularization cost
 };
 
-template <int KH, bool FRAC>
+template <int KH, bool FRAC, int TH>
 struct TileDims {
+  static constexpr int NT = TH * (FT_W / 8);      // threads per CTA: 8 pixels per thread
   static constexpr int K = 2 * KH + 1;
   static constexpr int HB = KH + (FRAC ? 1 : 0);  // halo of Bx around the tile
   static constexpr int HX = (KH + HB) > 0 ? (KH + HB) : 1;  // row halo of x around the tile (TV needs 1)
@@ -80,13 +82,13 @@ struct TileDims {
   static constexpr int HXC = (HX + 1) & ~1;
   static constexpr int XOR = HX - (KH + HB);      // xs rows the PSF passes skip
   static constexpr int XOC = HXC - (KH + HB);     // xs columns the PSF passes skip
-  static constexpr int XH = FT_H + 2 * HX, XW = FT_W + 2 * HXC;  // x tile, dense (TMA box)
+  static constexpr int XH = TH + 2 * HX, XW = FT_W + 2 * HXC;  // x tile, dense (TMA box)
   static constexpr int TW = FT_W + 2 * (KH + HB);                // vertical-pass output width
-  static constexpr int TR = FT_H + 2 * HB, TP = TW | 1;          // vertical-pass output
+  static constexpr int TR = TH + 2 * HB, TP = TW | 1;          // vertical-pass output
   static constexpr int BW = FT_W + 2 * HB, BP = BW | 1;          // Bx
-  static constexpr int ZH = FT_H + 2 * KH, ZW = FT_W + 2 * KH, ZP = ZW | 1;  // Z
+  static constexpr int ZH = TH + 2 * KH, ZW = FT_W + 2 * KH, ZP = ZW | 1;  // Z
   static constexpr int T2P = FT_W | 1;                           // adjoint horizontal pass
-  static constexpr int WH = FT_H + 1, WW = FT_W + 2;             // IRLS weights, dense (TMA box)
+  static constexpr int WH = TH + 1, WW = FT_W + 2;             // IRLS weights, dense (TMA box)
   static constexpr int cmax(int a, int b) { return a > b ? a : b; }
   static constexpr int A_DOUBLES = (cmax(cmax(XH * XW, TR * BP), ZH * T2P) + 15) & ~15;  // xs | bx | t2
   static constexpr int B_DOUBLES = (cmax(cmax(TR * TP, ZH * ZP), WH * WW) + 15) & ~15;   // ws | tmp | z
@@ -147,6 +149,7 @@ __device__ __forceinline__ double signed_by(double g, double t) {
 }
 
 // Sums two values over the thread block; results valid in thread 0.
+template <int NT>
 __device__ __forceinline__ void block_sum2(double& a, double& b) {
   __shared__ double part[2][32];
   const int tid = threadIdx.x;
@@ -159,8 +162,8 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
   }
   __syncthreads();
   if (wid == 0) {
-    a = (lane < FT_NT / 32) ? part[0][lane] : 0.0;
-    b = (lane < FT_NT / 32) ? part[1][lane] : 0.0;
+    a = (lane < NT / 32) ? part[0][lane] : 0.0;
+    b = (lane < NT / 32) ? part[1][lane] : 0.0;
     a = warp_sum(a);
     b = warp_sum(b);
   }
@@ -171,90 +174,52 @@ __device__ __forceinline__ int floordiv_scale(int a, int s, int sshift) {
   return sshift >= 0 ? (a >> sshift) : floordiv(a, s);
 }
 
-// Residual pass over the rows r = r_begin, r_begin + s, ... (< r_end) of column c of the Z region.
-// All these HR pixels share one sub-pixel phase, hence one list [e0, e1) of (frame, tap) entries;
-// going down one row of the list's LR cells is one LR row (ycell += w).
-//   EDGE: the tile touches the border band -- samples are range / band checked, and the cost of a
-//   sample whose transpose tap lies in the halo outside the image is owned by the border tile.
-template <int KH, bool FRAC, bool EDGE>
-__device__ __forceinline__ double tile_residuals(const TileParams& P, const double* __restrict__ bx,
-                                                 double* __restrict__ zs, const TEntry* __restrict__ ents,
-                                                 int e0, int e1, const double* __restrict__ ycell, int mr,
-                                                 int mc, int c, int r_begin, int r_end, bool own_c, int ty0) {
-  using D = TileDims<KH, FRAC>;
-  const int s = P.s;
-  double cost = 0.0;
-  if (!FRAC && !EDGE && e1 - e0 == 1) {
-    // the common case (one frame per sub-pixel phase): entry in registers, LR loads batched
-    const int4 head = *reinterpret_cast<const int4*>(ents + e0);
-    const double* __restrict__ yp = ycell + (((long long)head.y << 32) | (unsigned)head.x);
-    const double* __restrict__ bp = bx + c + head.z;
-    const int wstep = P.w;
-    constexpr int B = 5;
-    for (int r = r_begin; r < r_end; r += B * s) {
-      double obs[B];
-#pragma unroll
-      for (int j = 0; j < B; ++j) obs[j] = (r + j * s < r_end) ? __ldg(yp + (size_t)j * wstep) : 0.0;
-#pragma unroll
-      for (int j = 0; j < B; ++j) {
-        const int rr = r + j * s;
-        if (rr < r_end) {
-          const double res = bp[rr * D::BP] - obs[j];
-          zs[rr * D::ZP + c] = res;
-          if (own_c && rr >= KH && rr < KH + FT_H) cost = fma(res, res, cost);
-        }
-      }
-      yp += (size_t)B * wstep;
-    }
-    return cost;
-  }
-  for (int r = r_begin; r < r_end; r += s) {
-    bool own = own_c && r >= KH && r < KH + FT_H;
-    if (EDGE && own_c) {  // halo rows outside the image belong to the first / last tile row
-      const int pr = ty0 - KH + r;
-      own = own || (pr < 0 && ty0 == 0) || (pr >= P.H && ty0 + FT_H >= P.H);
-    }
-    double z = 0.0;
+// Residuals of the regular LR samples that land on ONE HR pixel of the Z region (row r, column c):
+// z = sum over the pixel's (frame, tap) entries [e0, e1) of wT * (Bx sample - observation).
+//   EDGE: the tile touches the border band -- samples are range / band checked.
+template <int KH, bool FRAC, int TH, bool EDGE>
+__device__ __forceinline__ double pixel_residuals(const TileParams& P, const double* __restrict__ bx,
+                                                  const TEntry* __restrict__ ents, int e0, int e1,
+                                                  const double* __restrict__ ycell, int mr, int mc, int r,
+                                                  int c, bool own, double& cost) {
+  using D = TileDims<KH, FRAC, TH>;
+  double z = 0.0;
 #pragma unroll 1
-    for (int e = e0; e < e1; ++e) {
-      const int4 head = *reinterpret_cast<const int4*>(ents + e);  // yoff, bxoff, qoff
-      const long long yoff = ((long long)head.y << 32) | (unsigned)head.x;
-      if (EDGE) {
-        const int qr = mr + (int)(short)(head.w & 0xffff), qc = mc + (head.w >> 16);
-        if (qr < P.lo_r || qr >= P.hi_r || qc < P.lo_c || qc >= P.hi_c) continue;
-      }
-      const double obs = __ldg(ycell + yoff);
-      const double* b = bx + r * D::BP + c + head.z;
-      if (!FRAC) {
-        const double res = b[0] - obs;
-        z += res;
-        if (own) cost = fma(res, res, cost);
-      } else {
-        const TEntry en = ents[e];
-        const double wy1 = en.fy * (1.0 / 32.0), wy0 = 1.0 - wy1;
-        const double wx1 = en.fx * (1.0 / 32.0), wx0 = 1.0 - wx1;
-        const double pred = b[0] * (wy0 * wx0) + b[1] * (wy0 * wx1) + b[D::BP] * (wy1 * wx0) +
-                            b[D::BP + 1] * (wy1 * wx1);
-        const double res = pred - obs;
-        z = fma(en.wT, res, z);
-        if (own && en.owner) cost = fma(res, res, cost);
-      }
+  for (int e = e0; e < e1; ++e) {
+    const int4 head = *reinterpret_cast<const int4*>(ents + e);  // yoff, bxoff, qoff
+    const long long yoff = ((long long)head.y << 32) | (unsigned)head.x;
+    if (EDGE) {
+      const int qr = mr + (int)(short)(head.w & 0xffff), qc = mc + (head.w >> 16);
+      if (qr < P.lo_r || qr >= P.hi_r || qc < P.lo_c || qc >= P.hi_c) continue;
     }
-    zs[r * D::ZP + c] = z;
-    ++mr;
-    ycell += P.w;
+    const double obs = __ldg(ycell + yoff);
+    const double* b = bx + r * D::BP + c + head.z;
+    if (!FRAC) {
+      const double res = b[0] - obs;
+      z += res;
+      if (own) cost = fma(res, res, cost);
+    } else {
+      const TEntry en = ents[e];
+      const double wy1 = en.fy * (1.0 / 32.0), wy0 = 1.0 - wy1;
+      const double wx1 = en.fx * (1.0 / 32.0), wx0 = 1.0 - wx1;
+      const double pred = b[0] * (wy0 * wx0) + b[1] * (wy0 * wx1) + b[D::BP] * (wy1 * wx0) +
+                          b[D::BP + 1] * (wy1 * wx1);
+      const double res = pred - obs;
+      z = fma(en.wT, res, z);
+      if (own && en.owner) cost = fma(res, res, cost);
+    }
   }
-  return cost;
+  return z;
 }
 
 // IRLS-weighted 2-D TV gradient + cost of this thread's EL pixels (column ec, rows er0..).
 //   BORDER: the tile touches the right / bottom image border or the edge of the regularizer row
 //   band, so neighbours and outputs are checked per pixel.
-template <int KH, bool FRAC, int EL, bool BORDER>
+template <int KH, bool FRAC, int TH, int EL, bool BORDER>
 __device__ __forceinline__ void tile_tv(const TileParams& P, const double* __restrict__ xs,
                                         const double* __restrict__ ws, int ty0, int gc, int ec, int er0,
                                         double (&tvg)[EL], double& cost_reg) {
-  using D = TileDims<KH, FRAC>;
+  using D = TileDims<KH, FRAC, TH>;
   const bool has_r = !BORDER || gc + 1 < P.W;
   const double* __restrict__ xp = xs + (er0 + D::HX) * D::XW + (ec + D::HXC);
   const double* __restrict__ wp = ws + (er0 + 1) * D::WW + (ec + 2);
@@ -295,12 +260,13 @@ __device__ __forceinline__ void tile_tv(const TileParams& P, const double* __res
   cost_reg = 0.5 * cost;
 }
 
-template <int KH, bool FRAC>
-__global__ void __launch_bounds__(FT_NT, KH <= 3 ? 4 : 3)
+template <int KH, bool FRAC, int TH>
+__global__ void __launch_bounds__(TH * (FT_W / 8), TH == 32 ? (KH <= 3 ? 4 : 3) : 2)
 k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
        const __grid_constant__ CUtensorMap map_w) {
-  using D = TileDims<KH, FRAC>;
+  using D = TileDims<KH, FRAC, TH>;
   constexpr int K = D::K;
+  constexpr int FT_H = TH, FT_NT = D::NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* bufA = reinterpret_cast<double*>(smem_raw);  // xs [XH][XW] -> bx [TR][BP] -> t2 [ZH][T2P]
   double* bufB = bufA + D::A_DOUBLES;                  // ws [WH][WW] -> tmp [TR][TP] -> z [ZH][ZP]
@@ -350,12 +316,14 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
     // pull the LR rows this tile will read (one row segment per entry and LR cell row) into L2
     const int ncr = mr_hi - mr_lo + 1;
     const size_t row_bytes = (size_t)(mc_hi - mc_lo + 1) * sizeof(double);
-    for (int i = tid; i < P.num_entries * ncr; i += FT_NT) {
-      const int e = i / ncr, j = i - e * ncr;
-      const double* a = ych + s_ents[e].yoff + ((long long)(mr_lo + j) * P.w + mc_lo);
-      const size_t a0 = (size_t)a & ~(size_t)15;
-      const unsigned bytes = (unsigned)((((size_t)a + row_bytes + 15) & ~(size_t)15) - a0);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+    const double* rowbase = ych + ((long long)mr_lo * P.w + mc_lo);
+    for (int j = tid & 63; j < ncr; j += 64) {
+      for (int e = tid >> 6; e < P.num_entries; e += FT_NT / 64) {
+        const double* a = rowbase + s_ents[e].yoff + (long long)j * P.w;
+        const size_t a0 = (size_t)a & ~(size_t)15;
+        const unsigned bytes = (unsigned)((((size_t)a + row_bytes + 15) & ~(size_t)15) - a0);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
+      }
     }
   }
   if (P.use_tma) {
@@ -399,9 +367,9 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   for (int l = 0; l < EL; ++l) tvg[l] = 0.0;
   if (P.reg_fused) {
     if (tile_inside && ty0 >= P.row0 && ty0 + FT_H <= P.row1)
-      tile_tv<KH, FRAC, EL, false>(P, xs, ws, ty0, gc, ec, er0, tvg, cost_reg);
+      tile_tv<KH, FRAC, TH, EL, false>(P, xs, ws, ty0, gc, ec, er0, tvg, cost_reg);
     else
-      tile_tv<KH, FRAC, EL, true>(P, xs, ws, ty0, gc, ec, er0, tvg, cost_reg);
+      tile_tv<KH, FRAC, TH, EL, true>(P, xs, ws, ty0, gc, ec, er0, tvg, cost_reg);
     __syncthreads();  // ws (bufB) is overwritten by the vertical pass
   }
 
@@ -462,39 +430,95 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   __syncthreads();
 
   // ---- 3. residuals of the regular LR samples landing in the tile (+ halo), per HR pixel --------
-  //   pass A: the FT_W tile columns; work item = (column, row residue mod s) = one sub-pixel phase
-  //   pass B: the 2*KH halo columns, one (column, row) pixel per thread
+  //   pass A: the FT_H x FT_W pixels the tile owns; work item = (column, row residue mod s) = one
+  //           sub-pixel phase, i.e. one entry list; walking down its rows walks down LR rows
+  //   pass B: the halo ring of the Z region (not owned unless outside the image), pixel by pixel
   double cost_data = 0.0;
   {
-    for (int id = tid; id < FT_W * s; id += FT_NT) {
-      const int rho = id / FT_W, c = KH + (id - rho * FT_W);
-      const int pc = tx0 - KH + c, pr = ty0 - KH + rho;
-      const int mc = floordiv_scale(pc, s, sh), mr = floordiv_scale(pr, s, sh);
+    constexpr int RB = 32;  // rows per work item block
+    for (int id = tid; id < FT_W * s * (FT_H / RB); id += FT_NT) {
+      const int blk = id / (FT_W * s), id2 = id - blk * (FT_W * s);
+      const int rho = blk * RB + id2 / FT_W, cm = id2 % FT_W;  // first tile row of the item, tile column
+      const int c = KH + cm;
+      const int pc = tx0 + cm, pr = ty0 + rho;
+      const int mc = floordiv_scale(pc, s, sh);
+      int mr = floordiv_scale(pr, s, sh);
       const int phase = (pr - mr * s) * s + (pc - mc * s);
       const int e0 = s_pb[phase], e1 = s_pb[phase + 1];
-      const double* ycell = ych + ((long long)mr * P.w + mc);
-      if (interior)
-        cost_data += tile_residuals<KH, FRAC, false>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, rho, D::ZH, true, ty0);
-      else
-        cost_data += tile_residuals<KH, FRAC, true>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, rho, D::ZH, true, ty0);
+      const double* __restrict__ ycell = ych + ((long long)mr * P.w + mc);
+      const int nj = floordiv_scale((blk + 1) * RB - rho + s - 1, s, sh);  // rows rho, rho + s, ... of the block
+      if (!FRAC && interior && e1 - e0 == 1) {
+        // the common case (one frame per sub-pixel phase): entry in registers, LR loads batched
+        const int4 head = *reinterpret_cast<const int4*>(s_ents + e0);
+        const double* __restrict__ yp = ycell + (((long long)head.y << 32) | (unsigned)head.x);
+        const double* __restrict__ bp = bx + (KH + rho) * D::BP + c + head.z;
+        double* __restrict__ zp = zs + (KH + rho) * D::ZP + c;
+        const int bstep = s * D::BP, zstep = s * D::ZP;
+        const size_t ystep = (size_t)P.w;
+        int j = 0;
+        for (; j + 4 <= nj; j += 4) {
+          const double o0 = __ldg(yp), o1 = __ldg(yp + ystep), o2 = __ldg(yp + 2 * ystep), o3 = __ldg(yp + 3 * ystep);
+          const double r0 = bp[0] - o0, r1 = bp[bstep] - o1, r2 = bp[2 * bstep] - o2, r3 = bp[3 * bstep] - o3;
+          zp[0] = r0; zp[zstep] = r1; zp[2 * zstep] = r2; zp[3 * zstep] = r3;
+          cost_data = fma(r0, r0, cost_data);
+          cost_data = fma(r1, r1, cost_data);
+          cost_data = fma(r2, r2, cost_data);
+          cost_data = fma(r3, r3, cost_data);
+          yp += 4 * ystep; bp += 4 * bstep; zp += 4 * zstep;
+        }
+        for (; j < nj; ++j) {
+          const double r0 = bp[0] - __ldg(yp);
+          zp[0] = r0;
+          cost_data = fma(r0, r0, cost_data);
+          yp += ystep; bp += bstep; zp += zstep;
+        }
+      } else {
+        for (int j = 0; j < nj; ++j) {
+          const int r = KH + rho + j * s;
+          double z;
+          if (interior) z = pixel_residuals<KH, FRAC, TH, false>(P, bx, s_ents, e0, e1, ycell, mr, mc, r, c, true, cost_data);
+          else z = pixel_residuals<KH, FRAC, TH, true>(P, bx, s_ents, e0, e1, ycell, mr, mc, r, c, true, cost_data);
+          zs[r * D::ZP + c] = z;
+          ++mr;
+          ycell += P.w;
+        }
+      }
     }
     if (KH > 0) {
+      constexpr int NROWRING = 2 * KH * D::ZW;           // top + bottom halo rows, full width
+      constexpr int NRING = NROWRING + FT_H * 2 * KH;    // + left / right halo columns of the tile rows
       const bool first_col = tx0 == 0, last_col = tx0 + FT_W >= P.W;
-      for (int id = tid; id < 2 * KH * D::ZH; id += FT_NT) {
-        const int r = id / (2 * KH), hc = id - r * (2 * KH);
-        const int c = hc < KH ? hc : hc + FT_W;
+      const bool first_row = ty0 == 0, last_row = ty0 + FT_H >= P.H;
+      for (int id = tid; id < NRING; id += FT_NT) {
+        int r, c;
+        if (id < NROWRING) {
+          const int rr = id / D::ZW;
+          c = id - rr * D::ZW;
+          r = rr < KH ? rr : rr + FT_H;
+        } else {
+          const int t = id - NROWRING;
+          const int rm = t / (2 * KH), hc = t - rm * (2 * KH);
+          r = KH + rm;
+          c = hc < KH ? hc : hc + FT_W;
+        }
         const int pc = tx0 - KH + c, pr = ty0 - KH + r;
         const int mc = floordiv_scale(pc, s, sh), mr = floordiv_scale(pr, s, sh);
         const int phase = (pr - mr * s) * s + (pc - mc * s);
         const int e0 = s_pb[phase], e1 = s_pb[phase + 1];
         const double* ycell = ych + ((long long)mr * P.w + mc);
-        if (interior) {
-          cost_data += tile_residuals<KH, FRAC, false>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, r, r + 1, false, ty0);
+        double z, dummy = 0.0;
+        if (!FRAC && interior && e1 - e0 == 1) {
+          const int4 head = *reinterpret_cast<const int4*>(s_ents + e0);
+          z = bx[r * D::BP + c + head.z] - __ldg(ycell + (((long long)head.y << 32) | (unsigned)head.x));
+        } else if (interior) {
+          z = pixel_residuals<KH, FRAC, TH, false>(P, bx, s_ents, e0, e1, ycell, mr, mc, r, c, false, dummy);
         } else {
-          // halo columns outside the image belong to the first / last tile column
-          const bool own_c = (pc < 0 && first_col) || (pc >= P.W && last_col);
-          cost_data += tile_residuals<KH, FRAC, true>(P, bx, zs, s_ents, e0, e1, ycell, mr, mc, c, r, r + 1, own_c, ty0);
+          // halo positions outside the image belong to the first / last tile row / column
+          const bool in_r = (r >= KH && r < KH + FT_H) || (pr < 0 && first_row) || (pr >= P.H && last_row);
+          const bool in_c = (c >= KH && c < KH + FT_W) || (pc < 0 && first_col) || (pc >= P.W && last_col);
+          z = pixel_residuals<KH, FRAC, TH, true>(P, bx, s_ents, e0, e1, ycell, mr, mc, r, c, in_r && in_c, cost_data);
         }
+        zs[r * D::ZP + c] = z;
       }
     }
   }
@@ -552,7 +576,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 
   // ---- cost partial sums (deterministic: fixed per-CTA slot, fixed-order final reduction) --------
   const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  block_sum2(cost_data, cost_reg);
+  block_sum2<FT_NT>(cost_data, cost_reg);
   if (tid == 0) {
     P.part_data[cta] = P.s2 * cost_data;
     P.part_reg[cta] = cost_reg;
@@ -726,6 +750,7 @@ struct TileState {
   bool has_band = false;
   double* d_pooled = nullptr;  // [N][Ct][band.count()]
   bool tma_ok = false;
+  int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
   std::string why;         // why the tile kernel does not cover this model
 };
@@ -909,6 +934,7 @@ inline srb_status fused_setup(srb_ctx* c) {
       (void)cudaGetLastError();
     st->tma_ok = st->encode != nullptr && (G.W % 2 == 0);  // global strides must be multiples of 16 B
   }
+  if (const char* e = getenv("SRB_TILE_H")) st->tile_h = atoi(e) == 64 ? 64 : 32;
   st->supported = true;
   return SRB_OK;
 }
@@ -932,9 +958,10 @@ inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* 
   return r == CUDA_SUCCESS;
 }
 
-template <int KH, bool FRAC>
-inline srb_status tile_launch(srb_ctx* c, TileParams& P, dim3 grid) {
-  using D = TileDims<KH, FRAC>;
+template <int KH, bool FRAC, int TH>
+inline srb_status tile_launch(srb_ctx* c, TileParams& P) {
+  using D = TileDims<KH, FRAC, TH>;
+  const dim3 grid((P.W + FT_W - 1) / FT_W, (P.H + TH - 1) / TH, P.Ca);
   const TileState* st = tile_state(c);
   CUtensorMap mx, mw;
   memset(&mx, 0, sizeof mx);
@@ -948,10 +975,10 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, dim3 grid) {
   const size_t smem = D::smem_bytes(P.num_entries);
   static size_t attr_set[64] = {};
   if (c->device >= 64 || attr_set[c->device] < smem) {
-    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = smem;
   }
-  k_tile<KH, FRAC><<<grid, FT_NT, smem, c->stream>>>(P, mx, mw);
+  k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
   return SRB_OK;
 }
 
@@ -964,7 +991,7 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
   const Geometry& G = c->g;
   const int Ca = c->Ca();
   TileParams P;
-  P.H = G.H; P.W = G.W; P.h = G.h; P.w = G.w; P.s = G.s; P.Ct = G.Ct; P.c0 = c->c0;
+  P.H = G.H; P.W = G.W; P.h = G.h; P.w = G.w; P.s = G.s; P.Ct = G.Ct; P.c0 = c->c0; P.Ca = Ca;
   P.sshift = -1;
   for (int b = 0; b < 4; ++b)
     if ((1 << b) == G.s) P.sshift = b;
@@ -980,7 +1007,9 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
   P.reg_fused = (do_reg && c->reg_kind == SRB_REG_TV) ? 1 : 0;
   P.row0 = c->reg_row0; P.row1 = c->reg_row1;
   *reg_done = P.reg_fused != 0;
-  const dim3 grid((G.W + FT_W - 1) / FT_W, (G.H + FT_H - 1) / FT_H, Ca);
+  // tile height: 64 rows (512 threads) trims the halo overhead but pays more at the barriers
+  int TH = (G.H >= 256 && G.W >= 256) ? st->tile_h : 32;
+  const dim3 grid((G.W + FT_W - 1) / FT_W, (G.H + TH - 1) / TH, Ca);
   const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
   const long long bcount = st->has_band ? st->band.count() : 0;
   const dim3 bgrid((unsigned)((bcount + 255) / 256), (unsigned)(G.N * Ca));
@@ -998,18 +1027,14 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
   P.part_data = c->d_partial;
   P.part_reg = c->d_partial + nblocks + nband;
   srb_status rc = SRB_OK;
-  const int key = st->KH * 2 + (st->frac ? 1 : 0);
+  const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
   switch (key) {
-    case 0: rc = tile_launch<0, false>(c, P, grid); break;
-    case 1: rc = tile_launch<0, true>(c, P, grid); break;
-    case 2: rc = tile_launch<1, false>(c, P, grid); break;
-    case 3: rc = tile_launch<1, true>(c, P, grid); break;
-    case 4: rc = tile_launch<2, false>(c, P, grid); break;
-    case 5: rc = tile_launch<2, true>(c, P, grid); break;
-    case 6: rc = tile_launch<3, false>(c, P, grid); break;
-    case 7: rc = tile_launch<3, true>(c, P, grid); break;
-    case 8: rc = tile_launch<4, false>(c, P, grid); break;
-    case 9: rc = tile_launch<4, true>(c, P, grid); break;
+#define SRB_TILE_CASE(KH_, FR_)                                                   \
+    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P); break; \
+    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P); break;
+    SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
+    SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
+#undef SRB_TILE_CASE
     default: return c->fail(SRB_ERR_STATE, "tile kernel: unsupported PSF size");
   }
   if (rc != SRB_OK) return rc;
