@@ -497,7 +497,8 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
           r = rr < KH ? rr : rr + FT_H;
         } else {
           const int t = id - NROWRING;
-          const int rm = t / (2 * KH), hc = t - rm * (2 * KH);
+          constexpr int HC = KH > 0 ? 2 * KH : 1;  // (the ring is empty when KH == 0)
+          const int rm = t / HC, hc = t - rm * HC;
           r = KH + rm;
           c = hc < KH ? hc : hc + FT_W;
         }
