@@ -12,14 +12,17 @@ Metric unit: HR px * frames * channels per second.
   value     device-resident evaluations (x, gradient, observations in HBM), CUDA-event timed
   e2e       the same evaluation through the C-ABI call a host solver makes (srb_eval): x copied
             from pinned host memory, gradient + cost copied back, every step
-  roofline  algorithmic bytes (8*C*P*(3 + N/s^2)) / device time of the evaluation's
-            kernels, against the measured HBM peak in MEASURED_PEAKS.json
+  roofline  algorithmic bytes (8*C*P*(3 + N/s^2)) / device time of the fused tile kernel
+            (CUDA events recorded by the library around its launch, on the launching stream), against
+            the measured HBM peak in MEASURED_PEAKS.json; `traffic` = DRAM bytes of one launch from
+            the committed ncu capture (profiles/traffic.json)
   cpu_baseline  the CPU reference path (oracle/_ref: the reference's objective/regularizer sources +
             the C restatement of its OpenCV-backed data term) on this box's host cores, bounded sample
 
 Multi-GPU (N > 1): frames are sharded over ranks (weak scaling: every rank holds `N_frames` frames
 of a N*N_frames stack), x is replicated, the regularizer is split by HR row bands, and ONE NCCL
-allreduce over C*P+1 doubles per step yields gradient and cost everywhere.
+allreduce over C*P+1 doubles per step yields gradient and cost everywhere; the allreduce is cut
+into contiguous slices that overlap the tile kernel's work on the following rows (sharding.py).
 """
 import argparse
 import importlib
@@ -43,13 +46,14 @@ UNIT = "HRpx*frames*ch/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--path", default="auto", choices=["auto", "reference_order", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=512, help="HR side of the CPU-baseline crop")
+    ap.add_argument("--cpu-sample", type=int, default=1024, help="HR side of the CPU-baseline crop")
+    ap.add_argument("--chunks", type=int, default=4, help="allreduce pipeline depth (N > 1)")
     return ap.parse_args()
 
 
@@ -174,6 +178,7 @@ def main():
     import torch.distributed as dist
     srb = importlib.import_module("super-resolution_b200")
     wl = importlib.import_module("super-resolution_b200.workloads")
+    sharding = importlib.import_module("super-resolution_b200.sharding")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,18 +193,17 @@ def main():
     cf = wl.CONFIGS[args.config]
     n_local = cf["N"]                       # weak scaling: every rank holds the config's N frames
     n_total = n_local * world
-    frames = list(range(rank * n_local, (rank + 1) * n_local))
+    frames = sharding.frame_shard(n_total, rank, world)
     H, W, C, s = cf["H"], cf["W"], cf["C"], cf["s"]
     shifts_all = wl.default_shifts(n_total, s)
     psf = wl.gaussian_psf(cf["K"], cf["sigma"])
 
     eng = srb.Engine((n_local, C, H // s, W // s), s, psf, shifts_all[frames], device=local_rank)
-    work = wl.make(args.config, forward=lambda k, plane: eng.forward(k - frames[0], plane),
+    work = wl.make(args.config, forward=lambda k, plane: eng.forward(frames.index(k), plane),
                    N=n_total, frames=frames)
     eng.set_observations(work["lr"])
     eng.set_regularizer(work["reg_kind"], work["lam"], work["btv_range"], work["btv_decay"])
-    band = (H + world - 1) // world
-    eng.set_regularizer_rows(min(H, rank * band), min(H, (rank + 1) * band))
+    eng.set_regularizer_rows(*sharding.row_band(H, rank, world))
     eng.set_path({"auto": srb.PATH_AUTO, "reference_order": srb.PATH_REFERENCE_ORDER,
                   "fused": srb.PATH_FUSED}[args.path])
     n = C * H * W
@@ -216,6 +220,8 @@ def main():
         dist.broadcast(x_dev, src=0)        # replicas of the same estimate
     h_x = torch.from_numpy(x0.copy()).pin_memory()
     h_g = torch.empty(n + 1, dtype=torch.float64).pin_memory()
+    objective = sharding.ShardedObjective(sharding.EngineEvaluator(eng), n, dist=dist if world > 1 else None,
+                                          num_chunks=args.chunks)
 
     def barrier():
         if world > 1:
@@ -223,9 +229,8 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        eng.eval_partial_dev(x_dev, gc_dev)
-        if world > 1:
-            dist.all_reduce(gc_dev)
+        # one evaluation of the full objective: per-rank partial + (N > 1) pipelined allreduce
+        objective.evaluate(x_dev, gc_dev).wait()
 
     def step_e2e():
         # the call a host solver makes: host x in, host gradient + cost out
@@ -235,19 +240,19 @@ def main():
         if rank == 0:
             x_dev.copy_(h_x, non_blocking=True)
         dist.broadcast(x_dev, src=0)
-        eng.eval_partial_dev(x_dev, gc_dev)
-        dist.all_reduce(gc_dev)
+        objective.evaluate(x_dev, gc_dev).wait()
         if rank == 0:
             h_g.copy_(gc_dev, non_blocking=True)
         stream.synchronize()
         return float(h_g[n]) if rank == 0 else 0.0
 
+    warmup = max(args.warmup, 3)
     with torch.cuda.stream(stream):
-        # ---- device-resident throughput ---------------------------------------------------------
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             step_resident()
         barrier()
         sampler = ClockSampler(local_rank) if rank == 0 else None
+        # ---- device-resident throughput: EXACTLY args.steps steps, barrier + sync on both sides ----
         launches0 = eng.timing()["kernel_launches"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -258,30 +263,35 @@ def main():
         ms_total = e0.elapsed_time(e1)
         launches = eng.timing()["kernel_launches"] - launches0
 
-        # ---- kernel-only time of one evaluation (events on the launching stream) ------------------
+        # ---- the dominant kernel alone: CUDA events recorded by the library around the tile kernel
+        #      launch, on the launching stream (srb_set_profiling) ----------------------------------
+        eng.set_profiling(True)
         kern_ms = []
-        ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(min(args.steps, 20)):
-            ke0.record(stream)
+        for _ in range(min(max(args.steps, 5), 50)):
             eng.eval_partial_dev(x_dev, gc_dev)
-            ke1.record(stream)
             stream.synchronize()
-            kern_ms.append(ke0.elapsed_time(ke1))
+            kern_ms.append(eng.timing()["last_main_kernel_ms"])
+        eng.set_profiling(False)
         kernel_ms = float(np.mean(kern_ms))
 
         # ---- end to end through the host-facing call ----------------------------------------------
         for _ in range(3):
             step_e2e()
         barrier()
-        e_steps = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
+        e_steps = max(3, min(args.steps, 20))
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for _ in range(e_steps):
             cost = step_e2e()
         f1.record(stream)
         barrier()
-        e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
+        e2e_ms = f0.elapsed_time(f1)
+        # keep the same step running until the clock sampler has seen >= ~1 s of load
+        t_end = time.perf_counter() + max(0.0, 1.2 - (ms_total + e2e_ms) * 1e-3)
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                step_resident()
+            stream.synchronize()
         clocks = sampler.stop() if sampler else None
 
     t = torch.tensor([ms_total, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
@@ -295,13 +305,15 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        path_name = {1: "reference_order", 2: "fused"}[eng.active_path]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cf["name"], "frames_per_gpu": n_local, "frames_total": n_total,
-                       "partition": "frame-shard + 1 NCCL allreduce(C*P+1 f64)" if world > 1 else "single GPU",
-                       "kernel_path": {1: "reference_order", 2: "fused"}[eng.active_path],
+                       "partition": ("frame shard + 1 allreduce(C*P+1 f64) per step, pipelined in %d slices"
+                                     % args.chunks) if world > 1 else "single GPU",
+                       "kernel_path": path_name,
                        "l2": "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % (alg_bytes / 1e6),
                        "cost_check": cost},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e_steps,
@@ -311,16 +323,17 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                         "kernel": "all kernels of one evaluation on this rank"},
+                         "kernel": "k_tile (fused tile kernel), one launch per evaluation"
+                                   if path_name == "fused" else "reference-order kernels"},
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
-                line["roofline"]["traffic"] = json.load(open(prof)).get(line["config"]["kernel_path"])
+                line["roofline"]["traffic"] = json.load(open(prof)).get(path_name)
             except Exception:
                 pass
         if not args.no_cpu_baseline and world == 1:
-            cores = 1
+            cores = os.cpu_count() or 1
             val, dt, desc, kind = cpu_reference_run(args.config, args.cpu_sample, 3, 1, cores)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": desc, "note": kind}

@@ -126,6 +126,23 @@ srb_status srb_eval_dev(srb_ctx* ctx, const double* x_dev, double* gradient_dev,
  * synchronisation -- ready for ONE allreduce(sum) over n+1 doubles. */
 srb_status srb_eval_partial_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev);
 
+/* Pipelined multi-GPU form.  The active gradient is cut, in memory order, into "units" of
+ * rows_per_unit HR rows of one channel (the last unit of a channel may be shorter).
+ * srb_eval_units_dev evaluates units [unit_begin, unit_end): it writes exactly those gradient rows
+ * of gradient_cost_dev (a contiguous range, see srb_unit_range) so the caller can start the
+ * allreduce of that slice on another stream while the next units are computed.  After the last
+ * unit, srb_eval_finish_dev adds what is not tiled (border-band samples, non-fused regularizers)
+ * and writes the rank's partial cost to gradient_cost_dev[n].  Needs the fused path
+ * (srb_active_path == SRB_PATH_FUSED); srb_num_units reports 1 unit when pipelining is not
+ * possible for the current configuration (then [0,1) is the whole evaluation). */
+srb_status srb_num_units(srb_ctx* ctx, int* num_units, int* rows_per_unit);
+/* Element range [*begin, *end) of the gradient covered by units [unit_begin, unit_end). */
+srb_status srb_unit_range(srb_ctx* ctx, int unit_begin, int unit_end, unsigned long long* begin,
+                          unsigned long long* end);
+srb_status srb_eval_units_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev,
+                              int unit_begin, int unit_end);
+srb_status srb_eval_finish_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev);
+
 /* ObjectiveDataTerm::Compute (objective_data_term.cpp:98-116): returns the data cost and ADDS the
  * data gradient into gradient_host (may be NULL). */
 srb_status srb_data_term(srb_ctx* ctx, const double* x_host, double* gradient_host_accum,
@@ -165,12 +182,17 @@ double* srb_dev_x(srb_ctx* ctx);         /* (c1-c0)*H*W estimate buffer */
 double* srb_dev_gradient(srb_ctx* ctx);  /* (c1-c0)*H*W + 1 gradient (+cost) buffer */
 srb_status srb_synchronize(srb_ctx* ctx);
 
+/* Records CUDA events around the dominant kernel of every evaluation (the fused tile kernel) so
+ * that srb_get_timing can report its device time; off by default. */
+srb_status srb_set_profiling(srb_ctx* ctx, int on);
+
 typedef struct {
   double last_eval_kernel_ms;   /* device time of the kernels of the last evaluation */
   double last_eval_h2d_ms, last_eval_d2h_ms;
   unsigned long long num_evals; /* evaluations so far */
   unsigned long long kernel_launches; /* CUDA kernels launched by this context so far */
   unsigned long long algorithmic_bytes_per_eval; /* 8*C*P*(2|3 + N/s^2) */
+  double last_main_kernel_ms;   /* device time of the last fused tile kernel launch (profiling on) */
 } srb_timing;
 srb_status srb_get_timing(srb_ctx* ctx, srb_timing* out);
 

@@ -71,6 +71,9 @@ def lib():
                                 C.c_int, C.c_double, C.c_double, C.POINTER(Options),
                                 C.POINTER(Callbacks), _dp, C.POINTER(Stats)]
         L.ref_solve.restype = C.c_int
+        L.ref_solve_fused.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_double,
+                                      C.POINTER(Options), _dp, C.POINTER(Stats)]
+        L.ref_solve_fused.restype = C.c_int
         _lib = L
     return _lib
 
@@ -136,5 +139,20 @@ def solve(model, lr, x0, reg_kind=-1, lam=0.0, btv_range=3, btv_decay=0.5, optio
                          btv_range, btv_decay, lam, C.byref(opt),
                          C.byref(callbacks) if callbacks is not None else None, _p(out),
                          C.byref(st))
+    assert rc == 0
+    return out, st
+
+
+def solve_fused(engine, x0, has_regularizer, lambda_sum, options=None):
+    """The reference's IRLS + ALGLIB loop with the B200 engine plugged in through the C++ adapters
+    of include/srb200_adapters.hpp (ref_shim.cpp: ref_solve_fused).  `engine` is a configured
+    super-resolution_b200 Engine (model, observations, regularizer).  Returns (result, Stats)."""
+    x0 = _f64(x0)
+    Cn, H, W = x0.shape
+    out = np.empty_like(x0)
+    st = Stats()
+    opt = options if options is not None else default_options()
+    rc = lib().ref_solve_fused(engine._ctx, Cn, H, W, _p(x0), 1 if has_regularizer else 0,
+                               float(lambda_sum), C.byref(opt), _p(out), C.byref(st))
     assert rc == 0
     return out, st

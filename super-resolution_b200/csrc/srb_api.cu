@@ -499,6 +499,84 @@ srb_status srb_eval_partial_dev(srb_ctx* c, const double* x_dev, double* gc_dev)
   return eval_core(c, x_dev, gc_dev, gc_dev + c->n_active(), true, true, false);
 }
 
+// ---- pipelined multi-GPU form -------------------------------------------------------------------
+static bool units_pipelined(const srb_ctx* c) {
+  // units need the tile kernel to be the only writer of the gradient: no border band, and a
+  // regularizer that is fused (2-D TV) or absent
+  const TileState* st = tile_state(c);
+  const bool reg_ok = !reg_active(c) || c->reg_kind == SRB_REG_TV;
+  return resolve_path(c) == SRB_PATH_FUSED && st && !st->has_band && reg_ok;
+}
+
+srb_status srb_num_units(srb_ctx* c, int* num_units, int* rows_per_unit) {
+  if (!c || !num_units) return SRB_ERR_INVALID;
+  if (units_pipelined(c)) {
+    *num_units = tile_rows_per_channel(c) * c->Ca();
+    if (rows_per_unit) *rows_per_unit = tile_height(c);
+  } else {
+    *num_units = 1;
+    if (rows_per_unit) *rows_per_unit = c->g.H * c->Ca();
+  }
+  return SRB_OK;
+}
+
+srb_status srb_unit_range(srb_ctx* c, int u0, int u1, unsigned long long* begin, unsigned long long* end) {
+  if (!c || !begin || !end) return SRB_ERR_INVALID;
+  int nu = 0;
+  srb_num_units(c, &nu, nullptr);
+  if (u0 < 0 || u1 > nu || u1 < u0) return c->fail(SRB_ERR_INVALID, "invalid unit range");
+  if (!units_pipelined(c)) {
+    *begin = 0;
+    *end = u1 > u0 ? c->n_active() : 0;
+    return SRB_OK;
+  }
+  const int tr = tile_rows_per_channel(c), TH = tile_height(c);
+  auto first_elem = [&](int u) -> unsigned long long {
+    const int ch = u / tr, t = u - ch * tr;
+    const int row = t * TH < c->g.H ? t * TH : c->g.H;
+    return (unsigned long long)ch * c->P + (unsigned long long)row * c->g.W;
+  };
+  *begin = first_elem(u0);
+  *end = first_elem(u1);
+  return SRB_OK;
+}
+
+srb_status srb_eval_units_dev(srb_ctx* c, const double* x_dev, double* gc_dev, int u0, int u1) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev || !gc_dev) return c->fail(SRB_ERR_INVALID, "null buffer");
+  if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
+  int nu = 0;
+  srb_num_units(c, &nu, nullptr);
+  if (u0 < 0 || u1 > nu || u1 <= u0) return c->fail(SRB_ERR_INVALID, "invalid unit range");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (!units_pipelined(c))  // single unit: the whole evaluation happens in srb_eval_finish_dev
+    return SRB_OK;
+  const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
+  bool reg_done = false;
+  srb_status st = fused_eval_units(c, x_dev, gc_dev, do_reg, u0, u1, &reg_done);
+  if (st != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  return SRB_OK;
+}
+
+srb_status srb_eval_finish_dev(srb_ctx* c, const double* x_dev, double* gc_dev) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev || !gc_dev) return c->fail(SRB_ERR_INVALID, "null buffer");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (!units_pipelined(c)) return eval_core(c, x_dev, gc_dev, gc_dev + c->n_active(), true, true, false);
+  srb_status st = fused_eval_finish(c, x_dev, gc_dev, gc_dev + c->n_active());
+  if (st != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  c->timing.num_evals += 1;
+  return SRB_OK;
+}
+
+srb_status srb_set_profiling(srb_ctx* c, int on) {
+  if (!c) return SRB_ERR_INVALID;
+  c->profiling = on != 0;
+  return SRB_OK;
+}
+
 static srb_status term_host(srb_ctx* c, const double* x_host, double* g_accum, double* cost, bool data) {
   if (!c) return SRB_ERR_INVALID;
   if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
@@ -660,6 +738,13 @@ srb_status srb_get_timing(srb_ctx* c, srb_timing* out) {
   const double nf = (double)c->g.N / ((double)c->g.s * c->g.s);
   c->timing.algorithmic_bytes_per_eval =
       (unsigned long long)(8.0 * (double)c->n_active() * ((reg_active(c) ? 3.0 : 2.0) + nf));
+  if (c->profiling) {
+    float ms = 0.f;
+    if (cudaEventQuery(c->ev[5]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess)
+      c->timing.last_main_kernel_ms = ms;
+    else
+      (void)cudaGetLastError();
+  }
   *out = c->timing;
   return SRB_OK;
 }

@@ -94,6 +94,7 @@ struct srb_ctx {
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool timing_valid = false;
+  bool profiling = false;  // record events around the dominant kernel (srb_set_profiling)
   srb_timing timing{};
   std::string err;
 

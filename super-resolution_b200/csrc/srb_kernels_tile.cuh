@@ -67,6 +67,7 @@ struct TileParams {
   int reg_fused;       // 1: 2-D TV term evaluated here
   int row0, row1;      // HR row band of the regularizer term on this rank
   int use_tma;
+  int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
 };
@@ -281,8 +282,10 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   double* t2 = bufA;
 
   const int tid = threadIdx.x;
-  const int tx0 = blockIdx.x * FT_W, ty0 = blockIdx.y * FT_H;
-  const int ch = blockIdx.z;
+  // blockIdx.y walks "units": (channel, tile row) pairs in memory order, from P.unit_begin
+  const int unit = P.unit_begin + blockIdx.y;
+  const int ch = unit / P.tile_rows;
+  const int tx0 = blockIdx.x * FT_W, ty0 = (unit - ch * P.tile_rows) * FT_H;
   const size_t HW = (size_t)P.H * P.W;
   const int s = P.s, sh = P.sshift;
 
@@ -576,7 +579,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   }
 
   // ---- cost partial sums (deterministic: fixed per-CTA slot, fixed-order final reduction) --------
-  const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const size_t cta = (size_t)unit * gridDim.x + blockIdx.x;
   block_sum2<FT_NT>(cost_data, cost_reg);
   if (tid == 0) {
     P.part_data[cta] = P.s2 * cost_data;
@@ -960,17 +963,17 @@ inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* 
 }
 
 template <int KH, bool FRAC, int TH>
-inline srb_status tile_launch(srb_ctx* c, TileParams& P) {
+inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   using D = TileDims<KH, FRAC, TH>;
-  const dim3 grid((P.W + FT_W - 1) / FT_W, (P.H + TH - 1) / TH, P.Ca);
+  const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
   const TileState* st = tile_state(c);
   CUtensorMap mx, mw;
   memset(&mx, 0, sizeof mx);
   memset(&mw, 0, sizeof mw);
   P.use_tma = 0;
   if (st->tma_ok) {
-    bool ok = make_plane_map(st, &mx, P.x, P.W, P.H, (int)grid.z, D::XW, D::XH);
-    if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, (int)grid.z, D::WW, D::WH);
+    bool ok = make_plane_map(st, &mx, P.x, P.W, P.H, P.Ca, D::XW, D::XH);
+    if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, P.Ca, D::WW, D::WH);
     P.use_tma = ok ? 1 : 0;
   }
   const size_t smem = D::smem_bytes(P.num_entries);
@@ -979,15 +982,41 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P) {
     SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = smem;
   }
+  if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
   k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
+  if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
   return SRB_OK;
 }
 
-// Data term (+ 2-D TV term when fused) for the active channel range.  Leaves the data cost in
-// d_cost[0], the fused regularization cost in d_cost[1] and their sum in d_cost[2] (and *tail);
-// returns whether the regularizer was handled here through *reg_done.
-inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, double* tail,
-                             bool* reg_done) {
+// Tile height the current model runs with, and the number of (channel, tile row) units.
+inline int tile_height(const srb_ctx* c) {
+  const TileState* st = tile_state(c);
+  return (c->g.H >= 256 && c->g.W >= 256) ? st->tile_h : 32;
+}
+inline int tile_rows_per_channel(const srb_ctx* c) {
+  const int TH = tile_height(c);
+  return (c->g.H + TH - 1) / TH;
+}
+
+struct TileLayout {  // cost-partial slots of one evaluation
+  size_t nblocks, nband;
+  dim3 bgrid;
+};
+inline TileLayout tile_layout(const srb_ctx* c) {
+  const TileState* st = tile_state(c);
+  const Geometry& G = c->g;
+  TileLayout L;
+  L.nblocks = (size_t)((G.W + FT_W - 1) / FT_W) * tile_rows_per_channel(c) * c->Ca();
+  const long long bcount = st->has_band ? st->band.count() : 0;
+  L.bgrid = dim3((unsigned)((bcount + 255) / 256), (unsigned)(G.N * c->Ca()));
+  L.nband = st->has_band ? (size_t)L.bgrid.x * L.bgrid.y : 0;
+  return L;
+}
+
+// Data term (+ 2-D TV term when fused) of the (channel, tile row) units [unit_begin, unit_end) of
+// the active channel range: writes their gradient rows and their cost partial sums.
+inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, int unit_begin,
+                                   int unit_end, bool* reg_done) {
   const TileState* st = tile_state(c);
   const Geometry& G = c->g;
   const int Ca = c->Ca();
@@ -1008,14 +1037,11 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
   P.reg_fused = (do_reg && c->reg_kind == SRB_REG_TV) ? 1 : 0;
   P.row0 = c->reg_row0; P.row1 = c->reg_row1;
   *reg_done = P.reg_fused != 0;
-  // tile height: 64 rows (512 threads) trims the halo overhead but pays more at the barriers
-  int TH = (G.H >= 256 && G.W >= 256) ? st->tile_h : 32;
-  const dim3 grid((G.W + FT_W - 1) / FT_W, (G.H + TH - 1) / TH, Ca);
-  const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
-  const long long bcount = st->has_band ? st->band.count() : 0;
-  const dim3 bgrid((unsigned)((bcount + 255) / 256), (unsigned)(G.N * Ca));
-  const size_t nband = st->has_band ? (size_t)bgrid.x * bgrid.y : 0;
-  const size_t need = 2 * nblocks + nband;
+  const int TH = tile_height(c);
+  P.tile_rows = tile_rows_per_channel(c);
+  P.unit_begin = unit_begin;
+  const TileLayout L = tile_layout(c);
+  const size_t need = 2 * L.nblocks + L.nband;
   if (need > c->partial_capacity) {
     if (c->d_partial) cudaFree(c->d_partial);
     c->d_partial = nullptr;
@@ -1026,13 +1052,13 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
   }
   // layout: [data partials of the tiles][data partials of the band][reg partials of the tiles]
   P.part_data = c->d_partial;
-  P.part_reg = c->d_partial + nblocks + nband;
+  P.part_reg = c->d_partial + L.nblocks + L.nband;
   srb_status rc = SRB_OK;
   const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
   switch (key) {
-#define SRB_TILE_CASE(KH_, FR_)                                                   \
-    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P); break; \
-    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P); break;
+#define SRB_TILE_CASE(KH_, FR_)                                                             \
+    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P, unit_end); break; \
+    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P, unit_end); break;
     SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
     SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
 #undef SRB_TILE_CASE
@@ -1040,14 +1066,25 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
   }
   if (rc != SRB_OK) return rc;
   c->timing.kernel_launches += 1;
+  return SRB_OK;
+}
+
+// After every unit has been evaluated: the border band (exact, reference order) and the cost.
+// Leaves the data cost in d_cost[0], the fused regularization cost in d_cost[1] and their sum in
+// d_cost[2] (and *tail).
+inline srb_status fused_eval_finish(srb_ctx* c, const double* d_x, double* d_g, double* tail) {
+  const TileState* st = tile_state(c);
+  const Geometry& G = c->g;
+  const int Ca = c->Ca();
+  const TileLayout L = tile_layout(c);
   if (st->has_band) {
     GenericParams GP;
     GP.H = G.H; GP.W = G.W; GP.h = G.h; GP.w = G.w; GP.s = G.s; GP.K = G.K; GP.hk = G.hk;
     GP.N = G.N; GP.Ca = Ca; GP.Ct = G.Ct; GP.c0 = c->c0;
     GP.src_r = c->d_src_r; GP.src_c = c->d_src_c; GP.psf = c->d_psf;
     GP.rowY = c->d_rowY_fwd; GP.nX = c->d_nX_fwd;
-    k_band_forward<<<bgrid, 256, 0, c->stream>>>(GP, st->band, d_x, c->d_y, st->d_pooled,
-                                                  c->d_partial + nblocks);
+    k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, d_x, c->d_y, st->d_pooled,
+                                                   c->d_partial + L.nblocks);
     c->timing.kernel_launches += 1;
     if (d_g) {
       GP.rowY = c->d_rowY_tr; GP.nX = c->d_nX_tr;
@@ -1056,9 +1093,18 @@ inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do
       c->timing.kernel_launches += 1;
     }
   }
-  k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks + nband, P.part_reg, nblocks, c->d_cost, tail);
+  k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, L.nblocks + L.nband,
+                                               c->d_partial + L.nblocks + L.nband, L.nblocks, c->d_cost, tail);
   c->timing.kernel_launches += 1;
   return SRB_OK;
+}
+
+inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, double* tail,
+                             bool* reg_done) {
+  const int units = tile_rows_per_channel(c) * c->Ca();
+  srb_status st = fused_eval_units(c, d_x, d_g, do_reg, 0, units, reg_done);
+  if (st != SRB_OK) return st;
+  return fused_eval_finish(c, d_x, d_g, tail);
 }
 
 }  // namespace srb

@@ -38,6 +38,11 @@ SIGNATURES = {
     "srb_eval": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_eval_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_eval_partial_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_num_units": (C.c_int, [_ctx_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "srb_unit_range": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "srb_eval_units_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "srb_eval_finish_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_set_profiling": (C.c_int, [_ctx_p, C.c_int]),
     "srb_data_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_irls_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_reg_apply": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -63,7 +68,8 @@ class ModelDesc(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("last_eval_kernel_ms", C.c_double), ("last_eval_h2d_ms", C.c_double),
                 ("last_eval_d2h_ms", C.c_double), ("num_evals", C.c_ulonglong),
-                ("kernel_launches", C.c_ulonglong), ("algorithmic_bytes_per_eval", C.c_ulonglong)]
+                ("kernel_launches", C.c_ulonglong), ("algorithmic_bytes_per_eval", C.c_ulonglong),
+                ("last_main_kernel_ms", C.c_double)]
 
 
 class SrbError(RuntimeError):
@@ -229,6 +235,27 @@ class Engine:
 
     def eval_partial_dev(self, x_dev, gc_dev):
         self._check(self._lib.srb_eval_partial_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(gc_dev)))
+
+    # -- pipelined multi-GPU form
+    def num_units(self):
+        """(number of units, HR rows per unit) -- see srb_num_units."""
+        n, r = C.c_int(), C.c_int()
+        self._check(self._lib.srb_num_units(self._ctx, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def unit_range(self, u0, u1):
+        b, e = C.c_ulonglong(), C.c_ulonglong()
+        self._check(self._lib.srb_unit_range(self._ctx, int(u0), int(u1), C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def eval_units_dev(self, x_dev, gc_dev, u0, u1):
+        self._check(self._lib.srb_eval_units_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(gc_dev), int(u0), int(u1)))
+
+    def eval_finish_dev(self, x_dev, gc_dev):
+        self._check(self._lib.srb_eval_finish_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(gc_dev)))
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.srb_set_profiling(self._ctx, 1 if on else 0))
 
     def data_term(self, x, gradient=None):
         """ObjectiveDataTerm::Compute: returns cost; ADDS into `gradient` (in place) if given."""

@@ -1,0 +1,102 @@
+"""Multi-GPU frame sharding of the MAP objective, one process per GPU.
+
+The data term is a sum over LR frames (objective_data_term.cpp:104-114), so rank r of G holds the
+frames {k : k mod G == r} and their observations; the estimate x and the IRLS weights are
+replicated; the regularization term is split by HR row bands so that the sum over ranks is the
+full objective.  ONE allreduce(sum) over C*P + 1 doubles (gradient, cost in the last slot) per
+evaluation gives gradient and cost on every rank.
+
+The allreduce is pipelined against the computation: the gradient is produced in contiguous
+"units" (srb_eval_units_dev), and the slice of the units already computed is reduced over
+NVLink (NCCL, its own stream) while the tile kernel works on the next ones.
+
+`ShardedObjective` only needs an evaluator with the four methods of `EngineEvaluator`; the CPU
+tests drive it with an oracle-backed evaluator over gloo (world_size 2).
+"""
+import numpy as np
+
+
+def frame_shard(num_frames, rank, world):
+    """Frame indices owned by `rank` (round robin)."""
+    return [k for k in range(num_frames) if k % world == rank]
+
+
+def row_band(H, rank, world):
+    """HR row band [r0, r1) whose regularization term `rank` evaluates."""
+    band = (H + world - 1) // world
+    return min(H, rank * band), min(H, (rank + 1) * band)
+
+
+def chunk_bounds(num_units, num_chunks):
+    """Splits units [0, num_units) into at most num_chunks contiguous, near-equal chunks."""
+    num_chunks = max(1, min(int(num_chunks), int(num_units)))
+    edges = [(i * num_units) // num_chunks for i in range(num_chunks + 1)]
+    return [(edges[i], edges[i + 1]) for i in range(num_chunks) if edges[i + 1] > edges[i]]
+
+
+class EngineEvaluator:
+    """Adapter of one `Engine` (one rank's srb_ctx) to the evaluator protocol."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def num_units(self):
+        return self.e.num_units()[0]
+
+    def unit_range(self, u0, u1):
+        return self.e.unit_range(u0, u1)
+
+    def eval_units(self, x, gc, u0, u1):
+        self.e.eval_units_dev(x, gc, u0, u1)
+
+    def eval_finish(self, x, gc):
+        self.e.eval_finish_dev(x, gc)
+
+
+class ShardedObjective:
+    """cost + gradient of the full objective from per-rank partial evaluations.
+
+    evaluate(x, gc): x is the replicated estimate, gc a buffer of n + 1 doubles; on return (after
+    `wait()`, or immediately for synchronous backends) gc[:n] is the full gradient and gc[n] the
+    full cost on every rank.
+    """
+
+    def __init__(self, evaluator, n, dist=None, group=None, num_chunks=4):
+        self.ev = evaluator
+        self.n = int(n)
+        self.dist = dist            # torch.distributed (None or world size 1: no collective)
+        self.group = group
+        self.num_chunks = num_chunks
+        self._pending = []
+
+    def _world(self):
+        if self.dist is None or not self.dist.is_initialized():
+            return 1
+        return self.dist.get_world_size(self.group)
+
+    def evaluate(self, x, gc):
+        world = self._world()
+        chunks = chunk_bounds(self.ev.num_units(), self.num_chunks if world > 1 else 1)
+        self._pending = []
+        for i, (u0, u1) in enumerate(chunks):
+            self.ev.eval_units(x, gc, u0, u1)
+            last = i == len(chunks) - 1
+            if last:
+                self.ev.eval_finish(x, gc)
+            if world > 1:
+                b, e = self.ev.unit_range(u0, u1)
+                if last:
+                    e = self.n + 1      # the cost slot rides with the last slice
+                work = self.dist.all_reduce(gc[b:e], group=self.group, async_op=True)
+                self._pending.append(work)
+        return self
+
+    def wait(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+
+
+def reduce_reference(partials):
+    """What the collective computes: elementwise sum of the ranks' (gradient, cost) buffers."""
+    return np.sum(np.stack(partials, axis=0), axis=0)

@@ -1,0 +1,84 @@
+"""Worker of tests/test_sharding.py: one rank of a world_size-2 gloo group evaluating its frame
+shard + regularizer row band with the CPU oracle behind `ShardedObjective` (the same host logic
+bench.py runs over NCCL with the CUDA engine).  Writes its result to argv[3]."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import sr_oracle as o  # noqa: E402
+
+sharding = importlib.import_module("super-resolution_b200.sharding")
+
+
+class OracleEvaluator:
+    """Evaluator protocol on top of the CPU oracle: units are HR row groups of one channel."""
+
+    def __init__(self, model, lr, reg_kind, lam, wts, rows, rows_per_unit):
+        self.m, self.kind, self.lam, self.wts, self.rows = model, reg_kind, lam, wts, rows
+        self.obs = o.upsample_observations(model, lr)
+        self.C, self.H, self.W = wts.shape
+        self.rpu = rows_per_unit
+        self.tr = (self.H + rows_per_unit - 1) // rows_per_unit
+        self._g = None
+
+    def num_units(self):
+        return self.C * self.tr
+
+    def _first(self, u):
+        ch, t = divmod(u, self.tr)
+        return ch * self.H * self.W + min(t * self.rpu, self.H) * self.W
+
+    def unit_range(self, u0, u1):
+        return self._first(u0), self._first(u1)
+
+    def _partial(self, x):
+        xs = x.numpy().reshape(self.C, self.H, self.W)
+        f, g = o.evaluate(self.m, xs, self.obs, self.kind, 0.0, None)
+        vals, parts = o.reg_apply_diff(self.kind, xs, self.lam * self.wts)
+        r0, r1 = self.rows
+        g[:, r0:r1] += parts[:, r0:r1]
+        f += float(np.sum(self.lam * self.wts[:, r0:r1] * vals[:, r0:r1] ** 2))
+        return f, g.reshape(-1)
+
+    def eval_units(self, x, gc, u0, u1):
+        if self._g is None:
+            self._f, self._g = self._partial(x)
+        b, e = self.unit_range(u0, u1)
+        gc[b:e] = torch.from_numpy(self._g[b:e])
+
+    def eval_finish(self, x, gc):
+        gc[-1] = self._f
+        self._g = None
+
+
+def main():
+    rank, world, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    C, h, w, s, K, N = 2, 12, 10, 2, 3, 5
+    psf = o.gaussian_psf(K, 1.0)
+    shifts = rng.integers(-2, 3, size=(N, 2)).astype(np.float64)
+    x = rng.random((C, h * s, w * s))
+    lr = rng.random((N, C, h, w))
+    wts = 0.5 + rng.random(x.shape)
+    frames = sharding.frame_shard(N, rank, world)
+    rows = sharding.row_band(h * s, rank, world)
+    model = o.Model(s, psf, shifts[frames])
+    ev = OracleEvaluator(model, lr[frames], o.REG_TV, 0.02, wts, rows, rows_per_unit=5)
+    n = x.size
+    gc = torch.zeros(n + 1, dtype=torch.float64)
+    obj = sharding.ShardedObjective(ev, n, dist=dist, num_chunks=3)
+    obj.evaluate(torch.from_numpy(x.reshape(-1).copy()), gc).wait()
+    np.save(out, gc.numpy())
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
