@@ -187,7 +187,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL kernels on a high-priority stream: they must be able to start while the tile kernel
+        # of the following gradient slice still fills the SMs
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=os.environ.get("SRB_NCCL_PRIO", "1") == "1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
 
     cf = wl.CONFIGS[args.config]
@@ -286,18 +289,18 @@ def main():
         f1.record(stream)
         barrier()
         e2e_ms = f0.elapsed_time(f1)
-        # keep the same step running until the clock sampler has seen >= ~1 s of load
-        t_end = time.perf_counter() + max(0.0, 1.2 - (ms_total + e2e_ms) * 1e-3)
-        while time.perf_counter() < t_end:
-            for _ in range(20):
-                step_resident()
-            stream.synchronize()
-        clocks = sampler.stop() if sampler else None
-
     t = torch.tensor([ms_total, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms, kernel_ms = (float(v) for v in t.cpu())
+    # keep the same step running until the clock sampler has seen >= ~1 s of load; the number of
+    # extra steps is derived from the rank-reduced timings so that every rank runs the same count
+    extra = int(max(0.0, 1.2 - (ms_total + e2e_ms) * 1e-3) / max(ms_total / args.steps * 1e-3, 1e-6))
+    with torch.cuda.stream(stream):
+        for _ in range(min(extra, 20000)):
+            step_resident()
+        barrier()
+    clocks = sampler.stop() if sampler else None
     ms_per_step = ms_total / args.steps
     value = units / (ms_per_step * 1e-3)
     e2e_value = units / (e2e_ms / e_steps * 1e-3)

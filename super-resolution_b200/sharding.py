@@ -68,15 +68,35 @@ class ShardedObjective:
         self.group = group
         self.num_chunks = num_chunks
         self._pending = []
+        self._agreed_units = None
 
     def _world(self):
         if self.dist is None or not self.dist.is_initialized():
             return 1
         return self.dist.get_world_size(self.group)
 
+    def _units(self, gc):
+        """Number of units every rank cuts its gradient into.  Ranks must issue the SAME sequence of
+        collectives, but whether a rank can pipeline depends on its own frames (a shift beyond the
+        PSF half width puts border-band samples on that rank only): agree once on the minimum;
+        1 means "no pipelining anywhere"."""
+        mine = self.ev.num_units()
+        if self._world() == 1:
+            return mine
+        if self._agreed_units is None:
+            import torch
+            t = torch.tensor([mine, -mine], dtype=torch.int64, device=gc.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+            lo, hi = int(t[0]), -int(t[1])
+            self._agreed_units = lo if lo == hi else 1
+        return self._agreed_units if self._agreed_units == mine else 1
+
     def evaluate(self, x, gc):
         world = self._world()
-        chunks = chunk_bounds(self.ev.num_units(), self.num_chunks if world > 1 else 1)
+        units = self._units(gc)
+        chunks = chunk_bounds(units, self.num_chunks if world > 1 else 1)
+        if units == 1 and self.ev.num_units() != 1:
+            chunks = [(0, self.ev.num_units())]   # this rank could pipeline, another cannot
         self._pending = []
         for i, (u0, u1) in enumerate(chunks):
             self.ev.eval_units(x, gc, u0, u1)

@@ -25,12 +25,15 @@ class OracleEvaluator:
         self.C, self.H, self.W = wts.shape
         self.rpu = rows_per_unit
         self.tr = (self.H + rows_per_unit - 1) // rows_per_unit
+        self.single = rows_per_unit >= self.H * self.C
         self._g = None
 
     def num_units(self):
-        return self.C * self.tr
+        return 1 if self.single else self.C * self.tr
 
     def _first(self, u):
+        if self.single:
+            return u * self.C * self.H * self.W
         ch, t = divmod(u, self.tr)
         return ch * self.H * self.W + min(t * self.rpu, self.H) * self.W
 
@@ -71,7 +74,9 @@ def main():
     frames = sharding.frame_shard(N, rank, world)
     rows = sharding.row_band(h * s, rank, world)
     model = o.Model(s, psf, shifts[frames])
-    ev = OracleEvaluator(model, lr[frames], o.REG_TV, 0.02, wts, rows, rows_per_unit=5)
+    # SRB_TEST_MIXED=1: rank 1 cannot pipeline (one unit = everything), rank 0 can
+    rpu = 10 ** 6 if (os.environ.get("SRB_TEST_MIXED") == "1" and rank == 1) else 5
+    ev = OracleEvaluator(model, lr[frames], o.REG_TV, 0.02, wts, rows, rows_per_unit=rpu)
     n = x.size
     gc = torch.zeros(n + 1, dtype=torch.float64)
     obj = sharding.ShardedObjective(ev, n, dist=dist, num_chunks=3)

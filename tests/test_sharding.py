@@ -35,9 +35,15 @@ def _free_port():
     return p
 
 
-def test_world2_gloo_sharded_objective_equals_full(tmp_path, oracle):
+import pytest
+
+
+@pytest.mark.parametrize("mixed", ["0", "1"])
+def test_world2_gloo_sharded_objective_equals_full(tmp_path, oracle, mixed):
+    """mixed = 1: one rank reports a single unit (cannot pipeline) -- all ranks must then agree on one
+    collective per evaluation."""
     o = oracle
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), SRB_TEST_MIXED=mixed)
     outs = [str(tmp_path / ("rank%d.npy" % r)) for r in range(2)]
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_sharding_worker.py"),
                                str(r), "2", outs[r]], env=env) for r in range(2)]
