@@ -266,6 +266,7 @@ srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
   if (device < 0 || device >= ndev) return c->fail(SRB_ERR_INVALID, "invalid CUDA device index");
   c->device = device;
   SRB_CUDA_CHECK(c, cudaSetDevice(device));
+  SRB_CUDA_CHECK(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   SRB_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) SRB_CUDA_CHECK(c, cudaEventCreate(&e));
 

@@ -51,6 +51,7 @@ struct GenericParams {
 
 struct srb_ctx {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   srb::Geometry g{};
   size_t P = 0, p = 0;  // HR / LR pixels per channel

@@ -49,6 +49,17 @@ struct __align__(16) TEntry {
 };
 static_assert(sizeof(TEntry) == 32, "TEntry layout");
 
+// Precomputed work item of the residual pass for interior tiles of models where every sub-pixel
+// phase holds exactly one (frame, tap) entry and the scale divides the tile size: everything that
+// does not depend on the tile (observation offset relative to the tile's first LR cell, Bx and Z
+// element) is resolved on the host.  Items [0, FT_W*s*(TH/32)) are the pass-A columns (first row
+// of the item), the rest the halo-ring pixels.
+struct __align__(16) TFast {
+  long long yrel;  // + (ty0/s)*w + tx0/s = observation index within the channel
+  int bxo;         // Bx element
+  int zo;          // Z element
+};
+
 struct TileParams {
   int H, W, h, w, s, sshift, Ct, c0, Ca;  // sshift = log2(s) when s is a power of two, else -1
   const double* x;
@@ -67,6 +78,7 @@ struct TileParams {
   int reg_fused;       // 1: 2-D TV term evaluated here
   int row0, row1;      // HR row band of the regularizer term on this rank
   int use_tma;
+  const TFast* fast;   // NULL: generic residual pass only
   int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
@@ -296,6 +308,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
                         mc_lo + P.qoff_min_c >= P.lo_c && mc_hi + P.qoff_max_c < P.hi_c &&
                         ty0 - KH >= 0 && tx0 - KH >= 0 && ty0 + FT_H + KH <= P.H && tx0 + FT_W + KH <= P.W;
   const double* __restrict__ ych = P.y + (size_t)(P.c0 + ch) * ((size_t)P.h * P.w);
+  const bool fastpath = !FRAC && interior && P.fast != nullptr;
 
   // ---- 0. stage the x tile + halo and the IRLS weights (zero outside the image) ------------------
   if (P.use_tma) {
@@ -315,20 +328,6 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
     for (int i = tid; i < P.num_entries * 2; i += FT_NT) dst[i] = src[i];
   }
   __syncthreads();  // tables visible; mbarrier initialised before anyone waits on it
-  if (interior) {
-    // pull the LR rows this tile will read (one row segment per entry and LR cell row) into L2
-    const int ncr = mr_hi - mr_lo + 1;
-    const size_t row_bytes = (size_t)(mc_hi - mc_lo + 1) * sizeof(double);
-    const double* rowbase = ych + ((long long)mr_lo * P.w + mc_lo);
-    for (int j = tid & 63; j < ncr; j += 64) {
-      for (int e = tid >> 6; e < P.num_entries; e += FT_NT / 64) {
-        const double* a = rowbase + s_ents[e].yoff + (long long)j * P.w;
-        const size_t a0 = (size_t)a & ~(size_t)15;
-        const unsigned bytes = (unsigned)((((size_t)a + row_bytes + 15) & ~(size_t)15) - a0);
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(bytes) : "memory");
-      }
-    }
-  }
   if (P.use_tma) {
     mbar_wait(bar, 0);
   } else {
@@ -437,7 +436,54 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   //           sub-pixel phase, i.e. one entry list; walking down its rows walks down LR rows
   //   pass B: the halo ring of the Z region (not owned unless outside the image), pixel by pixel
   double cost_data = 0.0;
-  {
+  if (fastpath) {
+    // interior tile of a one-entry-per-phase model: table-driven work items (see TFast)
+    const double* __restrict__ ytile = ych + ((long long)(ty0 >> sh) * P.w + (tx0 >> sh));
+    constexpr int NITEM_A_PER_S = FT_W * (FT_H / 32);
+    constexpr int NRING = 2 * KH * D::ZW + FT_H * 2 * KH;
+    const int nitem_a = NITEM_A_PER_S * s;
+    const int nj = 32 >> sh;  // rows of one pass-A item (s divides 32)
+    const int bstep = s * D::BP, zstep = s * D::ZP;
+    const size_t ystep = (size_t)P.w;
+    const int4* __restrict__ tab = reinterpret_cast<const int4*>(P.fast);
+    {
+      for (int id = tid; id < nitem_a; id += FT_NT) {
+        const int4 f = __ldg(tab + id);
+        const double* __restrict__ yp = ytile + (((long long)f.y << 32) | (unsigned)f.x);
+        const double* __restrict__ bp = bx + f.z;
+        double* __restrict__ zp = zs + f.w;
+        int j = 0;
+        for (; j + 8 <= nj; j += 8) {
+          double o[8], r[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] = __ldg(yp + t * ystep);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) r[t] = bp[t * bstep] - o[t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) zp[t * zstep] = r[t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) cost_data = fma(r[t], r[t], cost_data);
+          yp += 8 * ystep; bp += 8 * bstep; zp += 8 * zstep;
+        }
+        for (; j < nj; ++j) {
+          const double r0 = bp[0] - __ldg(yp);
+          zp[0] = r0;
+          cost_data = fma(r0, r0, cost_data);
+          yp += ystep; bp += bstep; zp += zstep;
+        }
+      }
+    }
+    // halo ring: two pixels per thread and iteration, both loads in flight before the first use
+    for (int id = tid; id < NRING; id += 2 * FT_NT) {
+      const int id2 = id + FT_NT;
+      const int4 f0 = __ldg(tab + nitem_a + id);
+      const int4 f1 = id2 < NRING ? __ldg(tab + nitem_a + id2) : f0;
+      const double o0 = __ldg(ytile + (((long long)f0.y << 32) | (unsigned)f0.x));
+      const double o1 = __ldg(ytile + (((long long)f1.y << 32) | (unsigned)f1.x));
+      zs[f0.w] = bx[f0.z] - o0;
+      if (id2 < NRING) zs[f1.w] = bx[f1.z] - o1;
+    }
+  } else {
     constexpr int RB = 32;  // rows per work item block
     for (int id = tid; id < FT_W * s * (FT_H / RB); id += FT_NT) {
       const int blk = id / (FT_W * s), id2 = id - blk * (FT_W * s);
@@ -459,6 +505,20 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
         const int bstep = s * D::BP, zstep = s * D::ZP;
         const size_t ystep = (size_t)P.w;
         int j = 0;
+#ifndef SRB_EXP_BATCH4
+        for (; j + 8 <= nj; j += 8) {
+          double o[8], r[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[t] = __ldg(yp + t * ystep);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) r[t] = bp[t * bstep] - o[t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) zp[t * zstep] = r[t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) cost_data = fma(r[t], r[t], cost_data);
+          yp += 8 * ystep; bp += 8 * bstep; zp += 8 * zstep;
+        }
+#endif
         for (; j + 4 <= nj; j += 4) {
           const double o0 = __ldg(yp), o1 = __ldg(yp + ystep), o2 = __ldg(yp + 2 * ystep), o3 = __ldg(yp + 3 * ystep);
           const double r0 = bp[0] - o0, r1 = bp[bstep] - o1, r2 = bp[2 * bstep] - o2, r3 = bp[3 * bstep] - o3;
@@ -563,17 +623,33 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
       for (int i = 0; i < K - 1; ++i) win[i] = t2[(er0 + i) * D::T2P + ec];
       double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
+      const size_t gstep = (size_t)P.W;
       const bool all_in = tx0 + FT_W <= P.W && ty0 + FT_H <= P.H;
+      if (all_in) {
 #pragma unroll
-      for (int l = 0; l < EL; ++l) {
-        const int r = er0 + l;
-        win[K - 1] = t2[(r + K - 1) * D::T2P + ec];
-        double acc = 0.0;
+        for (int l = 0; l < EL; ++l) {
+          win[K - 1] = t2[(er0 + l + K - 1) * D::T2P + ec];
+          double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
+          for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
 #pragma unroll
-        for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
-        if (all_in || (ty0 + r < P.H && gc < P.W)) gp[(size_t)l * P.W] = fma(P.two_s2, acc, tvg[l]);
+          for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
+          *gp = fma(P.two_s2, acc, tvg[l]);
+          gp += gstep;
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < EL; ++l) {
+          const int r = er0 + l;
+          win[K - 1] = t2[(r + K - 1) * D::T2P + ec];
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
+#pragma unroll
+          for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
+          if (ty0 + r < P.H && gc < P.W) *gp = fma(P.two_s2, acc, tvg[l]);
+          gp += gstep;
+        }
       }
     }
   }
@@ -753,6 +829,7 @@ struct TileState {
   BandGeom reach{};      // HR pixels the special samples can reach
   bool has_band = false;
   double* d_pooled = nullptr;  // [N][Ct][band.count()]
+  TFast* d_fast[2] = {nullptr, nullptr};  // tile height 32 / 64; NULL when the model does not qualify
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -772,6 +849,8 @@ inline void fused_teardown(srb_ctx* c) {
   if (st->d_entries) cudaFree(st->d_entries);
   if (st->d_phase_begin) cudaFree(st->d_phase_begin);
   if (st->d_pooled) cudaFree(st->d_pooled);
+  for (TFast* f : st->d_fast)
+    if (f) cudaFree(f);
   delete st;
   st = nullptr;
 }
@@ -927,6 +1006,37 @@ inline srb_status fused_setup(srb_ctx* c) {
       return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (border band residuals)");
   }
 
+  // ---- table-driven residual pass (TFast): integer shifts, one entry per phase, s | tile size ----
+  {
+    bool one_each = !st->frac && (32 % s == 0);
+    for (size_t ph = 0; one_each && ph < lists.size(); ++ph) one_each = lists[ph].size() == 1;
+    for (int v = 0; one_each && v < 2; ++v) {
+      const int TH = v == 0 ? 32 : 64;
+      const int ZW = FT_W + 2 * hk, ZP = ZW | 1;
+      std::vector<TFast> tab;
+      auto item = [&](int r, int c) {  // Z-region pixel (r, c): tile-relative HR position (r-hk, c-hk)
+        const int pr = r - hk, pc = c - hk;
+        const int dmr = pydiv(pr, s), dmc = pydiv(pc, s);
+        const TEntry& e = lists[(size_t)(pr - dmr * s) * s + (pc - dmc * s)][0];
+        TFast f;
+        f.yrel = e.yoff + (long long)dmr * G.w + dmc;
+        f.bxo = r * BP + c + e.bxoff;
+        f.zo = r * ZP + c;
+        tab.push_back(f);
+      };
+      for (int blk = 0; blk < TH / 32; ++blk)          // pass A: id = blk*(FT_W*s) + rho*FT_W + cm
+        for (int rho = 0; rho < s; ++rho)
+          for (int cm = 0; cm < FT_W; ++cm) item(hk + blk * 32 + rho, hk + cm);
+      for (int rr = 0; rr < 2 * hk; ++rr)             // ring: top + bottom halo rows, full width
+        for (int c = 0; c < ZW; ++c) item(rr < hk ? rr : rr + TH, c);
+      for (int rm = 0; rm < TH; ++rm)                 // ring: left / right halo columns
+        for (int hc = 0; hc < 2 * hk; ++hc) item(hk + rm, hc < hk ? hc : hc + FT_W);
+      if (cudaMalloc((void**)&st->d_fast[v], (tab.size() + 1) * sizeof(TFast)) != cudaSuccess)
+        return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
+      SRB_CUDA_CHECK(c, cudaMemcpy(st->d_fast[v], tab.data(), tab.size() * sizeof(TFast), cudaMemcpyHostToDevice));
+    }
+  }
+
   // ---- TMA: the tensor-map encoder comes from the driver through the runtime ---------------------
   {
     void* fn = nullptr;
@@ -976,7 +1086,8 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
     if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, P.Ca, D::WW, D::WH);
     P.use_tma = ok ? 1 : 0;
   }
-  const size_t smem = D::smem_bytes(P.num_entries);
+  static const size_t smem_pad = getenv("SRB_SMEM_PAD") ? (size_t)atoi(getenv("SRB_SMEM_PAD")) : 0;  // occupancy experiments
+  const size_t smem = D::smem_bytes(P.num_entries) + smem_pad;
   static size_t attr_set[64] = {};
   if (c->device >= 64 || attr_set[c->device] < smem) {
     SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1039,6 +1150,7 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   *reg_done = P.reg_fused != 0;
   const int TH = tile_height(c);
   P.tile_rows = tile_rows_per_channel(c);
+  P.fast = st->d_fast[TH == 64 ? 1 : 0];
   P.unit_begin = unit_begin;
   const TileLayout L = tile_layout(c);
   const size_t need = 2 * L.nblocks + L.nband;
