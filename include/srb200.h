@@ -117,7 +117,10 @@ srb_status srb_set_regularizer_rows(srb_ctx* ctx, int row_begin, int row_end);
 /* ObjectiveFunction::ComputeAllTerms (objective_function.cpp:5-20), the body of
  * AlglibObjectiveFunction (alglib_objective.cpp:142-152): cost = data term + IRLS regularization
  * term, gradient OVERWRITTEN with the full sum (gradient_host may be NULL: cost only).
- * x and gradient: (c1-c0)*H*W doubles on the host. */
+ * x and gradient: (c1-c0)*H*W doubles on the host.  On the fused path the call is pipelined: x is
+ * copied in slices, each slice's gradient rows return while the next slices are computed, so H2D,
+ * kernel and D2H overlap (pin the buffers with srb_pin_host for full effect; SRB_PIPE_CHUNKS sets
+ * the slice count, default 16, 1 = serial). */
 srb_status srb_eval(srb_ctx* ctx, const double* x_host, double* gradient_host, double* cost);
 /* Same with device-resident x / gradient (no PCIe traffic except the cost scalar). */
 srb_status srb_eval_dev(srb_ctx* ctx, const double* x_dev, double* gradient_dev, double* cost);

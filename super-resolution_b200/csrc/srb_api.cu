@@ -3,7 +3,9 @@
 // Host-side orchestration only: geometry tables, buffer management, kernel launches, timing.
 // All arithmetic of the hot path runs in the CUDA kernels of srb_kernels_*.cuh; there is no CPU
 // fallback anywhere in this library.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -269,6 +271,12 @@ srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
   SRB_CUDA_CHECK(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   SRB_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (auto& e : c->ev) SRB_CUDA_CHECK(c, cudaEventCreate(&e));
+  SRB_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  SRB_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (auto& e : c->ev_in) SRB_CUDA_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : c->ev_k) SRB_CUDA_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : c->ev_pipe) SRB_CUDA_CHECK(c, cudaEventCreate(&e));
+  if (const char* e = getenv("SRB_PIPE_CHUNKS")) c->pipe_chunks = std::max(1, std::min(atoi(e), (int)srb_ctx::kMaxPipe));
 
   // tables
   std::vector<int> src_r(G.h), src_c(G.w);
@@ -334,6 +342,14 @@ void srb_destroy(srb_ctx* c) {
   if (c->h_cost) cudaFreeHost(c->h_cost);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_in)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_k)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_pipe)
+    if (e) cudaEventDestroy(e);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -455,10 +471,69 @@ srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {
 }
 
 // ---- hot path -----------------------------------------------------------------------------------
+static bool units_pipelined(const srb_ctx* c);
+// srb_eval, pipelined: the estimate goes to the device in contiguous slices on a copy-in stream, the
+// tile kernel evaluates the units whose rows (and the halo rows of the next slice) have arrived, and
+// every finished gradient slice returns on a copy-out stream -- H2D, compute and D2H overlap, so the
+// call costs about one PCIe direction instead of two (both directions of the link work at once).
+static srb_status eval_host_pipelined(srb_ctx* c, const double* x_host, double* g_host, double* cost) {
+  const int nu = tile_rows_per_channel(c) * c->Ca();
+  const int nch = std::max(1, std::min(c->pipe_chunks, nu));
+  unsigned long long b[srb_ctx::kMaxPipe + 1];
+  int u[srb_ctx::kMaxPipe + 1];
+  for (int i = 0; i <= nch; ++i) {
+    u[i] = (int)((long long)i * nu / nch);
+    unsigned long long e;
+    if (i < nch) srb_unit_range(c, u[i], u[i] + 1, &b[i], &e);
+  }
+  b[nch] = c->n_active();
+  const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
+  cudaEventRecord(c->ev_pipe[0], c->s_in);
+  for (int i = 0; i < nch; ++i) {
+    SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x + b[i], x_host + b[i], (b[i + 1] - b[i]) * sizeof(double),
+                                      cudaMemcpyHostToDevice, c->s_in));
+    cudaEventRecord(c->ev_in[i], c->s_in);
+  }
+  cudaEventRecord(c->ev_pipe[1], c->s_in);
+  cudaEventRecord(c->ev[1], c->stream);
+  for (int i = 0; i < nch; ++i) {
+    // rows of slice i need the halo rows below them: the head of slice i + 1
+    SRB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->ev_in[std::min(i + 1, nch - 1)], 0));
+    bool reg_done = false;
+    srb_status st = fused_eval_units(c, c->d_x, g_host ? c->d_grad : nullptr, do_reg, u[i], u[i + 1], &reg_done);
+    if (st != SRB_OK) return st;
+    if (g_host) {
+      cudaEventRecord(c->ev_k[i], c->stream);
+      SRB_CUDA_CHECK(c, cudaStreamWaitEvent(c->s_out, c->ev_k[i], 0));
+      if (i == 0) cudaEventRecord(c->ev_pipe[2], c->s_out);
+      SRB_CUDA_CHECK(c, cudaMemcpyAsync(g_host + b[i], c->d_grad + b[i], (b[i + 1] - b[i]) * sizeof(double),
+                                        cudaMemcpyDeviceToHost, c->s_out));
+    }
+  }
+  srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr);
+  if (st != SRB_OK) return st;
+  cudaEventRecord(c->ev[2], c->stream);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_cost, c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (g_host) cudaEventRecord(c->ev_pipe[3], c->s_out);
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (g_host) SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->s_out));
+  c->timing.num_evals += 1;
+  if (cost) *cost = c->h_cost[2];
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev_pipe[0], c->ev_pipe[1]) == cudaSuccess) c->timing.last_eval_h2d_ms = ms;
+  if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->timing.last_eval_kernel_ms = ms;
+  if (g_host && cudaEventElapsedTime(&ms, c->ev_pipe[2], c->ev_pipe[3]) == cudaSuccess) c->timing.last_eval_d2h_ms = ms;
+  (void)cudaGetLastError();
+  return SRB_OK;
+}
+
 srb_status srb_eval(srb_ctx* c, const double* x_host, double* g_host, double* cost) {
   if (!c) return SRB_ERR_INVALID;
   if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
+  if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  if (units_pipelined(c) && c->pipe_chunks > 1) return eval_host_pipelined(c, x_host, g_host, cost);
   const size_t bytes = c->n_active() * sizeof(double);
   cudaEventRecord(c->ev[0], c->stream);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));

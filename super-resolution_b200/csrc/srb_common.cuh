@@ -94,6 +94,11 @@ struct srb_ctx {
   double* h_cost = nullptr;   // pinned mirror of d_cost
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // host<->device pipeline of srb_eval: copy-in / copy-out streams and per-chunk events
+  static constexpr int kMaxPipe = 16;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[kMaxPipe] = {}, ev_k[kMaxPipe] = {}, ev_pipe[4] = {};
+  int pipe_chunks = 16;
   bool timing_valid = false;
   bool profiling = false;  // record events around the dominant kernel (srb_set_profiling)
   srb_timing timing{};
