@@ -37,6 +37,9 @@ constexpr int FT_W = 64;    // tile columns
 constexpr int FT_NT = 256;  // threads per CTA
 constexpr int FT_MAX_ENTRIES = 4096;  // 128 KB of shared memory
 constexpr int FT_MAX_SCALE = 8;
+#ifndef SRB_SLIDE_B
+#define SRB_SLIDE_B 2  // inputs fetched ahead per batch in the 1-D PSF passes (1: 0.1403, 2: 0.1374, 4: 0.1457 ms at cfg3)
+#endif
 
 // One way a regular LR sample lands on an HR pixel of a given sub-pixel phase.
 struct __align__(16) TEntry {
@@ -225,6 +228,32 @@ __device__ __forceinline__ double pixel_residuals(const TileParams& P, const dou
   return z;
 }
 
+// 1-D sliding correlation of one thread's segment: out(l) = sum_i coef[i] * in(l + i) for
+// l in [0, L), only the first `nvalid` outputs being stored.  Inputs are fetched B at a time ahead of
+// the FMAs that use them, so that one shared-memory latency covers B outputs instead of one.
+template <int K, int L, int B, class In, class Out>
+__device__ __forceinline__ void slide_correlate(const double* __restrict__ coef, int nvalid, In in, Out out) {
+  double win[K - 1 + B];
+#pragma unroll
+  for (int i = 0; i < K - 1; ++i) win[i] = in(i);
+#pragma unroll
+  for (int l0 = 0; l0 < L; l0 += B) {
+#pragma unroll
+    for (int b = 0; b < B; ++b) win[K - 1 + b] = (l0 + b < L && l0 + b < nvalid) ? in(l0 + b + K - 1) : 0.0;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      if (l0 + b < L && l0 + b < nvalid) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc = fma(coef[i], win[b + i], acc);
+        out(l0 + b, acc);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) win[i] = win[i + B];
+  }
+}
+
 // IRLS-weighted 2-D TV gradient + cost of this thread's EL pixels (column ec, rows er0..).
 //   BORDER: the tile touches the right / bottom image border or the edge of the regularizer row
 //   band, so neighbours and outputs are checked per pixel.
@@ -383,25 +412,15 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
     for (int id = tid; id < D::TW * NSEG; id += FT_NT) {
       const int c = id % D::TW, seg = id / D::TW;
       const int r0 = seg * L;
-      double win[K];
-#pragma unroll
-      for (int i = 0; i < K - 1; ++i) win[i] = (r0 + i < D::TR + K - 1) ? xo[(r0 + i) * D::XW + c] : 0.0;
-#pragma unroll
-      for (int l = 0; l < L; ++l) {
-        const int r = r0 + l;
-        if (r < D::TR) {
-          win[K - 1] = xo[(r + K - 1) * D::XW + c];
-          double acc = 0.0;
-#pragma unroll
-          for (int i = 0; i < K; ++i) acc = fma(P.u[i], win[i], acc);
-          tmp[r * D::TP + c] = acc;
-#pragma unroll
-          for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
-        }
-      }
+      const double* __restrict__ src = xo + r0 * D::XW + c;
+      double* __restrict__ dst = tmp + r0 * D::TP + c;
+      slide_correlate<K, L, SRB_SLIDE_B>(P.u, D::TR - r0,
+                                [&](int i) { return src[i * D::XW]; },
+                                [&](int l, double v) { dst[l * D::TP] = v; });
     }
   }
   __syncthreads();
+
 
   // ---- 2b. horizontal PSF pass: bx[r][c] = sum_j v[j] * tmp[r][c+j]   (bx overwrites xs) --------
   {
@@ -410,23 +429,10 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
     for (int id = tid; id < D::TR * NSEG; id += FT_NT) {
       const int r = id % D::TR, seg = id / D::TR;
       const int c0 = seg * L;
-      const double* __restrict__ row = tmp + r * D::TP;
-      double win[K];
-#pragma unroll
-      for (int j = 0; j < K - 1; ++j) win[j] = (c0 + j < D::TW) ? row[c0 + j] : 0.0;
-#pragma unroll
-      for (int l = 0; l < L; ++l) {
-        const int c = c0 + l;
-        if (c < D::BW) {
-          win[K - 1] = row[c + K - 1];
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < K; ++j) acc = fma(P.v[j], win[j], acc);
-          bx[r * D::BP + c] = acc;
-#pragma unroll
-          for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
-        }
-      }
+      const double* __restrict__ src = tmp + r * D::TP + c0;
+      double* __restrict__ dst = bx + r * D::BP + c0;
+      slide_correlate<K, L, SRB_SLIDE_B>(P.v, D::BW - c0, [&](int j) { return src[j]; },
+                                [&](int l, double v) { dst[l] = v; });
     }
   }
   __syncthreads();
@@ -596,23 +602,10 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
       for (int id = tid; id < D::ZH * NSEG; id += FT_NT) {
         const int r = id % D::ZH, seg = id / D::ZH;
         const int c0 = seg * L;
-        const double* __restrict__ row = zs + r * D::ZP;
-        double win[K];
-#pragma unroll
-        for (int j = 0; j < K - 1; ++j) win[j] = (c0 + j < D::ZW) ? row[c0 + j] : 0.0;
-#pragma unroll
-        for (int l = 0; l < L; ++l) {
-          const int c = c0 + l;
-          if (c < FT_W) {
-            win[K - 1] = row[c + K - 1];
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < K; ++j) acc = fma(P.u[j], win[j], acc);
-            t2[r * D::T2P + c] = acc;
-#pragma unroll
-            for (int j = 0; j < K - 1; ++j) win[j] = win[j + 1];
-          }
-        }
+        const double* __restrict__ src = zs + r * D::ZP + c0;
+        double* __restrict__ dst = t2 + r * D::T2P + c0;
+        slide_correlate<K, L, SRB_SLIDE_B>(P.u, FT_W - c0, [&](int j) { return src[j]; },
+                                  [&](int l, double v) { dst[l] = v; });
       }
     }
     __syncthreads();
