@@ -225,6 +225,14 @@ def main():
     h_g = torch.empty(n + 1, dtype=torch.float64).pin_memory()
     objective = sharding.ShardedObjective(sharding.EngineEvaluator(eng), n, dist=dist if world > 1 else None,
                                           num_chunks=args.chunks)
+    peer = None
+    if world > 1 and os.environ.get("SRB_MULTI", "peer") == "peer":
+        try:
+            with torch.cuda.stream(stream):
+                peer = sharding.PeerObjective(eng, n, dist, srb)
+        except srb.SrbError as err:
+            if rank == 0:
+                print("peer path not available (%s); using the NCCL allreduce path" % err, file=sys.stderr)
 
     def barrier():
         if world > 1:
@@ -232,8 +240,12 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        # one evaluation of the full objective: per-rank partial + (N > 1) pipelined allreduce
-        objective.evaluate(x_dev, gc_dev).wait()
+        # one evaluation of the full objective: per-rank partial + (N > 1) the cross-rank sum, either
+        # fused into the tile kernel over NVLink peer memory or as a pipelined NCCL allreduce
+        if peer is not None:
+            peer.evaluate(x_dev)
+        else:
+            objective.evaluate(x_dev, gc_dev).wait()
 
     def step_e2e():
         # the call a host solver makes: host x in, host gradient + cost out
@@ -243,9 +255,14 @@ def main():
         if rank == 0:
             x_dev.copy_(h_x, non_blocking=True)
         dist.broadcast(x_dev, src=0)
-        objective.evaluate(x_dev, gc_dev).wait()
-        if rank == 0:
-            h_g.copy_(gc_dev, non_blocking=True)
+        if peer is not None:
+            peer.evaluate(x_dev)
+            if rank == 0:
+                h_g.copy_(peer.out[:n + 1], non_blocking=True)
+        else:
+            objective.evaluate(x_dev, gc_dev).wait()
+            if rank == 0:
+                h_g.copy_(gc_dev, non_blocking=True)
         stream.synchronize()
         return float(h_g[n]) if rank == 0 else 0.0
 
@@ -314,8 +331,11 @@ def main():
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cf["name"], "frames_per_gpu": n_local, "frames_total": n_total,
-                       "partition": ("frame shard + 1 allreduce(C*P+1 f64) per step, pipelined in %d slices"
-                                     % args.chunks) if world > 1 else "single GPU",
+                       "partition": ("single GPU" if world == 1 else
+                                     "frame shard; reduce-scatter fused into the tile kernel over NVLink peer "
+                                     "memory + gather (C*P+1 f64 per step)" if peer is not None else
+                                     "frame shard + 1 NCCL allreduce(C*P+1 f64) per step, pipelined in %d slices"
+                                     % args.chunks),
                        "kernel_path": path_name,
                        "l2": "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % (alg_bytes / 1e6),
                        "cost_check": cost},
@@ -341,7 +361,14 @@ def main():
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": desc, "note": kind}
         print(json.dumps(line))
+    # release every tensor that lives on the engine's stream before the stream goes away
+    if peer is not None:
+        peer.close()
+    del objective, peer, x_dev, gc_dev, h_x, h_g, t
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     eng.close()
 

@@ -146,6 +146,35 @@ srb_status srb_eval_units_dev(srb_ctx* ctx, const double* x_dev, double* gradien
                               int unit_begin, int unit_end);
 srb_status srb_eval_finish_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev);
 
+/* ---- multi-GPU peer path: reduce-scatter fused into the tile kernel's epilogue ---------------
+ * One process per GPU.  Every rank owns a contiguous band of gradient units; the tile kernel
+ * stores each tile's partial gradient rows straight into the owner's memory (slot [rank] of the
+ * owner's slot array, a CUDA-IPC peer mapping over NVLink), so the transfer overlaps the math tile
+ * by tile.  After a barrier the owner sums its slots in fixed rank order and stores the result into
+ * the gradient buffer of every rank (srb_peer_gather_dev), which is the all-gather half.
+ * Buffers are allocated with srb_dev_alloc (plain cudaMalloc, exportable), exchanged as 64-byte IPC
+ * handles by the host layer (sharding.py uses torch.distributed for that), opened with
+ * srb_ipc_open and registered with srb_peer_setup.  Needs the fused path without border band and
+ * with a fused or absent regularizer (srb_num_units > 1); otherwise SRB_ERR_STATE. */
+srb_status srb_peer_sizes(srb_ctx* ctx, int world, unsigned long long* slots_bytes,
+                          unsigned long long* out_bytes);
+srb_status srb_dev_alloc(void** dev_ptr, unsigned long long bytes);
+srb_status srb_dev_free(void* dev_ptr);
+srb_status srb_ipc_export(const void* dev_ptr, unsigned char handle[64]);
+srb_status srb_ipc_open(const unsigned char handle[64], void** dev_ptr);
+srb_status srb_ipc_close(void* dev_ptr);
+/* slot_bases[o] / out_bases[o]: slot array / gradient buffer of rank o (local pointer for o == rank).
+ * out buffers hold n gradient doubles, the total cost at [n], and `world` partial-cost slots. */
+srb_status srb_peer_setup(srb_ctx* ctx, int rank, int world, double* const* slot_bases,
+                          double* const* out_bases);
+/* Phase 1 (then barrier): evaluate this rank's partial objective, scattering gradient rows to
+ * their owners and posting the partial cost to every rank. */
+srb_status srb_peer_scatter_dev(srb_ctx* ctx, const double* x_dev);
+/* Phase 2 (then barrier): sum this rank's band over the slots and store it, with the total cost,
+ * into every rank's gradient buffer. */
+srb_status srb_peer_gather_dev(srb_ctx* ctx);
+srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, unsigned long long bytes);
+
 /* ObjectiveDataTerm::Compute (objective_data_term.cpp:98-116): returns the data cost and ADDS the
  * data gradient into gradient_host (may be NULL). */
 srb_status srb_data_term(srb_ctx* ctx, const double* x_host, double* gradient_host_accum,

@@ -647,6 +647,143 @@ srb_status srb_eval_finish_dev(srb_ctx* c, const double* x_dev, double* gc_dev) 
   return SRB_OK;
 }
 
+// ---- multi-GPU peer path ------------------------------------------------------------------------
+srb_status srb_dev_alloc(void** ptr, unsigned long long bytes) {
+  if (!ptr || !bytes) return SRB_ERR_INVALID;
+  if (cudaMalloc(ptr, (size_t)bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    *ptr = nullptr;
+    return SRB_ERR_NOMEM;
+  }
+  cudaMemset(*ptr, 0, (size_t)bytes);
+  return SRB_OK;
+}
+srb_status srb_dev_free(void* ptr) {
+  if (!ptr) return SRB_ERR_INVALID;
+  return cudaFree(ptr) == cudaSuccess ? SRB_OK : SRB_ERR_CUDA;
+}
+srb_status srb_ipc_export(const void* dev_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!dev_ptr || !handle) return SRB_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SRB_ERR_CUDA;
+  }
+  memcpy(handle, &h, 64);
+  return SRB_OK;
+}
+srb_status srb_ipc_open(const unsigned char handle[64], void** dev_ptr) {
+  if (!handle || !dev_ptr) return SRB_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  if (cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    (void)cudaGetLastError();
+    *dev_ptr = nullptr;
+    return SRB_ERR_CUDA;
+  }
+  return SRB_OK;
+}
+srb_status srb_ipc_close(void* dev_ptr) {
+  if (!dev_ptr) return SRB_ERR_INVALID;
+  return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? SRB_OK : SRB_ERR_CUDA;
+}
+
+static void peer_bands(const srb_ctx* c, int world, int* band_unit, long long* band_elem, long long* cap) {
+  const int nu = tile_rows_per_channel(c) * c->Ca();
+  const int tr = tile_rows_per_channel(c), TH = tile_height(c);
+  *cap = 0;
+  for (int o = 0; o <= world; ++o) {
+    const int u = (int)((long long)o * nu / world);
+    band_unit[o] = u;
+    const int ch = u / tr, t = u - ch * tr;
+    const int row = t * TH < c->g.H ? t * TH : c->g.H;
+    band_elem[o] = u >= nu ? (long long)c->n_active() : (long long)ch * (long long)c->P + (long long)row * c->g.W;
+    if (o > 0 && band_elem[o] - band_elem[o - 1] > *cap) *cap = band_elem[o] - band_elem[o - 1];
+  }
+}
+
+srb_status srb_peer_sizes(srb_ctx* c, int world, unsigned long long* slots_bytes, unsigned long long* out_bytes) {
+  if (!c || !slots_bytes || !out_bytes) return SRB_ERR_INVALID;
+  if (world < 1 || world > SRB_MAX_PEERS) return c->fail(SRB_ERR_INVALID, "world size must be 1..8");
+  if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "the peer path needs the fused tile kernel without a border band");
+  int bu[SRB_MAX_PEERS + 1];
+  long long be[SRB_MAX_PEERS + 1], cap;
+  peer_bands(c, world, bu, be, &cap);
+  *slots_bytes = (unsigned long long)world * (unsigned long long)cap * sizeof(double);
+  *out_bytes = (unsigned long long)(c->n_active() + 1 + world) * sizeof(double);
+  return SRB_OK;
+}
+
+srb_status srb_peer_setup(srb_ctx* c, int rank, int world, double* const* slot_bases, double* const* out_bases) {
+  if (!c || !slot_bases || !out_bases) return SRB_ERR_INVALID;
+  if (world < 1 || world > SRB_MAX_PEERS || rank < 0 || rank >= world) return c->fail(SRB_ERR_INVALID, "bad rank / world");
+  if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "the peer path needs the fused tile kernel without a border band");
+  srb_ctx::Peer& p = c->peer;
+  p.rank = rank;
+  p.world = world;
+  peer_bands(c, world, p.band_unit, p.band_elem, &p.band_cap);
+  for (int o = 0; o < world; ++o) {
+    if (!slot_bases[o] || !out_bases[o]) return c->fail(SRB_ERR_INVALID, "null peer buffer");
+    p.slots[o] = slot_bases[o];
+    p.out[o] = out_bases[o];
+  }
+  p.token = p.slots[rank];
+  p.active = true;
+  return SRB_OK;
+}
+
+srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev) return c->fail(SRB_ERR_INVALID, "null estimate");
+  if (!c->peer.active) return c->fail(SRB_ERR_STATE, "srb_peer_setup has not been called");
+  if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
+  if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "configuration changed: the peer path no longer applies");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
+  const int nu = tile_rows_per_channel(c) * c->Ca();
+  bool reg_done = false;
+  srb_status st = fused_eval_units(c, x_dev, c->peer.token, do_reg, 0, nu, &reg_done);
+  if (st != SRB_OK) return st;
+  if ((st = fused_eval_finish(c, x_dev, nullptr, nullptr)) != SRB_OK) return st;
+  GatherParams G;
+  G.world = c->peer.world;
+  for (int r = 0; r < c->peer.world; ++r) G.out[r] = c->peer.out[r];
+  k_post_cost<<<1, 32, 0, c->stream>>>(c->d_cost, c->peer.rank, c->peer.world, nullptr, G,
+                                       (long long)c->n_active() + 1);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  c->timing.num_evals += 1;
+  return SRB_OK;
+}
+
+srb_status srb_peer_gather_dev(srb_ctx* c) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!c->peer.active) return c->fail(SRB_ERR_STATE, "srb_peer_setup has not been called");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const srb_ctx::Peer& p = c->peer;
+  GatherParams G;
+  G.world = p.world;
+  G.band_begin = p.band_elem[p.rank];
+  G.band_len = p.band_elem[p.rank + 1] - p.band_elem[p.rank];
+  G.band_cap = p.band_cap;
+  G.slots = p.slots[p.rank];
+  for (int r = 0; r < p.world; ++r) G.out[r] = p.out[r];
+  k_sum_gather<<<c->num_sms * 8, 256, 0, c->stream>>>(G);
+  k_sum_cost<<<1, 1, 0, c->stream>>>(p.out[p.rank], (long long)c->n_active() + 1, p.world, (long long)c->n_active());
+  c->timing.kernel_launches += 2;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  return SRB_OK;
+}
+
+srb_status srb_memcpy_d2h(srb_ctx* c, void* dst_host, const void* src_dev, unsigned long long bytes) {
+  if (!c || !dst_host || !src_dev) return SRB_ERR_INVALID;
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
 srb_status srb_set_profiling(srb_ctx* c, int on) {
   if (!c) return SRB_ERR_INVALID;
   c->profiling = on != 0;

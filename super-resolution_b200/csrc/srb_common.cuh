@@ -93,6 +93,20 @@ struct srb_ctx {
   double* d_cost = nullptr;   // [4] data cost, reg cost, total, spare
   double* h_cost = nullptr;   // pinned mirror of d_cost
 
+  // multi-GPU peer state (srb_peer_*): slot arrays / gradient buffers of all ranks, mapped through
+  // CUDA IPC; `token` is the pseudo gradient pointer that selects scatter mode in fused_eval_units
+  struct Peer {
+    bool active = false;
+    int rank = 0, world = 1;
+    long long band_cap = 0;
+    int band_unit[9] = {};
+    long long band_elem[9] = {};
+    double* slots[8] = {};   // slot array bases (index = owner rank); [rank] is local
+    double* out[8] = {};     // gradient(+cost) buffers; [rank] is local
+    double* token = nullptr;
+    void* opened[16] = {};   // IPC mappings to close
+    int num_opened = 0;
+  } peer;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // host<->device pipeline of srb_eval: copy-in / copy-out streams and per-chunk events
   static constexpr int kMaxPipe = 16;

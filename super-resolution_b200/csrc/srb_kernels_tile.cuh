@@ -37,6 +37,7 @@ constexpr int FT_W = 64;    // tile columns
 constexpr int FT_NT = 256;  // threads per CTA
 constexpr int FT_MAX_ENTRIES = 4096;  // 128 KB of shared memory
 constexpr int FT_MAX_SCALE = 8;
+constexpr int SRB_MAX_PEERS = 8;
 #ifndef SRB_SLIDE_B
 #define SRB_SLIDE_B 2  // inputs fetched ahead per batch in the 1-D PSF passes (1: 0.1403, 2: 0.1374, 4: 0.1457 ms at cfg3)
 #endif
@@ -83,6 +84,16 @@ struct TileParams {
   int use_tma;
   const TFast* fast;   // NULL: generic residual pass only
   int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
+  // Scatter mode (multi-GPU reduce-scatter fused into the epilogue): the gradient rows of
+  // unit u go straight into the memory of the rank that owns u -- peer[o] is the base of owner o's
+  // slot array (a peer mapping over NVLink, or local for o == rank), where this rank's slot starts
+  // at slot_offset and holds the owner's band [band_elem[o], band_elem[o+1]).
+  int scatter;                 // 0: write P.g
+  int num_owners;
+  int band_unit[SRB_MAX_PEERS + 1];
+  long long band_elem[SRB_MAX_PEERS + 1];
+  long long slot_offset;       // rank * band capacity, in doubles
+  double* peer[SRB_MAX_PEERS];
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
 };
@@ -327,6 +338,14 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   const int unit = P.unit_begin + blockIdx.y;
   const int ch = unit / P.tile_rows;
   const int tx0 = blockIdx.x * FT_W, ty0 = (unit - ch * P.tile_rows) * FT_H;
+  double* scatter_base = nullptr;  // multi-GPU scatter mode: where the owner of this unit keeps our slot
+  if (P.scatter) {
+    int o = 0;
+#pragma unroll
+    for (int q = 1; q < SRB_MAX_PEERS; ++q)
+      if (q < P.num_owners && unit >= P.band_unit[q]) o = q;
+    scatter_base = P.peer[o] + (P.slot_offset - P.band_elem[o]);
+  }
   const size_t HW = (size_t)P.H * P.W;
   const int s = P.s, sh = P.sshift;
 
@@ -616,6 +635,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
       for (int i = 0; i < K - 1; ++i) win[i] = t2[(er0 + i) * D::T2P + ec];
       double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
+      if (P.scatter) gp = scatter_base + ((long long)ch * (long long)HW + (long long)(ty0 + er0) * P.W + gc);
       const size_t gstep = (size_t)P.W;
       const bool all_in = tx0 + FT_W <= P.W && ty0 + FT_H <= P.H;
       if (all_in) {
@@ -784,6 +804,37 @@ k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, const double* __restrict
   }
   const size_t o = (size_t)c * P.H * P.W + (size_t)pr * P.W + pc;
   g[o] += acc;
+}
+
+// Multi-GPU reduce + all-gather of one rank's band (after every rank has scattered its partial rows
+// into this rank's slots): out_r[band] = sum_s slots[s][band] in fixed slot order (deterministic),
+// written to the gradient buffer of EVERY rank (peer stores over NVLink).
+struct GatherParams {
+  int world;
+  long long band_begin, band_len, band_cap;
+  const double* slots;           // this rank's slot array [world][band_cap]
+  double* out[SRB_MAX_PEERS];    // gradient buffers of all ranks (peer mappings)
+};
+__global__ void __launch_bounds__(256)
+k_sum_gather(GatherParams G) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.band_len; i += stride) {
+    double acc = G.slots[i];
+    for (int s = 1; s < G.world; ++s) acc += G.slots[(long long)s * G.band_cap + i];
+    for (int r = 0; r < G.world; ++r) G.out[r][G.band_begin + i] = acc;
+  }
+}
+// Every rank's partial cost lands in slot [rank] of the cost array of every rank.
+__global__ void k_post_cost(const double* __restrict__ cost, int rank, int world, double* const* dummy,
+                            GatherParams G, long long cost_slot_base) {
+  (void)dummy;
+  if (threadIdx.x < world) G.out[threadIdx.x][cost_slot_base + rank] = cost[2];
+}
+// total cost = fixed-order sum of the ranks' partial costs
+__global__ void k_sum_cost(double* __restrict__ out, long long cost_slot_base, int world, long long n) {
+  double acc = 0.0;
+  for (int r = 0; r < world; ++r) acc += out[cost_slot_base + r];
+  out[n] = acc;
 }
 
 // cost[0] = sum(data partials), cost[1] = sum(reg partials), cost[2] = their sum (also written to
@@ -1130,6 +1181,15 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   for (int b = 0; b < 4; ++b)
     if ((1 << b) == G.s) P.sshift = b;
   P.x = d_x; P.y = c->d_y; P.g = d_g; P.wts = c->d_w;
+  P.scatter = 0;
+  P.num_owners = 0;
+  if (c->peer.active && d_g == c->peer.token) {
+    P.scatter = 1;
+    P.num_owners = c->peer.world;
+    P.slot_offset = (long long)c->peer.rank * c->peer.band_cap;
+    for (int o = 0; o <= c->peer.world; ++o) P.band_unit[o] = c->peer.band_unit[o], P.band_elem[o] = c->peer.band_elem[o];
+    for (int o = 0; o < c->peer.world; ++o) P.peer[o] = c->peer.slots[o];
+  }
   P.entries = st->d_entries; P.phase_begin = st->d_phase_begin; P.num_entries = st->num_entries;
   P.qoff_min_r = st->qoff_min_r; P.qoff_max_r = st->qoff_max_r;
   P.qoff_min_c = st->qoff_min_c; P.qoff_max_c = st->qoff_max_c;

@@ -43,6 +43,16 @@ SIGNATURES = {
     "srb_eval_units_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "srb_eval_finish_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "srb_set_profiling": (C.c_int, [_ctx_p, C.c_int]),
+    "srb_peer_sizes": (C.c_int, [_ctx_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "srb_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_ulonglong]),
+    "srb_dev_free": (C.c_int, [C.c_void_p]),
+    "srb_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "srb_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "srb_ipc_close": (C.c_int, [C.c_void_p]),
+    "srb_peer_setup": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "srb_peer_scatter_dev": (C.c_int, [_ctx_p, C.c_void_p]),
+    "srb_peer_gather_dev": (C.c_int, [_ctx_p]),
+    "srb_memcpy_d2h": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_ulonglong]),
     "srb_data_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_irls_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_reg_apply": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -257,6 +267,26 @@ class Engine:
     def set_profiling(self, on=True):
         self._check(self._lib.srb_set_profiling(self._ctx, 1 if on else 0))
 
+    # -- multi-GPU peer path (reduce-scatter fused into the tile kernel, gather over NVLink)
+    def peer_sizes(self, world):
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self._check(self._lib.srb_peer_sizes(self._ctx, int(world), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def peer_setup(self, rank, world, slot_ptrs, out_ptrs):
+        sa = (C.c_void_p * world)(*slot_ptrs)
+        oa = (C.c_void_p * world)(*out_ptrs)
+        self._check(self._lib.srb_peer_setup(self._ctx, int(rank), int(world), sa, oa))
+
+    def peer_scatter_dev(self, x_dev):
+        self._check(self._lib.srb_peer_scatter_dev(self._ctx, _dev_ptr(x_dev)))
+
+    def peer_gather_dev(self):
+        self._check(self._lib.srb_peer_gather_dev(self._ctx))
+
+    def memcpy_d2h(self, dst, src_ptr, nbytes):
+        self._check(self._lib.srb_memcpy_d2h(self._ctx, dst.ctypes.data_as(C.c_void_p), C.c_void_p(src_ptr), int(nbytes)))
+
     def data_term(self, x, gradient=None):
         """ObjectiveDataTerm::Compute: returns cost; ADDS into `gradient` (in place) if given."""
         xa = _f64(x).reshape(-1)
@@ -331,3 +361,35 @@ def pin_host(array):
 
 def unpin_host(array):
     load_library().srb_unpin_host(array.ctypes.data_as(C.c_void_p))
+
+
+def dev_alloc(nbytes):
+    p = C.c_void_p()
+    st = load_library().srb_dev_alloc(C.byref(p), int(nbytes))
+    if st != 0:
+        raise SrbError(st, "cudaMalloc failed")
+    return p.value
+
+
+def dev_free(ptr):
+    load_library().srb_dev_free(C.c_void_p(ptr))
+
+
+def ipc_export(ptr):
+    buf = C.create_string_buffer(64)
+    st = load_library().srb_ipc_export(C.c_void_p(ptr), buf)
+    if st != 0:
+        raise SrbError(st, "cudaIpcGetMemHandle failed")
+    return bytes(buf.raw)
+
+
+def ipc_open(handle):
+    p = C.c_void_p()
+    st = load_library().srb_ipc_open(C.c_char_p(handle), C.byref(p))
+    if st != 0:
+        raise SrbError(st, "cudaIpcOpenMemHandle failed (no peer access between these GPUs?)")
+    return p.value
+
+
+def ipc_close(ptr):
+    load_library().srb_ipc_close(C.c_void_p(ptr))

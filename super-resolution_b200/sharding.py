@@ -117,6 +117,88 @@ class ShardedObjective:
         self._pending = []
 
 
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (float64, 1-D)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerObjective:
+    """cost + gradient of the full objective with the reduce-scatter FUSED into the tile kernel:
+    each rank's kernel stores its partial gradient rows directly into the memory of the rank that
+    owns them (CUDA-IPC peer mappings over NVLink / NVSwitch), the owners sum their band in fixed
+    rank order and store the result into every rank's gradient buffer (the all-gather half).  The
+    two device-side barriers between the phases are one-element NCCL allreduces on the compute
+    stream.  Raises SrbError(SRB_ERR_STATE) at construction when the model does not qualify
+    (border band, non-fused regularizer) -- use ShardedObjective then.
+
+    evaluate(x): on return (stream-ordered) `self.out[:n]` holds the full gradient and
+    `self.out[n]` the full cost on every rank."""
+
+    def __init__(self, engine, n, dist, pkg, group=None):
+        import torch
+        self.e, self.n, self.dist, self.group, self.pkg = engine, int(n), dist, group, pkg
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        # whether a rank qualifies depends on its own frames (border bands): agree first, so that
+        # either every rank sets the peer path up or every rank raises
+        try:
+            slots_bytes, out_bytes = engine.peer_sizes(self.world)
+            err = None
+        except Exception as exc:   # SrbError(SRB_ERR_STATE)
+            slots_bytes = out_bytes = 0
+            err = exc
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok[0]) == 0:
+            raise err if err is not None else pkg.SrbError(4, "another rank cannot take the peer path")
+        self._slots = pkg.dev_alloc(slots_bytes)
+        self._out = pkg.dev_alloc(out_bytes)
+        mine = (pkg.ipc_export(self._slots), pkg.ipc_export(self._out))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=group)
+        self._opened = []
+        slot_ptrs, out_ptrs = [], []
+        for o, (hs, ho) in enumerate(handles):
+            if o == self.rank:
+                slot_ptrs.append(self._slots)
+                out_ptrs.append(self._out)
+            else:
+                ps, po = pkg.ipc_open(hs), pkg.ipc_open(ho)
+                self._opened += [ps, po]
+                slot_ptrs.append(ps)
+                out_ptrs.append(po)
+        engine.peer_setup(self.rank, self.world, slot_ptrs, out_ptrs)
+        self.out = torch.as_tensor(_DevArray(self._out, self.n + 1 + self.world), device="cuda")
+        self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        dist.barrier(group=group)
+
+    def _barrier(self):
+        # stream-ordered device barrier: nobody passes until every rank's preceding kernels are done
+        self.dist.all_reduce(self._flag, group=self.group)
+
+    def evaluate(self, x):
+        self.e.peer_scatter_dev(x)
+        self._barrier()
+        self.e.peer_gather_dev()
+        self._barrier()
+        return self
+
+    def wait(self):
+        return self
+
+    def close(self):
+        self.dist.barrier(group=self.group)
+        for p in self._opened:
+            self.pkg.ipc_close(p)
+        self._opened = []
+        self.out = None
+        self.dist.barrier(group=self.group)
+        self.pkg.dev_free(self._slots)
+        self.pkg.dev_free(self._out)
+
+
 def reduce_reference(partials):
     """What the collective computes: elementwise sum of the ranks' (gradient, cost) buffers."""
     return np.sum(np.stack(partials, axis=0), axis=0)

@@ -50,6 +50,18 @@ def main():
                 stream.synchronize()
             got = gc.cpu().numpy()
             units = e.num_units()[0]
+            got_peer = None
+            try:   # the fused reduce-scatter / peer-memory path, where the model qualifies
+                with torch.cuda.stream(stream):
+                    pobj = sharding.PeerObjective(e, n, dist, srb)
+                    for _ in range(2):
+                        pobj.evaluate(xd)
+                    stream.synchronize()
+                    got_peer = pobj.out[:n + 1].cpu().numpy()
+                    pobj.close()
+            except srb.SrbError as err:
+                if rank == 0:
+                    print("  peer path not applicable:", err, flush=True)
         if rank == 0:
             with srb.Engine(lr.shape, s, psf, shifts, device=local) as e:
                 e.set_observations(lr)
@@ -59,6 +71,11 @@ def main():
             rel = np.linalg.norm(got[:n] - g.ravel()) / np.linalg.norm(g)
             relf = abs(got[n] - f) / abs(f)
             good = rel <= 1e-13 and relf <= 1e-13
+            if got_peer is not None:
+                relp = np.linalg.norm(got_peer[:n] - g.ravel()) / np.linalg.norm(g)
+                relpf = abs(got_peer[n] - f) / abs(f)
+                print("  peer path: grad rel %.2e cost rel %.2e" % (relp, relpf), flush=True)
+                good = good and relp <= 1e-13 and relpf <= 1e-13
             ok = ok and good
             print("world %d case C=%d %dx%d s=%d K=%d N=%d reg=%d units=%d: grad rel %.2e cost rel %.2e %s" %
                   (world, C, h * s, w * s, s, K, N, reg, units, rel, relf, "OK" if good else "FAIL"), flush=True)
