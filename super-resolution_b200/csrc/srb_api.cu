@@ -339,6 +339,7 @@ void srb_destroy(srb_ctx* c) {
   dev_free(&c->d_y); dev_free(&c->d_decay); dev_free(&c->d_w); dev_free(&c->d_x); dev_free(&c->d_grad);
   dev_free(&c->d_pooled); dev_free(&c->d_vals); dev_free(&c->d_aux); dev_free(&c->d_partial);
   dev_free(&c->d_cost);
+  dev_free(&c->peer.d_err);
   if (c->h_cost) cudaFreeHost(c->h_cost);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -711,7 +712,8 @@ srb_status srb_peer_sizes(srb_ctx* c, int world, unsigned long long* slots_bytes
   long long be[SRB_MAX_PEERS + 1], cap;
   peer_bands(c, world, bu, be, &cap);
   *slots_bytes = (unsigned long long)world * (unsigned long long)cap * sizeof(double);
-  *out_bytes = (unsigned long long)(c->n_active() + 1 + world) * sizeof(double);
+  // gradient, total cost, `world` partial costs, 2 x `world` barrier flags
+  *out_bytes = (unsigned long long)(c->n_active() + 1 + 3 * world) * sizeof(double);
   return SRB_OK;
 }
 
@@ -729,6 +731,11 @@ srb_status srb_peer_setup(srb_ctx* c, int rank, int world, double* const* slot_b
     p.out[o] = out_bases[o];
   }
   p.token = p.slots[rank];
+  p.epoch = 0;
+  if (!p.d_err) {
+    SRB_CUDA_CHECK(c, cudaMalloc((void**)&p.d_err, sizeof(int)));
+    SRB_CUDA_CHECK(c, cudaMemset(p.d_err, 0, sizeof(int)));
+  }
   p.active = true;
   return SRB_OK;
 }
@@ -751,7 +758,10 @@ srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
   for (int r = 0; r < c->peer.world; ++r) G.out[r] = c->peer.out[r];
   k_post_cost<<<1, 32, 0, c->stream>>>(c->d_cost, c->peer.rank, c->peer.world, nullptr, G,
                                        (long long)c->n_active() + 1);
-  c->timing.kernel_launches += 1;
+  c->peer.epoch += 1;
+  k_peer_signal<<<1, 32, 0, c->stream>>>(G, (long long)c->n_active() + 1 + c->peer.world, 0, c->peer.rank,
+                                         c->peer.epoch);
+  c->timing.kernel_launches += 2;
   SRB_CUDA_CHECK(c, cudaGetLastError());
   c->timing.num_evals += 1;
   return SRB_OK;
@@ -769,9 +779,15 @@ srb_status srb_peer_gather_dev(srb_ctx* c) {
   G.band_cap = p.band_cap;
   G.slots = p.slots[p.rank];
   for (int r = 0; r < p.world; ++r) G.out[r] = p.out[r];
+  const long long flag_base = (long long)c->n_active() + 1 + p.world;
+  // every rank's scatter phase (gradient rows + partial cost) has landed here
+  k_peer_wait<<<1, 32, 0, c->stream>>>(p.out[p.rank], flag_base, 0, p.world, p.epoch, p.d_err);
   k_sum_gather<<<c->num_sms * 8, 256, 0, c->stream>>>(G);
   k_sum_cost<<<1, 1, 0, c->stream>>>(p.out[p.rank], (long long)c->n_active() + 1, p.world, (long long)c->n_active());
-  c->timing.kernel_launches += 2;
+  // ... and every rank's band has landed in this rank's gradient buffer
+  k_peer_signal<<<1, 32, 0, c->stream>>>(G, flag_base, 1, p.rank, p.epoch);
+  k_peer_wait<<<1, 32, 0, c->stream>>>(p.out[p.rank], flag_base, 1, p.world, p.epoch, p.d_err);
+  c->timing.kernel_launches += 5;
   SRB_CUDA_CHECK(c, cudaGetLastError());
   return SRB_OK;
 }

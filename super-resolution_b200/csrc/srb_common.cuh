@@ -104,6 +104,8 @@ struct srb_ctx {
     double* slots[8] = {};   // slot array bases (index = owner rank); [rank] is local
     double* out[8] = {};     // gradient(+cost) buffers; [rank] is local
     double* token = nullptr;
+    unsigned long long epoch = 0;  // evaluation counter, identical on every rank
+    int* d_err = nullptr;          // set by k_peer_wait on timeout
     void* opened[16] = {};   // IPC mappings to close
     int num_opened = 0;
   } peer;

@@ -830,6 +830,34 @@ __global__ void k_post_cost(const double* __restrict__ cost, int rank, int world
   (void)dummy;
   if (threadIdx.x < world) G.out[threadIdx.x][cost_slot_base + rank] = cost[2];
 }
+// Device-side barrier between the ranks, on flags that live behind every rank's gradient buffer:
+// k_peer_signal (after this rank's kernels of the phase, same stream) publishes `epoch` into slot
+// [phase][rank] of every rank; k_peer_wait spins until all ranks have published it.  The spin is
+// bounded: on timeout it records the failure in *err and returns instead of hanging the GPU.
+__global__ void k_peer_signal(GatherParams G, long long flag_base, int phase, int rank, unsigned long long epoch) {
+  if (threadIdx.x < G.world) {
+    __threadfence_system();
+    volatile unsigned long long* f =
+        reinterpret_cast<volatile unsigned long long*>(G.out[threadIdx.x] + flag_base) + phase * G.world + rank;
+    *f = epoch;
+  }
+}
+__global__ void k_peer_wait(const double* out_local, long long flag_base, int phase, int world,
+                            unsigned long long epoch, int* err) {
+  if (threadIdx.x < world) {
+    const volatile unsigned long long* f =
+        reinterpret_cast<const volatile unsigned long long*>(out_local + flag_base) + phase * world + threadIdx.x;
+    unsigned long long spins = 0;
+    while (*f < epoch) {
+      if (++spins > (1ull << 24)) {  // seconds: a rank is missing
+        *err = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
 // total cost = fixed-order sum of the ranks' partial costs
 __global__ void k_sum_cost(double* __restrict__ out, long long cost_slot_base, int world, long long n) {
   double acc = 0.0;

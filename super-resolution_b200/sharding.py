@@ -130,8 +130,8 @@ class PeerObjective:
     each rank's kernel stores its partial gradient rows directly into the memory of the rank that
     owns them (CUDA-IPC peer mappings over NVLink / NVSwitch), the owners sum their band in fixed
     rank order and store the result into every rank's gradient buffer (the all-gather half).  The
-    two device-side barriers between the phases are one-element NCCL allreduces on the compute
-    stream.  Raises SrbError(SRB_ERR_STATE) at construction when the model does not qualify
+    two barriers between the phases are flags in peer memory (k_peer_signal / k_peer_wait, bounded
+    spin); SRB_PEER_NCCL_BARRIER=1 adds one-element NCCL allreduces as well.  Raises SrbError(SRB_ERR_STATE) at construction when the model does not qualify
     (border band, non-fused regularizer) -- use ShardedObjective then.
 
     evaluate(x): on return (stream-ordered) `self.out[:n]` holds the full gradient and
@@ -170,7 +170,9 @@ class PeerObjective:
                 slot_ptrs.append(ps)
                 out_ptrs.append(po)
         engine.peer_setup(self.rank, self.world, slot_ptrs, out_ptrs)
-        self.out = torch.as_tensor(_DevArray(self._out, self.n + 1 + self.world), device="cuda")
+        self.out = torch.as_tensor(_DevArray(self._out, self.n + 1 + 3 * self.world), device="cuda")
+        import os
+        self._nccl_barrier = os.environ.get("SRB_PEER_NCCL_BARRIER", "0") == "1"
         self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
         dist.barrier(group=group)
 
@@ -180,9 +182,11 @@ class PeerObjective:
 
     def evaluate(self, x):
         self.e.peer_scatter_dev(x)
-        self._barrier()
+        if self._nccl_barrier:
+            self._barrier()
         self.e.peer_gather_dev()
-        self._barrier()
+        if self._nccl_barrier:
+            self._barrier()
         return self
 
     def wait(self):
