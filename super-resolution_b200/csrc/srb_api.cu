@@ -690,27 +690,22 @@ srb_status srb_ipc_close(void* dev_ptr) {
   return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? SRB_OK : SRB_ERR_CUDA;
 }
 
-static void peer_bands(const srb_ctx* c, int world, int* band_unit, long long* band_elem, long long* cap) {
+// Interleaved ownership: unit u belongs to rank u mod world; a slot holds the owner's units back to
+// back, unit_cap doubles each.
+static void peer_layout(const srb_ctx* c, int world, long long* unit_cap, int* owned_units, long long* band_cap) {
   const int nu = tile_rows_per_channel(c) * c->Ca();
-  const int tr = tile_rows_per_channel(c), TH = tile_height(c);
-  *cap = 0;
-  for (int o = 0; o <= world; ++o) {
-    const int u = (int)((long long)o * nu / world);
-    band_unit[o] = u;
-    const int ch = u / tr, t = u - ch * tr;
-    const int row = t * TH < c->g.H ? t * TH : c->g.H;
-    band_elem[o] = u >= nu ? (long long)c->n_active() : (long long)ch * (long long)c->P + (long long)row * c->g.W;
-    if (o > 0 && band_elem[o] - band_elem[o - 1] > *cap) *cap = band_elem[o] - band_elem[o - 1];
-  }
+  *unit_cap = (long long)tile_height(c) * c->g.W;
+  *owned_units = (nu + world - 1) / world;
+  *band_cap = (long long)*owned_units * *unit_cap;
 }
 
 srb_status srb_peer_sizes(srb_ctx* c, int world, unsigned long long* slots_bytes, unsigned long long* out_bytes) {
   if (!c || !slots_bytes || !out_bytes) return SRB_ERR_INVALID;
   if (world < 1 || world > SRB_MAX_PEERS) return c->fail(SRB_ERR_INVALID, "world size must be 1..8");
   if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "the peer path needs the fused tile kernel without a border band");
-  int bu[SRB_MAX_PEERS + 1];
-  long long be[SRB_MAX_PEERS + 1], cap;
-  peer_bands(c, world, bu, be, &cap);
+  long long ucap, cap;
+  int owned;
+  peer_layout(c, world, &ucap, &owned, &cap);
   *slots_bytes = (unsigned long long)world * (unsigned long long)cap * sizeof(double);
   // gradient, total cost, `world` partial costs, 2 x `world` barrier flags
   *out_bytes = (unsigned long long)(c->n_active() + 1 + 3 * world) * sizeof(double);
@@ -724,7 +719,7 @@ srb_status srb_peer_setup(srb_ctx* c, int rank, int world, double* const* slot_b
   srb_ctx::Peer& p = c->peer;
   p.rank = rank;
   p.world = world;
-  peer_bands(c, world, p.band_unit, p.band_elem, &p.band_cap);
+  peer_layout(c, world, &p.unit_cap, &p.owned_units, &p.band_cap);
   for (int o = 0; o < world; ++o) {
     if (!slot_bases[o] || !out_bases[o]) return c->fail(SRB_ERR_INVALID, "null peer buffer");
     p.slots[o] = slot_bases[o];
@@ -733,8 +728,8 @@ srb_status srb_peer_setup(srb_ctx* c, int rank, int world, double* const* slot_b
   p.token = p.slots[rank];
   p.epoch = 0;
   if (!p.d_err) {
-    SRB_CUDA_CHECK(c, cudaMalloc((void**)&p.d_err, sizeof(int)));
-    SRB_CUDA_CHECK(c, cudaMemset(p.d_err, 0, sizeof(int)));
+    SRB_CUDA_CHECK(c, cudaMalloc((void**)&p.d_err, 2 * sizeof(int)));
+    SRB_CUDA_CHECK(c, cudaMemset(p.d_err, 0, 2 * sizeof(int)));
   }
   p.active = true;
   return SRB_OK;
@@ -752,16 +747,17 @@ srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
   bool reg_done = false;
   srb_status st = fused_eval_units(c, x_dev, c->peer.token, do_reg, 0, nu, &reg_done);
   if (st != SRB_OK) return st;
-  if ((st = fused_eval_finish(c, x_dev, nullptr, nullptr)) != SRB_OK) return st;
+  const srb_ctx::Peer& p = c->peer;
   GatherParams G;
-  G.world = c->peer.world;
-  for (int r = 0; r < c->peer.world; ++r) G.out[r] = c->peer.out[r];
-  k_post_cost<<<1, 32, 0, c->stream>>>(c->d_cost, c->peer.rank, c->peer.world, nullptr, G,
-                                       (long long)c->n_active() + 1);
+  G.world = p.world;
+  G.rank = p.rank;
+  for (int r = 0; r < p.world; ++r) G.out[r] = p.out[r];
+  const TileLayout L = tile_layout(c);
   c->peer.epoch += 1;
-  k_peer_signal<<<1, 32, 0, c->stream>>>(G, (long long)c->n_active() + 1 + c->peer.world, 0, c->peer.rank,
-                                         c->peer.epoch);
-  c->timing.kernel_launches += 2;
+  k_peer_finish_scatter<<<1, 1024, 0, c->stream>>>(c->d_partial, L.nblocks + L.nband, c->d_partial + L.nblocks + L.nband,
+                                                   L.nblocks, c->d_cost, G, (long long)c->n_active() + 1,
+                                                   (long long)c->n_active() + 1 + p.world, c->peer.epoch);
+  c->timing.kernel_launches += 1;
   SRB_CUDA_CHECK(c, cudaGetLastError());
   c->timing.num_evals += 1;
   return SRB_OK;
@@ -774,20 +770,26 @@ srb_status srb_peer_gather_dev(srb_ctx* c) {
   const srb_ctx::Peer& p = c->peer;
   GatherParams G;
   G.world = p.world;
-  G.band_begin = p.band_elem[p.rank];
-  G.band_len = p.band_elem[p.rank + 1] - p.band_elem[p.rank];
+  G.rank = p.rank;
+  G.num_units = tile_rows_per_channel(c) * c->Ca();
+  G.tile_rows = tile_rows_per_channel(c);
+  G.tile_h = tile_height(c);
+  G.H = c->g.H;
+  G.W = c->g.W;
+  G.P = (long long)c->P;
+  G.unit_cap = p.unit_cap;
   G.band_cap = p.band_cap;
   G.slots = p.slots[p.rank];
   for (int r = 0; r < p.world; ++r) G.out[r] = p.out[r];
   const long long flag_base = (long long)c->n_active() + 1 + p.world;
-  // every rank's scatter phase (gradient rows + partial cost) has landed here
-  k_peer_wait<<<1, 32, 0, c->stream>>>(p.out[p.rank], flag_base, 0, p.world, p.epoch, p.d_err);
-  k_sum_gather<<<c->num_sms * 8, 256, 0, c->stream>>>(G);
-  k_sum_cost<<<1, 1, 0, c->stream>>>(p.out[p.rank], (long long)c->n_active() + 1, p.world, (long long)c->n_active());
-  // ... and every rank's band has landed in this rank's gradient buffer
-  k_peer_signal<<<1, 32, 0, c->stream>>>(G, flag_base, 1, p.rank, p.epoch);
+  {
+    const int bx = std::max(1, std::min(64, (c->num_sms * 8 + p.owned_units - 1) / p.owned_units));
+    k_sum_gather<<<dim3(bx, p.owned_units), 256, 0, c->stream>>>(G, (long long)c->n_active(), flag_base, p.epoch,
+                                                                 reinterpret_cast<unsigned int*>(p.d_err + 1), p.d_err);
+  }
+  // every rank's band (and with it the full gradient) has landed in this rank's buffer
   k_peer_wait<<<1, 32, 0, c->stream>>>(p.out[p.rank], flag_base, 1, p.world, p.epoch, p.d_err);
-  c->timing.kernel_launches += 5;
+  c->timing.kernel_launches += 2;
   SRB_CUDA_CHECK(c, cudaGetLastError());
   return SRB_OK;
 }

@@ -98,14 +98,14 @@ struct srb_ctx {
   struct Peer {
     bool active = false;
     int rank = 0, world = 1;
-    long long band_cap = 0;
-    int band_unit[9] = {};
-    long long band_elem[9] = {};
+    long long band_cap = 0;   // doubles per slot: owned units x unit_cap
+    long long unit_cap = 0;   // doubles per full unit
+    int owned_units = 0;      // max units owned by a rank
     double* slots[8] = {};   // slot array bases (index = owner rank); [rank] is local
     double* out[8] = {};     // gradient(+cost) buffers; [rank] is local
     double* token = nullptr;
     unsigned long long epoch = 0;  // evaluation counter, identical on every rank
-    int* d_err = nullptr;          // set by k_peer_wait on timeout
+    int* d_err = nullptr;          // [0] set by the waits on timeout, [1] = last-block counter of k_sum_gather
     void* opened[16] = {};   // IPC mappings to close
     int num_opened = 0;
   } peer;

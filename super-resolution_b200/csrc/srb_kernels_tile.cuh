@@ -85,14 +85,14 @@ struct TileParams {
   const TFast* fast;   // NULL: generic residual pass only
   int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
   // Scatter mode (multi-GPU reduce-scatter fused into the epilogue): the gradient rows of
-  // unit u go straight into the memory of the rank that owns u -- peer[o] is the base of owner o's
-  // slot array (a peer mapping over NVLink, or local for o == rank), where this rank's slot starts
-  // at slot_offset and holds the owner's band [band_elem[o], band_elem[o+1]).
+  // unit u go straight into the memory of the rank that owns u, owner = u mod world (interleaved, so
+  // that the peer stores are spread evenly over the kernel's life time).  peer[o] is the base of owner
+  // o's slot array (a peer mapping over NVLink, or local for o == rank); this rank's slot starts at
+  // slot_offset, and the owner's k-th unit (u = k * world + o) sits at k * unit_cap inside a slot.
   int scatter;                 // 0: write P.g
   int num_owners;
-  int band_unit[SRB_MAX_PEERS + 1];
-  long long band_elem[SRB_MAX_PEERS + 1];
-  long long slot_offset;       // rank * band capacity, in doubles
+  long long unit_cap;          // elements of a full unit (tile rows x W)
+  long long slot_offset;       // rank * slot capacity, in doubles
   double* peer[SRB_MAX_PEERS];
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
@@ -313,7 +313,7 @@ __device__ __forceinline__ void tile_tv(const TileParams& P, const double* __res
   cost_reg = 0.5 * cost;
 }
 
-template <int KH, bool FRAC, int TH>
+template <int KH, bool FRAC, int TH, bool SCAT>
 __global__ void __launch_bounds__(TH * (FT_W / 8), TH == 32 ? (KH <= 3 ? 4 : 3) : 2)
 k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
        const __grid_constant__ CUtensorMap map_w) {
@@ -338,15 +338,16 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   const int unit = P.unit_begin + blockIdx.y;
   const int ch = unit / P.tile_rows;
   const int tx0 = blockIdx.x * FT_W, ty0 = (unit - ch * P.tile_rows) * FT_H;
-  double* scatter_base = nullptr;  // multi-GPU scatter mode: where the owner of this unit keeps our slot
-  if (P.scatter) {
-    int o = 0;
-#pragma unroll
-    for (int q = 1; q < SRB_MAX_PEERS; ++q)
-      if (q < P.num_owners && unit >= P.band_unit[q]) o = q;
-    scatter_base = P.peer[o] + (P.slot_offset - P.band_elem[o]);
-  }
   const size_t HW = (size_t)P.H * P.W;
+  // multi-GPU scatter mode: offset (in doubles, relative to the owner's slot array) that turns a
+  // gradient element index into its place in our slot on the owner of this unit
+  long long scatter_off = 0;
+  int scatter_owner = 0;
+  if (SCAT) {
+    const int k = unit / P.num_owners;
+    scatter_owner = unit - k * P.num_owners;
+    scatter_off = P.slot_offset + (long long)k * P.unit_cap - ((long long)ch * (long long)HW + (long long)ty0 * P.W);
+  }
   const int s = P.s, sh = P.sshift;
 
   // LR cells under the Z region of this tile, and whether all their samples are regular
@@ -635,7 +636,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
       for (int i = 0; i < K - 1; ++i) win[i] = t2[(er0 + i) * D::T2P + ec];
       double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
-      if (P.scatter) gp = scatter_base + ((long long)ch * (long long)HW + (long long)(ty0 + er0) * P.W + gc);
+      if (SCAT) gp = P.peer[scatter_owner] + scatter_off + ((long long)ch * (long long)HW + (long long)(ty0 + er0) * P.W + gc);
       const size_t gstep = (size_t)P.W;
       const bool all_in = tx0 + FT_W <= P.W && ty0 + FT_H <= P.H;
       if (all_in) {
@@ -810,38 +811,103 @@ k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, const double* __restrict
 // into this rank's slots): out_r[band] = sum_s slots[s][band] in fixed slot order (deterministic),
 // written to the gradient buffer of EVERY rank (peer stores over NVLink).
 struct GatherParams {
-  int world;
-  long long band_begin, band_len, band_cap;
+  int world, rank;
+  int num_units, tile_rows, tile_h, H, W;   // unit u = (channel u / tile_rows, tile row u % tile_rows)
+  long long P;                               // H * W
+  long long unit_cap, band_cap;
   const double* slots;           // this rank's slot array [world][band_cap]
   double* out[SRB_MAX_PEERS];    // gradient buffers of all ranks (peer mappings)
 };
+// grid: (blocks per unit, owned units); unit u = blockIdx.y * world + rank.  Every block first waits
+// (bounded spin on the local phase-0 flags) until all ranks have finished their scatter phase; the
+// last block to finish publishes the total cost locally and raises this rank's phase-1 flag on
+// every rank after a system fence.
 __global__ void __launch_bounds__(256)
-k_sum_gather(GatherParams G) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.band_len; i += stride) {
-    double acc = G.slots[i];
-    for (int s = 1; s < G.world; ++s) acc += G.slots[(long long)s * G.band_cap + i];
-    for (int r = 0; r < G.world; ++r) G.out[r][G.band_begin + i] = acc;
+k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long long epoch, unsigned int* done_counter,
+             int* err) {
+  if (threadIdx.x < G.world) {
+    const volatile unsigned long long* f =
+        reinterpret_cast<const volatile unsigned long long*>(G.out[G.rank] + flag_base) + threadIdx.x;
+    unsigned long long spins = 0;
+    while (*f < epoch)
+      if (++spins > (1ull << 24)) {  // seconds: a rank is missing -- give up instead of hanging the GPU
+        *err = 1;
+        break;
+      }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int k = blockIdx.y;
+  const int u = k * G.world + G.rank;
+  if (u < G.num_units) {
+    const int ch = u / G.tile_rows, t = u - ch * G.tile_rows;
+    const int rows = min(G.tile_h, G.H - t * G.tile_h);
+    const long long len = (long long)rows * G.W;
+    const long long first = (long long)ch * G.P + (long long)t * G.tile_h * G.W;
+    const double* __restrict__ src = G.slots + (long long)k * G.unit_cap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+      double acc = src[i];
+      for (int s = 1; s < G.world; ++s) acc += src[(long long)s * G.band_cap + i];
+      for (int r = 0; r < G.world; ++r) G.out[r][first + i] = acc;
+    }
+  }
+  // last block done: total cost + phase-1 flags
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    last = atomicAdd(done_counter, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int r = 0; r < G.world; ++r) acc += G.out[G.rank][n + 1 + r];
+      G.out[G.rank][n] = acc;
+      *done_counter = 0;
+    }
+    if (threadIdx.x < G.world) {
+      __threadfence_system();
+      volatile unsigned long long* f =
+          reinterpret_cast<volatile unsigned long long*>(G.out[threadIdx.x] + flag_base) + G.world + G.rank;
+      *f = epoch;
+    }
   }
 }
-// Every rank's partial cost lands in slot [rank] of the cost array of every rank.
-__global__ void k_post_cost(const double* __restrict__ cost, int rank, int world, double* const* dummy,
-                            GatherParams G, long long cost_slot_base) {
-  (void)dummy;
-  if (threadIdx.x < world) G.out[threadIdx.x][cost_slot_base + rank] = cost[2];
+// End of a rank's scatter phase, one block: cost = fixed-order sum of the per-CTA partials (as
+// k_finish_partials), posted into slot [rank] of every rank's cost array, then -- after a system
+// fence -- the phase-0 flag of this rank is raised on every rank.  Runs after k_tile on the same
+// stream, i.e. after all of this rank's gradient rows have been stored to their owners.
+__global__ void __launch_bounds__(1024)
+k_peer_finish_scatter(const double* __restrict__ pd, size_t nd, const double* __restrict__ pr, size_t nr,
+                      double* __restrict__ cost, GatherParams G, long long cost_slot_base, long long flag_base,
+                      unsigned long long epoch) {
+  double a = 0.0, b = 0.0;
+  for (size_t i = threadIdx.x; i < nd; i += blockDim.x) a += pd[i];
+  for (size_t i = threadIdx.x; i < nr; i += blockDim.x) b += pr[i];
+  a = block_sum(a);
+  b = block_sum(b);
+  __shared__ double total;
+  if (threadIdx.x == 0) {
+    cost[0] = a;
+    cost[1] = b;
+    cost[2] = total = a + b;
+  }
+  __syncthreads();
+  if (threadIdx.x < G.world) {
+    G.out[threadIdx.x][cost_slot_base + G.rank] = total;
+    __threadfence_system();
+    volatile unsigned long long* f =
+        reinterpret_cast<volatile unsigned long long*>(G.out[threadIdx.x] + flag_base) + G.rank;
+    *f = epoch;
+  }
 }
+
 // Device-side barrier between the ranks, on flags that live behind every rank's gradient buffer:
 // k_peer_signal (after this rank's kernels of the phase, same stream) publishes `epoch` into slot
 // [phase][rank] of every rank; k_peer_wait spins until all ranks have published it.  The spin is
 // bounded: on timeout it records the failure in *err and returns instead of hanging the GPU.
-__global__ void k_peer_signal(GatherParams G, long long flag_base, int phase, int rank, unsigned long long epoch) {
-  if (threadIdx.x < G.world) {
-    __threadfence_system();
-    volatile unsigned long long* f =
-        reinterpret_cast<volatile unsigned long long*>(G.out[threadIdx.x] + flag_base) + phase * G.world + rank;
-    *f = epoch;
-  }
-}
 __global__ void k_peer_wait(const double* out_local, long long flag_base, int phase, int world,
                             unsigned long long epoch, int* err) {
   if (threadIdx.x < world) {
@@ -856,13 +922,6 @@ __global__ void k_peer_wait(const double* out_local, long long flag_base, int ph
     }
     __threadfence_system();
   }
-}
-
-// total cost = fixed-order sum of the ranks' partial costs
-__global__ void k_sum_cost(double* __restrict__ out, long long cost_slot_base, int world, long long n) {
-  double acc = 0.0;
-  for (int r = 0; r < world; ++r) acc += out[cost_slot_base + r];
-  out[n] = acc;
 }
 
 // cost[0] = sum(data partials), cost[1] = sum(reg partials), cost[2] = their sum (also written to
@@ -1144,7 +1203,7 @@ inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* 
   return r == CUDA_SUCCESS;
 }
 
-template <int KH, bool FRAC, int TH>
+template <int KH, bool FRAC, int TH, bool SCAT>
 inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   using D = TileDims<KH, FRAC, TH>;
   const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
@@ -1162,11 +1221,11 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   const size_t smem = D::smem_bytes(P.num_entries) + smem_pad;
   static size_t attr_set[64] = {};
   if (c->device >= 64 || attr_set[c->device] < smem) {
-    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH, SCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = smem;
   }
   if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
-  k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
+  k_tile<KH, FRAC, TH, SCAT><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
   if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
   return SRB_OK;
 }
@@ -1214,8 +1273,8 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   if (c->peer.active && d_g == c->peer.token) {
     P.scatter = 1;
     P.num_owners = c->peer.world;
+    P.unit_cap = c->peer.unit_cap;
     P.slot_offset = (long long)c->peer.rank * c->peer.band_cap;
-    for (int o = 0; o <= c->peer.world; ++o) P.band_unit[o] = c->peer.band_unit[o], P.band_elem[o] = c->peer.band_elem[o];
     for (int o = 0; o < c->peer.world; ++o) P.peer[o] = c->peer.slots[o];
   }
   P.entries = st->d_entries; P.phase_begin = st->d_phase_begin; P.num_entries = st->num_entries;
@@ -1248,10 +1307,23 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   P.part_reg = c->d_partial + L.nblocks + L.nband;
   srb_status rc = SRB_OK;
   const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
+  if (P.scatter) {  // multi-GPU scatter epilogue: separate instantiations keep the single-GPU kernel lean
+    if (TH != 32) return c->fail(SRB_ERR_STATE, "the peer path runs with 32-row tiles");
+    switch (st->KH * 2 + (st->frac ? 1 : 0)) {
+#define SRB_SCAT_CASE(KH_, FR_) case (KH_) * 2 + (FR_): rc = tile_launch<KH_, (FR_) != 0, 32, true>(c, P, unit_end); break;
+      SRB_SCAT_CASE(0, 0) SRB_SCAT_CASE(0, 1) SRB_SCAT_CASE(1, 0) SRB_SCAT_CASE(1, 1) SRB_SCAT_CASE(2, 0)
+      SRB_SCAT_CASE(2, 1) SRB_SCAT_CASE(3, 0) SRB_SCAT_CASE(3, 1) SRB_SCAT_CASE(4, 0) SRB_SCAT_CASE(4, 1)
+#undef SRB_SCAT_CASE
+      default: return c->fail(SRB_ERR_STATE, "tile kernel: unsupported PSF size");
+    }
+    if (rc != SRB_OK) return rc;
+    c->timing.kernel_launches += 1;
+    return SRB_OK;
+  }
   switch (key) {
-#define SRB_TILE_CASE(KH_, FR_)                                                             \
-    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P, unit_end); break; \
-    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P, unit_end); break;
+#define SRB_TILE_CASE(KH_, FR_)                                                                    \
+    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32, false>(c, P, unit_end); break;  \
+    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64, false>(c, P, unit_end); break;
     SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
     SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
 #undef SRB_TILE_CASE
