@@ -639,7 +639,33 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
       if (SCAT) gp = P.peer[scatter_owner] + scatter_off + ((long long)ch * (long long)HW + (long long)(ty0 + er0) * P.W + gc);
       const size_t gstep = (size_t)P.W;
       const bool all_in = tx0 + FT_W <= P.W && ty0 + FT_H <= P.H;
-      if (all_in) {
+      if (SCAT && all_in && (P.W & 1) == 0) {
+        // peer destination: stage the finished tile in shared memory (the Z buffer is dead) and hand
+        // it to the bulk-copy engine row by row (cp.async.bulk, 512 B per row) -- NVLink sees full
+        // bursts instead of 8-byte stores, and the SM does not wait on the link
+        double* gtile = bufB;  // [FT_H][FT_W], dense
+#pragma unroll
+        for (int l = 0; l < EL; ++l) {
+          win[K - 1] = t2[(er0 + l + K - 1) * D::T2P + ec];
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
+#pragma unroll
+          for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
+          gtile[(er0 + l) * FT_W + ec] = fma(P.two_s2, acc, tvg[l]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
+        __syncthreads();
+        if (tid < FT_H) {
+          double* dst = P.peer[scatter_owner] + scatter_off +
+                        ((long long)ch * (long long)HW + (long long)(ty0 + tid) * P.W + tx0);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                       "r"(smem_u32(gtile + tid * FT_W)), "r"((unsigned)(FT_W * sizeof(double)))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released
+        }
+      } else if (all_in) {
 #pragma unroll
         for (int l = 0; l < EL; ++l) {
           win[K - 1] = t2[(er0 + l + K - 1) * D::T2P + ec];
@@ -845,10 +871,25 @@ k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long lon
     const long long len = (long long)rows * G.W;
     const long long first = (long long)ch * G.P + (long long)t * G.tile_h * G.W;
     const double* __restrict__ src = G.slots + (long long)k * G.unit_cap;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
-      double acc = src[i];
-      for (int s = 1; s < G.world; ++s) acc += src[(long long)s * G.band_cap + i];
-      for (int r = 0; r < G.world; ++r) G.out[r][first + i] = acc;
+    if (((len | first | G.band_cap | G.unit_cap) & 1) == 0) {
+      // 16-byte accesses: 512 B per warp and store instruction on the link
+      const double2* __restrict__ src2 = reinterpret_cast<const double2*>(src);
+      const long long len2 = len >> 1, cap2 = G.band_cap >> 1, first2 = first >> 1;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len2; i += (long long)gridDim.x * blockDim.x) {
+        double2 acc = src2[i];
+        for (int s = 1; s < G.world; ++s) {
+          const double2 v = src2[(long long)s * cap2 + i];
+          acc.x += v.x;
+          acc.y += v.y;
+        }
+        for (int r = 0; r < G.world; ++r) reinterpret_cast<double2*>(G.out[r])[first2 + i] = acc;
+      }
+    } else {
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+        double acc = src[i];
+        for (int s = 1; s < G.world; ++s) acc += src[(long long)s * G.band_cap + i];
+        for (int r = 0; r < G.world; ++r) G.out[r][first + i] = acc;
+      }
     }
   }
   // last block done: total cost + phase-1 flags
