@@ -146,12 +146,13 @@ srb_status srb_eval_units_dev(srb_ctx* ctx, const double* x_dev, double* gradien
                               int unit_begin, int unit_end);
 srb_status srb_eval_finish_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev);
 
-/* ---- multi-GPU peer path: reduce-scatter fused into the tile kernel's epilogue ---------------
- * One process per GPU.  Every rank owns a contiguous band of gradient units; the tile kernel
- * stores each tile's partial gradient rows straight into the owner's memory (slot [rank] of the
- * owner's slot array, a CUDA-IPC peer mapping over NVLink), so the transfer overlaps the math tile
- * by tile.  After a barrier the owner sums its slots in fixed rank order and stores the result into
- * the gradient buffer of every rank (srb_peer_gather_dev), which is the all-gather half.
+/* ---- multi-GPU peer path: reduce-scatter / all-gather over NVLink peer memory ------------------
+ * One process per GPU.  Every rank owns a contiguous band of gradient units.  The tile kernel
+ * evaluates the gradient band by band; a finished band that belongs to another rank is pushed by a
+ * copy engine into slot [rank] of its owner (a CUDA-IPC peer mapping over NVLink) while the SMs
+ * compute the next band, so the reduce-scatter traffic hides behind the math.  After a flag barrier
+ * in peer memory the owner sums its band in fixed rank order and stores the result into the
+ * gradient buffer of every rank (srb_peer_gather_dev), which is the all-gather half.
  * Buffers are allocated with srb_dev_alloc (plain cudaMalloc, exportable), exchanged as 64-byte IPC
  * handles by the host layer (sharding.py uses torch.distributed for that), opened with
  * srb_ipc_open and registered with srb_peer_setup.  Needs the fused path without border band and
@@ -167,11 +168,11 @@ srb_status srb_ipc_close(void* dev_ptr);
  * out buffers hold n gradient doubles, the total cost at [n], and `world` partial-cost slots. */
 srb_status srb_peer_setup(srb_ctx* ctx, int rank, int world, double* const* slot_bases,
                           double* const* out_bases);
-/* Phase 1 (then barrier): evaluate this rank's partial objective, scattering gradient rows to
- * their owners and posting the partial cost to every rank. */
+/* Phase 1: evaluate this rank's partial objective band by band, pushing every finished band to
+ * its owner, then post the partial cost and raise this rank's "scattered" flag on every rank. */
 srb_status srb_peer_scatter_dev(srb_ctx* ctx, const double* x_dev);
-/* Phase 2 (then barrier): sum this rank's band over the slots and store it, with the total cost,
- * into every rank's gradient buffer. */
+/* Phase 2: wait for all ranks' flags, sum this rank's band over the slots and store it, with the
+ * total cost, into every rank's gradient buffer; wait until all bands have arrived here. */
 srb_status srb_peer_gather_dev(srb_ctx* ctx);
 srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, unsigned long long bytes);
 

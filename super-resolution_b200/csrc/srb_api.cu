@@ -340,6 +340,12 @@ void srb_destroy(srb_ctx* c) {
   dev_free(&c->d_pooled); dev_free(&c->d_vals); dev_free(&c->d_aux); dev_free(&c->d_partial);
   dev_free(&c->d_cost);
   dev_free(&c->peer.d_err);
+  for (auto& st : c->peer.s_copy)
+    if (st) cudaStreamDestroy(st);
+  for (auto& e : c->peer.ev_band)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : c->peer.ev_copy)
+    if (e) cudaEventDestroy(e);
   if (c->h_cost) cudaFreeHost(c->h_cost);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
@@ -690,22 +696,28 @@ srb_status srb_ipc_close(void* dev_ptr) {
   return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? SRB_OK : SRB_ERR_CUDA;
 }
 
-// Interleaved ownership: unit u belongs to rank u mod world; a slot holds the owner's units back to
-// back, unit_cap doubles each.
-static void peer_layout(const srb_ctx* c, int world, long long* unit_cap, int* owned_units, long long* band_cap) {
+// Contiguous ownership: rank o owns units [o*nu/world, (o+1)*nu/world), a contiguous element range.
+static void peer_bands(const srb_ctx* c, int world, int* band_unit, long long* band_elem, long long* cap) {
   const int nu = tile_rows_per_channel(c) * c->Ca();
-  *unit_cap = (long long)tile_height(c) * c->g.W;
-  *owned_units = (nu + world - 1) / world;
-  *band_cap = (long long)*owned_units * *unit_cap;
+  const int tr = tile_rows_per_channel(c), TH = tile_height(c);
+  *cap = 0;
+  for (int o = 0; o <= world; ++o) {
+    const int u = (int)((long long)o * nu / world);
+    band_unit[o] = u;
+    const int ch = u / tr, t = u - ch * tr;
+    const int row = t * TH < c->g.H ? t * TH : c->g.H;
+    band_elem[o] = u >= nu ? (long long)c->n_active() : (long long)ch * (long long)c->P + (long long)row * c->g.W;
+    if (o > 0 && band_elem[o] - band_elem[o - 1] > *cap) *cap = band_elem[o] - band_elem[o - 1];
+  }
 }
 
 srb_status srb_peer_sizes(srb_ctx* c, int world, unsigned long long* slots_bytes, unsigned long long* out_bytes) {
   if (!c || !slots_bytes || !out_bytes) return SRB_ERR_INVALID;
   if (world < 1 || world > SRB_MAX_PEERS) return c->fail(SRB_ERR_INVALID, "world size must be 1..8");
   if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "the peer path needs the fused tile kernel without a border band");
-  long long ucap, cap;
-  int owned;
-  peer_layout(c, world, &ucap, &owned, &cap);
+  int bu[SRB_MAX_PEERS + 1];
+  long long be[SRB_MAX_PEERS + 1], cap;
+  peer_bands(c, world, bu, be, &cap);
   *slots_bytes = (unsigned long long)world * (unsigned long long)cap * sizeof(double);
   // gradient, total cost, `world` partial costs, 2 x `world` barrier flags
   *out_bytes = (unsigned long long)(c->n_active() + 1 + 3 * world) * sizeof(double);
@@ -716,25 +728,39 @@ srb_status srb_peer_setup(srb_ctx* c, int rank, int world, double* const* slot_b
   if (!c || !slot_bases || !out_bases) return SRB_ERR_INVALID;
   if (world < 1 || world > SRB_MAX_PEERS || rank < 0 || rank >= world) return c->fail(SRB_ERR_INVALID, "bad rank / world");
   if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "the peer path needs the fused tile kernel without a border band");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   srb_ctx::Peer& p = c->peer;
   p.rank = rank;
   p.world = world;
-  peer_layout(c, world, &p.unit_cap, &p.owned_units, &p.band_cap);
+  peer_bands(c, world, p.band_unit, p.band_elem, &p.band_cap);
   for (int o = 0; o < world; ++o) {
     if (!slot_bases[o] || !out_bases[o]) return c->fail(SRB_ERR_INVALID, "null peer buffer");
     p.slots[o] = slot_bases[o];
     p.out[o] = out_bases[o];
   }
-  p.token = p.slots[rank];
   p.epoch = 0;
   if (!p.d_err) {
     SRB_CUDA_CHECK(c, cudaMalloc((void**)&p.d_err, 2 * sizeof(int)));
     SRB_CUDA_CHECK(c, cudaMemset(p.d_err, 0, 2 * sizeof(int)));
+    {
+      // highest priority: whatever executes the peer copies (copy engine or a copy kernel) must get
+      // going while the tile kernel of the next band still fills the SMs
+      int lo = 0, hi = 0;
+      SRB_CUDA_CHECK(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      for (auto& s : p.s_copy) SRB_CUDA_CHECK(c, cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+    }
+    for (auto& e : p.ev_band) SRB_CUDA_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : p.ev_copy) SRB_CUDA_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   p.active = true;
   return SRB_OK;
 }
 
+// Phase 1.  The tile kernel evaluates the gradient band by band, the bands of the OTHER ranks first
+// (starting with the next rank, so that at any time every rank's link carries one band in each
+// direction); as soon as a band is finished a copy engine pushes it over NVLink into slot [rank] of
+// its owner, while the SMs are already computing the next band.  The own band is evaluated last and
+// stays local.  After the last push the partial cost and the phase-0 flag go to every rank.
 srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
   if (!c) return SRB_ERR_INVALID;
   if (!x_dev) return c->fail(SRB_ERR_INVALID, "null estimate");
@@ -742,27 +768,67 @@ srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
   if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "configuration changed: the peer path no longer applies");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  srb_ctx::Peer& p = c->peer;
   const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
-  const int nu = tile_rows_per_channel(c) * c->Ca();
-  bool reg_done = false;
-  srb_status st = fused_eval_units(c, x_dev, c->peer.token, do_reg, 0, nu, &reg_done);
-  if (st != SRB_OK) return st;
-  const srb_ctx::Peer& p = c->peer;
+  static const bool trace = getenv("SRB_PEER_TRACE") != nullptr;  // one-off timeline on stderr
+  cudaEvent_t tr[20] = {};
+  if (trace) {
+    for (auto& e : tr) cudaEventCreate(&e);
+    cudaEventRecord(tr[0], c->stream);
+  }
+  for (int i = 0; i < p.world; ++i) {
+    const int o = (p.rank + 1 + i) % p.world;  // i == world - 1  <=>  o == rank
+    if (p.band_unit[o + 1] > p.band_unit[o]) {
+      bool reg_done = false;
+      srb_status st = fused_eval_units(c, x_dev, c->d_grad, do_reg, p.band_unit[o], p.band_unit[o + 1], &reg_done);
+      if (st != SRB_OK) return st;
+    }
+    if (o != p.rank && p.band_elem[o + 1] > p.band_elem[o]) {
+      cudaStream_t sc = p.s_copy[i & 1];
+      SRB_CUDA_CHECK(c, cudaEventRecord(p.ev_band[i], c->stream));
+      SRB_CUDA_CHECK(c, cudaStreamWaitEvent(sc, p.ev_band[i], 0));
+      SRB_CUDA_CHECK(c, cudaMemcpyAsync(p.slots[o] + (long long)p.rank * p.band_cap, c->d_grad + p.band_elem[o],
+                                        (size_t)(p.band_elem[o + 1] - p.band_elem[o]) * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, sc));
+      if (trace) cudaEventRecord(tr[10 + i], sc);
+    }
+    if (trace) cudaEventRecord(tr[1 + i], c->stream);
+  }
+  for (int k = 0; k < 2; ++k) {  // the flag may only be raised once every push has been delivered
+    SRB_CUDA_CHECK(c, cudaEventRecord(p.ev_copy[k], p.s_copy[k]));
+    SRB_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, p.ev_copy[k], 0));
+  }
   GatherParams G;
   G.world = p.world;
   G.rank = p.rank;
   for (int r = 0; r < p.world; ++r) G.out[r] = p.out[r];
   const TileLayout L = tile_layout(c);
-  c->peer.epoch += 1;
+  p.epoch += 1;
   k_peer_finish_scatter<<<1, 1024, 0, c->stream>>>(c->d_partial, L.nblocks + L.nband, c->d_partial + L.nblocks + L.nband,
                                                    L.nblocks, c->d_cost, G, (long long)c->n_active() + 1,
-                                                   (long long)c->n_active() + 1 + p.world, c->peer.epoch);
+                                                   (long long)c->n_active() + 1 + p.world, p.epoch);
+  if (trace) {
+    cudaEventRecord(tr[9], c->stream);
+    cudaStreamSynchronize(c->stream);
+    float ms = 0.f;
+    fprintf(stderr, "[srb peer trace rank %d]", p.rank);
+    for (int i = 0; i < p.world; ++i) {
+      cudaEventElapsedTime(&ms, tr[0], tr[1 + i]);
+      fprintf(stderr, " band%d kernel done %.3f", i, ms);
+      if (i + 1 < p.world && cudaEventElapsedTime(&ms, tr[0], tr[10 + i]) == cudaSuccess) fprintf(stderr, " (push done %.3f)", ms);
+    }
+    cudaEventElapsedTime(&ms, tr[0], tr[9]);
+    fprintf(stderr, " | flags raised %.3f ms\n", ms);
+    for (auto& e : tr) cudaEventDestroy(e);
+  }
   c->timing.kernel_launches += 1;
   SRB_CUDA_CHECK(c, cudaGetLastError());
   c->timing.num_evals += 1;
   return SRB_OK;
 }
 
+// Phase 2: wait for every rank's contribution, sum this rank's band in fixed rank order and store it,
+// with the total cost, into every rank's gradient buffer; then wait until all bands have arrived here.
 srb_status srb_peer_gather_dev(srb_ctx* c) {
   if (!c) return SRB_ERR_INVALID;
   if (!c->peer.active) return c->fail(SRB_ERR_STATE, "srb_peer_setup has not been called");
@@ -771,22 +837,15 @@ srb_status srb_peer_gather_dev(srb_ctx* c) {
   GatherParams G;
   G.world = p.world;
   G.rank = p.rank;
-  G.num_units = tile_rows_per_channel(c) * c->Ca();
-  G.tile_rows = tile_rows_per_channel(c);
-  G.tile_h = tile_height(c);
-  G.H = c->g.H;
-  G.W = c->g.W;
-  G.P = (long long)c->P;
-  G.unit_cap = p.unit_cap;
+  G.band_begin = p.band_elem[p.rank];
+  G.band_len = p.band_elem[p.rank + 1] - p.band_elem[p.rank];
   G.band_cap = p.band_cap;
   G.slots = p.slots[p.rank];
+  G.own = c->d_grad + p.band_elem[p.rank];
   for (int r = 0; r < p.world; ++r) G.out[r] = p.out[r];
   const long long flag_base = (long long)c->n_active() + 1 + p.world;
-  {
-    const int bx = std::max(1, std::min(64, (c->num_sms * 8 + p.owned_units - 1) / p.owned_units));
-    k_sum_gather<<<dim3(bx, p.owned_units), 256, 0, c->stream>>>(G, (long long)c->n_active(), flag_base, p.epoch,
-                                                                 reinterpret_cast<unsigned int*>(p.d_err + 1), p.d_err);
-  }
+  k_sum_gather<<<c->num_sms * 8, 256, 0, c->stream>>>(G, (long long)c->n_active(), flag_base, p.epoch,
+                                                      reinterpret_cast<unsigned int*>(p.d_err + 1), p.d_err);
   // every rank's band (and with it the full gradient) has landed in this rank's buffer
   k_peer_wait<<<1, 32, 0, c->stream>>>(p.out[p.rank], flag_base, 1, p.world, p.epoch, p.d_err);
   c->timing.kernel_launches += 2;

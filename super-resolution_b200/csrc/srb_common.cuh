@@ -98,16 +98,15 @@ struct srb_ctx {
   struct Peer {
     bool active = false;
     int rank = 0, world = 1;
-    long long band_cap = 0;   // doubles per slot: owned units x unit_cap
-    long long unit_cap = 0;   // doubles per full unit
-    int owned_units = 0;      // max units owned by a rank
-    double* slots[8] = {};   // slot array bases (index = owner rank); [rank] is local
-    double* out[8] = {};     // gradient(+cost) buffers; [rank] is local
-    double* token = nullptr;
+    long long band_cap = 0;        // doubles per slot (largest band)
+    int band_unit[9] = {};         // rank o owns units [band_unit[o], band_unit[o+1]) ...
+    long long band_elem[9] = {};   // ... = gradient elements [band_elem[o], band_elem[o+1])
+    double* slots[8] = {};         // slot array bases (index = owner rank); [rank] is local
+    double* out[8] = {};           // gradient(+cost, +flags) buffers; [rank] is local
     unsigned long long epoch = 0;  // evaluation counter, identical on every rank
     int* d_err = nullptr;          // [0] set by the waits on timeout, [1] = last-block counter of k_sum_gather
-    void* opened[16] = {};   // IPC mappings to close
-    int num_opened = 0;
+    cudaStream_t s_copy[2] = {nullptr, nullptr};  // DMA pushes of finished bands to their owners
+    cudaEvent_t ev_band[8] = {}, ev_copy[2] = {};
   } peer;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // host<->device pipeline of srb_eval: copy-in / copy-out streams and per-chunk events

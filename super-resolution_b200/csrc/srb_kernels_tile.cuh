@@ -84,16 +84,6 @@ struct TileParams {
   int use_tma;
   const TFast* fast;   // NULL: generic residual pass only
   int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
-  // Scatter mode (multi-GPU reduce-scatter fused into the epilogue): the gradient rows of
-  // unit u go straight into the memory of the rank that owns u, owner = u mod world (interleaved, so
-  // that the peer stores are spread evenly over the kernel's life time).  peer[o] is the base of owner
-  // o's slot array (a peer mapping over NVLink, or local for o == rank); this rank's slot starts at
-  // slot_offset, and the owner's k-th unit (u = k * world + o) sits at k * unit_cap inside a slot.
-  int scatter;                 // 0: write P.g
-  int num_owners;
-  long long unit_cap;          // elements of a full unit (tile rows x W)
-  long long slot_offset;       // rank * slot capacity, in doubles
-  double* peer[SRB_MAX_PEERS];
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
 };
@@ -313,7 +303,7 @@ __device__ __forceinline__ void tile_tv(const TileParams& P, const double* __res
   cost_reg = 0.5 * cost;
 }
 
-template <int KH, bool FRAC, int TH, bool SCAT>
+template <int KH, bool FRAC, int TH>
 __global__ void __launch_bounds__(TH * (FT_W / 8), TH == 32 ? (KH <= 3 ? 4 : 3) : 2)
 k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
        const __grid_constant__ CUtensorMap map_w) {
@@ -339,15 +329,6 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   const int ch = unit / P.tile_rows;
   const int tx0 = blockIdx.x * FT_W, ty0 = (unit - ch * P.tile_rows) * FT_H;
   const size_t HW = (size_t)P.H * P.W;
-  // multi-GPU scatter mode: offset (in doubles, relative to the owner's slot array) that turns a
-  // gradient element index into its place in our slot on the owner of this unit
-  long long scatter_off = 0;
-  int scatter_owner = 0;
-  if (SCAT) {
-    const int k = unit / P.num_owners;
-    scatter_owner = unit - k * P.num_owners;
-    scatter_off = P.slot_offset + (long long)k * P.unit_cap - ((long long)ch * (long long)HW + (long long)ty0 * P.W);
-  }
   const int s = P.s, sh = P.sshift;
 
   // LR cells under the Z region of this tile, and whether all their samples are regular
@@ -636,36 +617,9 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 #pragma unroll
       for (int i = 0; i < K - 1; ++i) win[i] = t2[(er0 + i) * D::T2P + ec];
       double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
-      if (SCAT) gp = P.peer[scatter_owner] + scatter_off + ((long long)ch * (long long)HW + (long long)(ty0 + er0) * P.W + gc);
       const size_t gstep = (size_t)P.W;
       const bool all_in = tx0 + FT_W <= P.W && ty0 + FT_H <= P.H;
-      if (SCAT && all_in && (P.W & 1) == 0) {
-        // peer destination: stage the finished tile in shared memory (the Z buffer is dead) and hand
-        // it to the bulk-copy engine row by row (cp.async.bulk, 512 B per row) -- NVLink sees full
-        // bursts instead of 8-byte stores, and the SM does not wait on the link
-        double* gtile = bufB;  // [FT_H][FT_W], dense
-#pragma unroll
-        for (int l = 0; l < EL; ++l) {
-          win[K - 1] = t2[(er0 + l + K - 1) * D::T2P + ec];
-          double acc = 0.0;
-#pragma unroll
-          for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
-#pragma unroll
-          for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
-          gtile[(er0 + l) * FT_W + ec] = fma(P.two_s2, acc, tvg[l]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
-        __syncthreads();
-        if (tid < FT_H) {
-          double* dst = P.peer[scatter_owner] + scatter_off +
-                        ((long long)ch * (long long)HW + (long long)(ty0 + tid) * P.W + tx0);
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                       "r"(smem_u32(gtile + tid * FT_W)), "r"((unsigned)(FT_W * sizeof(double)))
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released
-        }
-      } else if (all_in) {
+      if (all_in) {
 #pragma unroll
         for (int l = 0; l < EL; ++l) {
           win[K - 1] = t2[(er0 + l + K - 1) * D::T2P + ec];
@@ -838,16 +792,16 @@ k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, const double* __restrict
 // written to the gradient buffer of EVERY rank (peer stores over NVLink).
 struct GatherParams {
   int world, rank;
-  int num_units, tile_rows, tile_h, H, W;   // unit u = (channel u / tile_rows, tile row u % tile_rows)
-  long long P;                               // H * W
-  long long unit_cap, band_cap;
-  const double* slots;           // this rank's slot array [world][band_cap]
+  long long band_begin, band_len, band_cap;
+  const double* slots;           // this rank's slot array [world][band_cap]; slot [rank] is unused:
+  const double* own;             // ... this rank's own contribution is its local partial gradient band
   double* out[SRB_MAX_PEERS];    // gradient buffers of all ranks (peer mappings)
 };
-// grid: (blocks per unit, owned units); unit u = blockIdx.y * world + rank.  Every block first waits
-// (bounded spin on the local phase-0 flags) until all ranks have finished their scatter phase; the
-// last block to finish publishes the total cost locally and raises this rank's phase-1 flag on
-// every rank after a system fence.
+// Multi-GPU reduce + all-gather of this rank's band: out_r[band] = sum_s partial_s[band] in fixed
+// rank order (deterministic), stored into the gradient buffer of EVERY rank (peer stores over
+// NVLink).  Every block first waits (bounded spin on the local phase-0 flags) until all ranks'
+// contributions have arrived; the last block to finish publishes the total cost locally and raises
+// this rank's phase-1 flag on every rank after a system fence.
 __global__ void __launch_bounds__(256)
 k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long long epoch, unsigned int* done_counter,
              int* err) {
@@ -863,43 +817,34 @@ k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long lon
     __threadfence_system();
   }
   __syncthreads();
-  const int k = blockIdx.y;
-  const int u = k * G.world + G.rank;
-  if (u < G.num_units) {
-    const int ch = u / G.tile_rows, t = u - ch * G.tile_rows;
-    const int rows = min(G.tile_h, G.H - t * G.tile_h);
-    const long long len = (long long)rows * G.W;
-    const long long first = (long long)ch * G.P + (long long)t * G.tile_h * G.W;
-    const double* __restrict__ src = G.slots + (long long)k * G.unit_cap;
-    if (((len | first | G.band_cap | G.unit_cap) & 1) == 0) {
-      // 16-byte accesses: 512 B per warp and store instruction on the link
-      const double2* __restrict__ src2 = reinterpret_cast<const double2*>(src);
-      const long long len2 = len >> 1, cap2 = G.band_cap >> 1, first2 = first >> 1;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len2; i += (long long)gridDim.x * blockDim.x) {
-        double2 acc = src2[i];
-        for (int s = 1; s < G.world; ++s) {
-          const double2 v = src2[(long long)s * cap2 + i];
-          acc.x += v.x;
-          acc.y += v.y;
-        }
-        for (int r = 0; r < G.world; ++r) reinterpret_cast<double2*>(G.out[r])[first2 + i] = acc;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((G.band_len | G.band_begin | G.band_cap) & 1) == 0) {
+    // 16-byte accesses: 512 B per warp and store instruction on the link
+    const long long len2 = G.band_len >> 1, cap2 = G.band_cap >> 1, first2 = G.band_begin >> 1;
+    const double2* __restrict__ slots2 = reinterpret_cast<const double2*>(G.slots);
+    const double2* __restrict__ own2 = reinterpret_cast<const double2*>(G.own);
+    for (long long i = i0; i < len2; i += stride) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int s = 0; s < G.world; ++s) {
+        const double2 v = s == G.rank ? own2[i] : slots2[(long long)s * cap2 + i];
+        acc.x += v.x;
+        acc.y += v.y;
       }
-    } else {
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
-        double acc = src[i];
-        for (int s = 1; s < G.world; ++s) acc += src[(long long)s * G.band_cap + i];
-        for (int r = 0; r < G.world; ++r) G.out[r][first + i] = acc;
-      }
+      for (int r = 0; r < G.world; ++r) reinterpret_cast<double2*>(G.out[r])[first2 + i] = acc;
+    }
+  } else {
+    for (long long i = i0; i < G.band_len; i += stride) {
+      double acc = 0.0;
+      for (int s = 0; s < G.world; ++s) acc += s == G.rank ? G.own[i] : G.slots[(long long)s * G.band_cap + i];
+      for (int r = 0; r < G.world; ++r) G.out[r][G.band_begin + i] = acc;
     }
   }
   // last block done: total cost + phase-1 flags
   __threadfence_system();
   __syncthreads();
   __shared__ bool last;
-  if (threadIdx.x == 0) {
-    const unsigned int total = gridDim.x * gridDim.y;
-    last = atomicAdd(done_counter, 1u) == total - 1;
-  }
+  if (threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x * gridDim.y - 1;
   __syncthreads();
   if (last) {
     if (threadIdx.x == 0) {
@@ -916,6 +861,7 @@ k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long lon
     }
   }
 }
+
 // End of a rank's scatter phase, one block: cost = fixed-order sum of the per-CTA partials (as
 // k_finish_partials), posted into slot [rank] of every rank's cost array, then -- after a system
 // fence -- the phase-0 flag of this rank is raised on every rank.  Runs after k_tile on the same
@@ -1244,7 +1190,7 @@ inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* 
   return r == CUDA_SUCCESS;
 }
 
-template <int KH, bool FRAC, int TH, bool SCAT>
+template <int KH, bool FRAC, int TH>
 inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   using D = TileDims<KH, FRAC, TH>;
   const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
@@ -1262,11 +1208,11 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   const size_t smem = D::smem_bytes(P.num_entries) + smem_pad;
   static size_t attr_set[64] = {};
   if (c->device >= 64 || attr_set[c->device] < smem) {
-    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH, SCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = smem;
   }
   if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
-  k_tile<KH, FRAC, TH, SCAT><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
+  k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
   if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
   return SRB_OK;
 }
@@ -1309,15 +1255,6 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   for (int b = 0; b < 4; ++b)
     if ((1 << b) == G.s) P.sshift = b;
   P.x = d_x; P.y = c->d_y; P.g = d_g; P.wts = c->d_w;
-  P.scatter = 0;
-  P.num_owners = 0;
-  if (c->peer.active && d_g == c->peer.token) {
-    P.scatter = 1;
-    P.num_owners = c->peer.world;
-    P.unit_cap = c->peer.unit_cap;
-    P.slot_offset = (long long)c->peer.rank * c->peer.band_cap;
-    for (int o = 0; o < c->peer.world; ++o) P.peer[o] = c->peer.slots[o];
-  }
   P.entries = st->d_entries; P.phase_begin = st->d_phase_begin; P.num_entries = st->num_entries;
   P.qoff_min_r = st->qoff_min_r; P.qoff_max_r = st->qoff_max_r;
   P.qoff_min_c = st->qoff_min_c; P.qoff_max_c = st->qoff_max_c;
@@ -1348,23 +1285,10 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   P.part_reg = c->d_partial + L.nblocks + L.nband;
   srb_status rc = SRB_OK;
   const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
-  if (P.scatter) {  // multi-GPU scatter epilogue: separate instantiations keep the single-GPU kernel lean
-    if (TH != 32) return c->fail(SRB_ERR_STATE, "the peer path runs with 32-row tiles");
-    switch (st->KH * 2 + (st->frac ? 1 : 0)) {
-#define SRB_SCAT_CASE(KH_, FR_) case (KH_) * 2 + (FR_): rc = tile_launch<KH_, (FR_) != 0, 32, true>(c, P, unit_end); break;
-      SRB_SCAT_CASE(0, 0) SRB_SCAT_CASE(0, 1) SRB_SCAT_CASE(1, 0) SRB_SCAT_CASE(1, 1) SRB_SCAT_CASE(2, 0)
-      SRB_SCAT_CASE(2, 1) SRB_SCAT_CASE(3, 0) SRB_SCAT_CASE(3, 1) SRB_SCAT_CASE(4, 0) SRB_SCAT_CASE(4, 1)
-#undef SRB_SCAT_CASE
-      default: return c->fail(SRB_ERR_STATE, "tile kernel: unsupported PSF size");
-    }
-    if (rc != SRB_OK) return rc;
-    c->timing.kernel_launches += 1;
-    return SRB_OK;
-  }
   switch (key) {
 #define SRB_TILE_CASE(KH_, FR_)                                                                    \
-    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32, false>(c, P, unit_end); break;  \
-    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64, false>(c, P, unit_end); break;
+    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P, unit_end); break;  \
+    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P, unit_end); break;
     SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
     SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
 #undef SRB_TILE_CASE

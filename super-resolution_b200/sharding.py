@@ -1,7 +1,7 @@
 """Multi-GPU frame sharding of the MAP objective, one process per GPU.
 
-The data term is a sum over LR frames (objective_data_term.cpp:104-114), so rank r of G holds the
-frames {k : k mod G == r} and their observations; the estimate x and the IRLS weights are
+The data term is a sum over LR frames (objective_data_term.cpp:104-114), so rank r of G holds a
+contiguous block of the frames and their observations; the estimate x and the IRLS weights are
 replicated; the regularization term is split by HR row bands so that the sum over ranks is the
 full objective.  ONE allreduce(sum) over C*P + 1 doubles (gradient, cost in the last slot) per
 evaluation gives gradient and cost on every rank.
@@ -17,8 +17,13 @@ import numpy as np
 
 
 def frame_shard(num_frames, rank, world):
-    """Frame indices owned by `rank` (round robin)."""
-    return [k for k in range(num_frames) if k % world == rank]
+    """Frame indices owned by `rank`: contiguous blocks.  (Any partition of the frames is valid, the
+    data term is a plain sum over them; blocks keep a capture sequence that cycles through the
+    sub-pixel phases -- one frame per phase and block -- balanced on every rank, which is what the
+    tile kernel's table-driven residual pass wants.)"""
+    base, extra = divmod(int(num_frames), int(world))
+    start = rank * base + min(rank, extra)
+    return list(range(start, start + base + (1 if rank < extra else 0)))
 
 
 def row_band(H, rank, world):
@@ -170,6 +175,7 @@ class PeerObjective:
                 slot_ptrs.append(ps)
                 out_ptrs.append(po)
         engine.peer_setup(self.rank, self.world, slot_ptrs, out_ptrs)
+        self.slot_ptrs, self.out_ptrs = slot_ptrs, out_ptrs
         self.out = torch.as_tensor(_DevArray(self._out, self.n + 1 + 3 * self.world), device="cuda")
         import os
         self._nccl_barrier = os.environ.get("SRB_PEER_NCCL_BARRIER", "0") == "1"

@@ -52,6 +52,26 @@ with torch.cuda.stream(stream):
         tg.append(ev[1].elapsed_time(ev[2]))
     print("rank %d world %d: scatter phase %.3f ms, gather phase (incl. both barriers) %.3f ms" %
           (rank, world, float(np.median(ts)), float(np.median(tg))), flush=True)
+    # raw NVLink numbers between rank and its neighbour: one DMA copy, and a copy kernel (torch add)
+    if world > 1:
+        nbytes = 50 * 1024 * 1024
+        peer_ptr = obj.slot_ptrs[(rank + 1) % world]
+        dst = torch.as_tensor(sharding._DevArray(peer_ptr, nbytes // 8), device="cuda")
+        src = torch.zeros(nbytes // 8, dtype=torch.float64, device="cuda")
+        for name, fn in (("DMA copy (cudaMemcpyAsync)", lambda: dst.copy_(src)),
+                         ("SM copy kernel (torch.add out=peer)", lambda: torch.add(src, 1.0, out=dst))):
+            for _ in range(3):
+                fn()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(10):
+                fn()
+            b.record(stream)
+            stream.synchronize()
+            if rank == 0:
+                print("rank 0 -> peer, 50 MiB, %s: %.1f GB/s" % (name, nbytes * 10 / (a.elapsed_time(b) * 1e-3) / 1e9), flush=True)
+            dist.barrier()
     obj.close()
 dist.barrier()
 dist.destroy_process_group()
