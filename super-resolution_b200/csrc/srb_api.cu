@@ -776,23 +776,38 @@ srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
     for (auto& e : tr) cudaEventCreate(&e);
     cudaEventRecord(tr[0], c->stream);
   }
-  for (int i = 0; i < p.world; ++i) {
-    const int o = (p.rank + 1 + i) % p.world;  // i == world - 1  <=>  o == rank
-    if (p.band_unit[o + 1] > p.band_unit[o]) {
-      bool reg_done = false;
-      srb_status st = fused_eval_units(c, x_dev, c->d_grad, do_reg, p.band_unit[o], p.band_unit[o + 1], &reg_done);
-      if (st != SRB_OK) return st;
+  // Bands are evaluated in groups of `grp` consecutive owners per tile-kernel launch (a launch should
+  // span several waves of CTAs: 148 SMs x 4 resident CTAs = 592 tiles per wave); the bands of a group
+  // are pushed as soon as the group's launch has finished.
+  static const int grp_env = getenv("SRB_PEER_GROUP") ? atoi(getenv("SRB_PEER_GROUP")) : 0;
+  const int grp = grp_env > 0 ? grp_env : (p.world + 3) / 4;
+  for (int i0 = 0; i0 < p.world; i0 += grp) {
+    const int i1 = std::min(i0 + grp, p.world);
+    // owners (rank + 1 + i) % world for i in [i0, i1): one or two contiguous unit ranges
+    for (int i = i0; i < i1;) {
+      const int o = (p.rank + 1 + i) % p.world;  // i == world - 1  <=>  o == rank
+      int j = i;
+      while (j + 1 < i1 && (p.rank + 1 + j + 1) % p.world == (p.rank + 1 + j) % p.world + 1) ++j;
+      const int o_last = (p.rank + 1 + j) % p.world;
+      if (p.band_unit[o_last + 1] > p.band_unit[o]) {
+        bool reg_done = false;
+        srb_status st = fused_eval_units(c, x_dev, c->d_grad, do_reg, p.band_unit[o], p.band_unit[o_last + 1], &reg_done);
+        if (st != SRB_OK) return st;
+      }
+      i = j + 1;
     }
-    if (o != p.rank && p.band_elem[o + 1] > p.band_elem[o]) {
+    SRB_CUDA_CHECK(c, cudaEventRecord(p.ev_band[i0 / grp], c->stream));
+    for (int i = i0; i < i1; ++i) {
+      const int o = (p.rank + 1 + i) % p.world;
+      if (o == p.rank || p.band_elem[o + 1] <= p.band_elem[o]) continue;
       cudaStream_t sc = p.s_copy[i & 1];
-      SRB_CUDA_CHECK(c, cudaEventRecord(p.ev_band[i], c->stream));
-      SRB_CUDA_CHECK(c, cudaStreamWaitEvent(sc, p.ev_band[i], 0));
+      SRB_CUDA_CHECK(c, cudaStreamWaitEvent(sc, p.ev_band[i0 / grp], 0));
       SRB_CUDA_CHECK(c, cudaMemcpyAsync(p.slots[o] + (long long)p.rank * p.band_cap, c->d_grad + p.band_elem[o],
                                         (size_t)(p.band_elem[o + 1] - p.band_elem[o]) * sizeof(double),
                                         cudaMemcpyDeviceToDevice, sc));
       if (trace) cudaEventRecord(tr[10 + i], sc);
     }
-    if (trace) cudaEventRecord(tr[1 + i], c->stream);
+    if (trace) cudaEventRecord(tr[1 + i0 / grp], c->stream);
   }
   for (int k = 0; k < 2; ++k) {  // the flag may only be raised once every push has been delivered
     SRB_CUDA_CHECK(c, cudaEventRecord(p.ev_copy[k], p.s_copy[k]));
@@ -812,14 +827,16 @@ srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
     cudaStreamSynchronize(c->stream);
     float ms = 0.f;
     fprintf(stderr, "[srb peer trace rank %d]", p.rank);
-    for (int i = 0; i < p.world; ++i) {
-      cudaEventElapsedTime(&ms, tr[0], tr[1 + i]);
-      fprintf(stderr, " band%d kernel done %.3f", i, ms);
-      if (i + 1 < p.world && cudaEventElapsedTime(&ms, tr[0], tr[10 + i]) == cudaSuccess) fprintf(stderr, " (push done %.3f)", ms);
+    for (int gi = 0; gi * grp < p.world; ++gi) {
+      cudaEventElapsedTime(&ms, tr[0], tr[1 + gi]);
+      fprintf(stderr, " group%d kernels done %.3f", gi, ms);
     }
+    for (int i = 0; i + 1 < p.world; ++i)
+      if (cudaEventElapsedTime(&ms, tr[0], tr[10 + i]) == cudaSuccess) fprintf(stderr, " push%d done %.3f", i, ms);
     cudaEventElapsedTime(&ms, tr[0], tr[9]);
     fprintf(stderr, " | flags raised %.3f ms\n", ms);
     for (auto& e : tr) cudaEventDestroy(e);
+    (void)cudaGetLastError();  // unrecorded trace events
   }
   c->timing.kernel_launches += 1;
   SRB_CUDA_CHECK(c, cudaGetLastError());
