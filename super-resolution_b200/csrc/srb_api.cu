@@ -776,11 +776,12 @@ srb_status srb_peer_scatter_dev(srb_ctx* c, const double* x_dev) {
     for (auto& e : tr) cudaEventCreate(&e);
     cudaEventRecord(tr[0], c->stream);
   }
-  // Bands are evaluated in groups of `grp` consecutive owners per tile-kernel launch (a launch should
-  // span several waves of CTAs: 148 SMs x 4 resident CTAs = 592 tiles per wave); the bands of a group
-  // are pushed as soon as the group's launch has finished.
+  // Bands are evaluated in groups of `grp` consecutive owners per tile-kernel launch and pushed as soon
+  // as the group's launch has finished.  One band per launch measured best (8 GPUs, cfg3: 0.423 ms per
+  // step vs 0.445 with two bands per launch, although a band is then only 1.3 waves of CTAs);
+  // SRB_PEER_GROUP overrides.
   static const int grp_env = getenv("SRB_PEER_GROUP") ? atoi(getenv("SRB_PEER_GROUP")) : 0;
-  const int grp = grp_env > 0 ? grp_env : (p.world + 3) / 4;
+  const int grp = grp_env > 0 ? grp_env : 1;
   for (int i0 = 0; i0 < p.world; i0 += grp) {
     const int i1 = std::min(i0 + grp, p.world);
     // owners (rank + 1 + i) % world for i in [i0, i1): one or two contiguous unit ranges
