@@ -68,6 +68,29 @@ const char* srb_version(void);
 /* Number of CUDA devices visible (0 if none / no driver). */
 int srb_device_count(void);
 
+/* ---- planning (host only: works without a CUDA device) ---------------------------------------
+ * What srb_create would decide for this model: whether the fused tile kernel covers it (and why
+ * not), how the (frame, tap) entries spread over the sub-pixel phases, and the band of "special" LR
+ * samples near the image border that are evaluated in the reference's operation order instead
+ * (regular samples: band_lo_r <= row < band_hi_r and band_lo_c <= column < band_hi_c). */
+typedef struct {
+  int hr_height, hr_width;
+  int warps_uniform, warps_integer;
+  int fused;                 /* 1: the fused tile kernel covers this model */
+  int fractional;            /* bilinear forward / transpose taps */
+  int psf_half;
+  int num_entries, min_entries_per_phase, max_entries_per_phase;
+  int band_lo_r, band_hi_r, band_lo_c, band_hi_c;
+  int table_driven;          /* interior tiles use the precomputed residual table */
+  char why[160];             /* reason when fused == 0, or the validation error */
+} srb_plan_info;
+srb_status srb_plan(const srb_model_desc* desc, srb_plan_info* out);
+/* cv::warpAffine's fixed-point translation (motion_module.cpp:18-24): the source coordinate of
+ * destination pixel p is p + n/32, n = srb_quantize_shift(d). */
+int srb_quantize_shift(double shift);
+/* One dimension of the special-sample test: LR sample q of an image of hr_size pixels. */
+int srb_sample_is_special(int q, int hr_size, int psf_half, int scale, double shift);
+
 /* ---- life cycle ------------------------------------------------------------------------- */
 /* Builds a context on CUDA device `device`.  Replaces: ImageModel::CreateImageModel +
  * MapSolver::MapSolver (map_solver.cpp:52-86).  Fails with SRB_ERR_GEOMETRY when cv::resize

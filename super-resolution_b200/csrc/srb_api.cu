@@ -10,47 +10,17 @@
 #include <new>
 
 #include "srb_common.cuh"
+#include "srb_geometry.h"
 #include "srb_kernels_generic.cuh"
 #include "srb_kernels_reg.cuh"
 #include "srb_kernels_tile.cuh"
+#include "srb_kernels_band.cuh"
+#include "srb_kernels_peer.cuh"
+#include "srb_tile_plan.cuh"
 
 using namespace srb;
 
 namespace {
-
-// ---- geometry (host) ---------------------------------------------------------------------------
-// cv::resize INTER_NEAREST index map (reference call: image_data.cpp:341-347): bit-exact fp64.
-int nearest_index(int q, int n_src, int n_dst) {
-  const double inv_scale = (double)n_dst / (double)n_src;
-  const double ifx = 1.0 / inv_scale;
-  int s = (int)std::floor(q * ifx);
-  if (s > n_src - 1) s = n_src - 1;
-  return s;
-}
-// ImageData::ResizeImage(scale factor) output size (image_data.cpp:353-364).
-void lr_size(int s, int H, int W, int* h, int* w) {
-  const double f = 1.0 / (double)s;
-  *w = (int)(W * f);
-  *h = (int)(H * f);
-}
-// Fixed-point translation of cv::warpAffine for the matrix [1 0 dx; 0 1 dy] (motion_module.cpp:
-// 18-24): AB_BITS = 10, round_delta = 16, INTER_BITS = 5.
-WarpQ quantize_warp(double dx, double dy, int H, int* rowY) {
-  WarpQ q;
-  const double m2 = -dx, m5 = -dy;
-  const long X0 = std::lrint(m2 * 1024.0) + 16;
-  q.nX = (int)(X0 >> 5);
-  q.uniform = true;
-  q.nY = 0;
-  for (int y = 0; y < H; ++y) {
-    const long Y0 = std::lrint((1.0 * y + m5) * 1024.0) + 16;
-    const int Y = (int)(Y0 >> 5);
-    if (y == 0) q.nY = Y;
-    if (Y != 32 * y + q.nY) q.uniform = false;
-    if (rowY) rowY[y] = Y;
-  }
-  return q;
-}
 
 template <class T>
 srb_status dev_alloc(srb_ctx* ctx, T** ptr, size_t count) {
@@ -193,33 +163,11 @@ void update_timing(srb_ctx* c) {
   if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->timing.last_eval_d2h_ms = ms;
 }
 
-}  // namespace
-
-// ================================================================================================
-extern "C" {
-
-const char* srb_version(void) { return "srb200 0.1 (sm_100a)"; }
-
-int srb_device_count(void) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return 0;
-  }
-  return n;
-}
-
-const char* srb_last_error(const srb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-
-srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
-  if (!out) return SRB_ERR_INVALID;
-  *out = nullptr;
-  srb_ctx* c = new (std::nothrow) srb_ctx();
-  if (!c) return SRB_ERR_NOMEM;
-  *out = c;  // returned even on failure so the caller can read srb_last_error, then srb_destroy
+// Host part of srb_create, shared with srb_plan: validates the description the way the reference
+// CHECK-fails (map_solver.cpp:52-76, blur_module.cpp:13-18, downsampling_module.cpp:13-17,
+// objective_data_term.cpp:91-95), fills the geometry and quantises the warps.  No CUDA calls.
+srb_status build_host_model(srb_ctx* c, const srb_model_desc* d) {
   if (!d) return c->fail(SRB_ERR_INVALID, "null model description");
-  // The reference CHECK-fails on these (map_solver.cpp:52-76, blur_module.cpp:13-18,
-  // downsampling_module.cpp:13-17, objective_data_term.cpp:91-95).
   if (d->lr_height <= 0 || d->lr_width <= 0 || d->num_channels <= 0)
     return c->fail(SRB_ERR_INVALID, "observation size and channel count must be positive");
   if (d->num_frames <= 0) return c->fail(SRB_ERR_INVALID, "cannot solve with 0 observations");
@@ -260,6 +208,91 @@ srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
     if (!ok) return c->fail(SRB_ERR_GEOMETRY, "cv::resize nearest index map is not block-regular for this size/scale");
   }
 
+  c->warp_fwd.resize(G.N);
+  c->warp_tr.resize(G.N);
+  c->warps_uniform = true;
+  c->warps_integer = true;
+  for (int k = 0; k < G.N; ++k) {
+    const double dx = c->shifts_h[2 * k], dy = c->shifts_h[2 * k + 1];
+    c->warp_fwd[k] = quantize_warp(dx, dy, G.H, nullptr);
+    c->warp_tr[k] = quantize_warp(-dx, -dy, G.H, nullptr);
+    c->warps_uniform = c->warps_uniform && c->warp_fwd[k].uniform && c->warp_tr[k].uniform;
+    const int frac = (c->warp_fwd[k].nX | c->warp_fwd[k].nY | c->warp_tr[k].nX | c->warp_tr[k].nY) & 31;
+    c->warps_integer = c->warps_integer && frac == 0;
+  }
+  return SRB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* srb_version(void) { return "srb200 0.1 (sm_100a)"; }
+
+int srb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+srb_status srb_plan(const srb_model_desc* d, srb_plan_info* out) {
+  if (!out) return SRB_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  srb_ctx tmp;   // host-only use: no CUDA call is made on it
+  srb_status st = build_host_model(&tmp, d);
+  if (st != SRB_OK) {
+    snprintf(out->why, sizeof out->why, "%s", tmp.err.c_str());
+    return st;
+  }
+  TilePlan plan;
+  plan_tile_model(tmp.g, tmp.psf_h, tmp.warp_fwd, tmp.warp_tr, tmp.warps_uniform, tmp.warps_integer, &plan);
+  out->hr_height = tmp.g.H;
+  out->hr_width = tmp.g.W;
+  out->warps_uniform = tmp.warps_uniform ? 1 : 0;
+  out->warps_integer = tmp.warps_integer ? 1 : 0;
+  out->fused = plan.supported ? 1 : 0;
+  snprintf(out->why, sizeof out->why, "%s", plan.why.c_str());
+  if (!plan.supported) return SRB_OK;
+  out->fractional = plan.frac ? 1 : 0;
+  out->psf_half = plan.KH;
+  out->num_entries = (int)plan.entries.size();
+  out->min_entries_per_phase = out->num_entries;
+  for (size_t ph = 0; ph + 1 < plan.phase_begin.size(); ++ph) {
+    const int n = plan.phase_begin[ph + 1] - plan.phase_begin[ph];
+    out->min_entries_per_phase = std::min(out->min_entries_per_phase, n);
+    out->max_entries_per_phase = std::max(out->max_entries_per_phase, n);
+  }
+  out->band_lo_r = plan.band.lo_r; out->band_hi_r = plan.band.hi_r;
+  out->band_lo_c = plan.band.lo_c; out->band_hi_c = plan.band.hi_c;
+  out->table_driven = plan.fast[0].empty() ? 0 : 1;
+  return SRB_OK;
+}
+
+int srb_quantize_shift(double d) { return quantize_warp(d, 0.0, 1, nullptr).nX; }
+
+int srb_sample_is_special(int q, int hr_size, int psf_half, int scale, double shift) {
+  const WarpQ f = quantize_warp(shift, 0.0, 1, nullptr), t = quantize_warp(-shift, 0.0, 1, nullptr);
+  return sample_is_special(q, hr_size, psf_half, scale, f.nX, t.nX) ? 1 : 0;
+}
+
+const char* srb_last_error(const srb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
+  if (!out) return SRB_ERR_INVALID;
+  *out = nullptr;
+  srb_ctx* c = new (std::nothrow) srb_ctx();
+  if (!c) return SRB_ERR_NOMEM;
+  *out = c;  // returned even on failure so the caller can read srb_last_error, then srb_destroy
+  {
+    srb_status hst = build_host_model(c, d);
+    if (hst != SRB_OK) return hst;
+  }
+  Geometry& G = c->g;
+
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     (void)cudaGetLastError();
@@ -283,19 +316,12 @@ srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
   for (int q = 0; q < G.h; ++q) src_r[q] = nearest_index(q, G.H, G.h);
   for (int q = 0; q < G.w; ++q) src_c[q] = nearest_index(q, G.W, G.w);
   std::vector<int> rowY_f((size_t)G.N * G.H), rowY_t((size_t)G.N * G.H), nX_f(G.N), nX_t(G.N);
-  c->warp_fwd.resize(G.N);
-  c->warp_tr.resize(G.N);
-  c->warps_uniform = true;
-  c->warps_integer = true;
   for (int k = 0; k < G.N; ++k) {
     const double dx = c->shifts_h[2 * k], dy = c->shifts_h[2 * k + 1];
-    c->warp_fwd[k] = quantize_warp(dx, dy, G.H, &rowY_f[(size_t)k * G.H]);
-    c->warp_tr[k] = quantize_warp(-dx, -dy, G.H, &rowY_t[(size_t)k * G.H]);
+    quantize_warp(dx, dy, G.H, &rowY_f[(size_t)k * G.H]);
+    quantize_warp(-dx, -dy, G.H, &rowY_t[(size_t)k * G.H]);
     nX_f[k] = c->warp_fwd[k].nX;
     nX_t[k] = c->warp_tr[k].nX;
-    c->warps_uniform = c->warps_uniform && c->warp_fwd[k].uniform && c->warp_tr[k].uniform;
-    const int frac = (c->warp_fwd[k].nX | c->warp_fwd[k].nY | c->warp_tr[k].nX | c->warp_tr[k].nY) & 31;
-    c->warps_integer = c->warps_integer && frac == 0;
   }
   srb_status st;
 #define ALLOC_COPY(dptr, hvec)                                                                   \

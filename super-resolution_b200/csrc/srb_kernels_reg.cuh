@@ -186,11 +186,6 @@ __global__ void k_fill(double* __restrict__ p, size_t n, double v) {
     p[i] = v;
 }
 
-// host_out[i] += dev[i] is done on the host; this adds device planes: a += b.
-__global__ void k_axpy1(double* __restrict__ a, const double* __restrict__ b, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    a[i] = __dadd_rn(a[i], b[i]);
-}
 
 // cost[2] = cost[0] + cost[1]; optionally also written behind the gradient (multi-GPU form).
 __global__ void k_finish_cost(double* __restrict__ cost, double* __restrict__ tail) {

@@ -37,7 +37,6 @@ constexpr int FT_W = 64;    // tile columns
 constexpr int FT_NT = 256;  // threads per CTA
 constexpr int FT_MAX_ENTRIES = 4096;  // 128 KB of shared memory
 constexpr int FT_MAX_SCALE = 8;
-constexpr int SRB_MAX_PEERS = 8;
 #ifndef SRB_SLIDE_B
 #define SRB_SLIDE_B 2  // inputs fetched ahead per batch in the 1-D PSF passes (1: 0.1403, 2: 0.1374, 4: 0.1457 ms at cfg3)
 #endif
@@ -655,686 +654,6 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
     P.part_data[cta] = P.s2 * cost_data;
     P.part_reg[cta] = cost_reg;
   }
-}
-
-// ---- border band ("special" samples) -----------------------------------------------------------
-// The special LR samples form a frame-independent band: LR rows [0, lo_r) and [hi_r, h), and in
-// the rows between, LR columns [0, lo_c) and [hi_c, w).  They are stored compactly:
-//   index = rr * w + qc                      for the row bands (rr counts band rows top to bottom)
-//         = n_rows_part + m * nc + cc        for the column bands (m = qr - lo_r, cc counts band columns)
-struct BandGeom {
-  int h, w;
-  int lo_r, hi_r, lo_c, hi_c;
-  __host__ __device__ int band_rows() const { return lo_r + (h - hi_r); }
-  __host__ __device__ int band_cols() const { return lo_c + (w - hi_c); }
-  __host__ __device__ long long rows_part() const { return (long long)band_rows() * w; }
-  __host__ __device__ long long count() const {
-    return rows_part() + (long long)(hi_r - lo_r) * band_cols();
-  }
-  // compact index of LR sample (qr, qc), or -1 when it is a regular sample
-  __host__ __device__ long long index_of(int qr, int qc) const {
-    if (qr < lo_r) return (long long)qr * w + qc;
-    if (qr >= hi_r) return (long long)(lo_r + qr - hi_r) * w + qc;
-    if (qc < lo_c) return rows_part() + (long long)(qr - lo_r) * band_cols() + qc;
-    if (qc >= hi_c) return rows_part() + (long long)(qr - lo_r) * band_cols() + lo_c + (qc - hi_c);
-    return -1;
-  }
-  __host__ __device__ void sample_of(long long i, int* qr, int* qc) const {
-    if (i < rows_part()) {
-      const int rr = (int)(i / w);
-      *qc = (int)(i - (long long)rr * w);
-      *qr = rr < lo_r ? rr : hi_r + (rr - lo_r);
-    } else {
-      const long long j = i - rows_part();
-      const int nc = band_cols();
-      const int m = (int)(j / nc), cc = (int)(j - (long long)m * nc);
-      *qr = lo_r + m;
-      *qc = cc < lo_c ? cc : hi_c + (cc - lo_c);
-    }
-  }
-};
-
-// Forward model + residual of the special samples in the reference's operation order
-// (forward_pixel): pooled[(k*Ca + c) * count + i] = s^2-fold sum of r, cost partials s^2 r^2.
-// grid: (ceil(count/256), N*Ca)
-__global__ void __launch_bounds__(256)
-k_band_forward(GenericParams P, BandGeom B, const double* __restrict__ x, const double* __restrict__ y,
-               double* __restrict__ pooled, double* __restrict__ cost_partial) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long cnt = B.count();
-  const int kc = blockIdx.y;
-  const int k = kc / P.Ca, c = kc % P.Ca;
-  double cost = 0.0;
-  if (i < cnt) {
-    int qr, qc;
-    B.sample_of(i, &qr, &qc);
-    const size_t HW = (size_t)P.H * P.W, hw = (size_t)P.h * P.w;
-    const double pred = forward_pixel(P, x + (size_t)c * HW, k, qr, qc);
-    const double obs = y[((size_t)k * P.Ct + P.c0 + c) * hw + (size_t)qr * P.w + qc];
-    const double r = __dadd_rn(pred, -obs);
-    double acc = 0.0;
-    const int reps = P.s * P.s;
-    for (int t = 0; t < reps; ++t) acc = __dadd_rn(acc, r);
-    pooled[(size_t)kc * cnt + i] = acc;
-    cost = (double)reps * (r * r);
-  }
-  const double bs = block_sum(cost);
-  if (threadIdx.x == 0) cost_partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = bs;
-}
-
-// B^T D^T restricted to the special samples of one frame, at HR pixel (pr, pc) (cf.
-// backproject_pixel).
-__device__ __forceinline__ double band_backproject(const GenericParams& P, const BandGeom& B,
-                                                   const double* __restrict__ pooled_kc, int pr, int pc) {
-  if (pr < 0 || pr >= P.H || pc < 0 || pc >= P.W) return 0.0;
-  const int s = P.s, K = P.K, hk = P.hk;
-  int i0 = (hk - pr) % s;
-  if (i0 < 0) i0 += s;
-  int j0 = (hk - pc) % s;
-  if (j0 < 0) j0 += s;
-  double acc = 0.0;
-  for (int i = i0; i < K; i += s) {
-    const int zr = pr + i - hk;
-    if (zr < 0 || zr >= P.H) continue;
-    const int qr = zr / s;
-    for (int j = j0; j < K; j += s) {
-      const double kv = P.psf[j * K + i];  // transposed kernel
-      const int zc = pc + j - hk;
-      if (kv == 0.0 || zc < 0 || zc >= P.W) continue;
-      const long long idx = B.index_of(qr, zc / s);
-      if (idx < 0) continue;
-      acc = __dadd_rn(acc, __dmul_rn(kv, pooled_kc[idx]));
-    }
-  }
-  return acc;
-}
-
-// g[c][p] += 2 * sum_k warp_{-shift_k}( B^T D^T pooled_k )(p) over the HR pixels the special
-// samples can reach: HR rows [0, R.lo_r) and [R.hi_r, H), and between them HR columns [0, R.lo_c)
-// and [R.hi_c, W)  (R is the BandGeom of the HR-pixel band, B the one of the LR samples).
-// grid: (ceil(R.count()/256), Ca)
-__global__ void __launch_bounds__(256)
-k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, const double* __restrict__ pooled,
-               double* __restrict__ g) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= R.count()) return;
-  int pr, pc;
-  R.sample_of(i, &pr, &pc);
-  const int c = blockIdx.y;
-  const long long cnt = B.count();
-  double acc = 0.0;
-  for (int k = 0; k < P.N; ++k) {
-    const double* __restrict__ pk = pooled + ((size_t)k * P.Ca + c) * cnt;
-    const int Y = P.rowY[(size_t)k * P.H + pr];
-    const int X = 32 * pc + P.nX[k];
-    const int sy = Y >> 5, fy = Y & 31, sx = X >> 5, fx = X & 31;
-    double back;
-    if ((fy | fx) == 0) {
-      back = band_backproject(P, B, pk, sy, sx);
-    } else if (sx >= P.W || sx + 1 < 0 || sy >= P.H || sy + 1 < 0) {
-      back = 0.0;
-    } else {
-      const double wy1 = fy * (1.0 / 32.0), wy0 = (32 - fy) * (1.0 / 32.0);
-      const double wx1 = fx * (1.0 / 32.0), wx0 = (32 - fx) * (1.0 / 32.0);
-      back = __dmul_rn(band_backproject(P, B, pk, sy, sx), wy0 * wx0);
-      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, pk, sy, sx + 1), wy0 * wx1));
-      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, pk, sy + 1, sx), wy1 * wx0));
-      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, pk, sy + 1, sx + 1), wy1 * wx1));
-    }
-    acc = __dadd_rn(acc, __dmul_rn(2.0, back));
-  }
-  const size_t o = (size_t)c * P.H * P.W + (size_t)pr * P.W + pc;
-  g[o] += acc;
-}
-
-// Multi-GPU reduce + all-gather of one rank's band (after every rank has scattered its partial rows
-// into this rank's slots): out_r[band] = sum_s slots[s][band] in fixed slot order (deterministic),
-// written to the gradient buffer of EVERY rank (peer stores over NVLink).
-struct GatherParams {
-  int world, rank;
-  long long band_begin, band_len, band_cap;
-  const double* slots;           // this rank's slot array [world][band_cap]; slot [rank] is unused:
-  const double* own;             // ... this rank's own contribution is its local partial gradient band
-  double* out[SRB_MAX_PEERS];    // gradient buffers of all ranks (peer mappings)
-};
-// Multi-GPU reduce + all-gather of this rank's band: out_r[band] = sum_s partial_s[band] in fixed
-// rank order (deterministic), stored into the gradient buffer of EVERY rank (peer stores over
-// NVLink).  Every block first waits (bounded spin on the local phase-0 flags) until all ranks'
-// contributions have arrived; the last block to finish publishes the total cost locally and raises
-// this rank's phase-1 flag on every rank after a system fence.
-__global__ void __launch_bounds__(256)
-k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long long epoch, unsigned int* done_counter,
-             int* err) {
-  if (threadIdx.x < G.world) {
-    const volatile unsigned long long* f =
-        reinterpret_cast<const volatile unsigned long long*>(G.out[G.rank] + flag_base) + threadIdx.x;
-    unsigned long long spins = 0;
-    while (*f < epoch)
-      if (++spins > (1ull << 24)) {  // seconds: a rank is missing -- give up instead of hanging the GPU
-        *err = 1;
-        break;
-      }
-    __threadfence_system();
-  }
-  __syncthreads();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (((G.band_len | G.band_begin | G.band_cap) & 1) == 0) {
-    // 16-byte accesses: 512 B per warp and store instruction on the link
-    const long long len2 = G.band_len >> 1, cap2 = G.band_cap >> 1, first2 = G.band_begin >> 1;
-    const double2* __restrict__ slots2 = reinterpret_cast<const double2*>(G.slots);
-    const double2* __restrict__ own2 = reinterpret_cast<const double2*>(G.own);
-    for (long long i = i0; i < len2; i += stride) {
-      double2 acc = make_double2(0.0, 0.0);
-      for (int s = 0; s < G.world; ++s) {
-        const double2 v = s == G.rank ? own2[i] : slots2[(long long)s * cap2 + i];
-        acc.x += v.x;
-        acc.y += v.y;
-      }
-      for (int r = 0; r < G.world; ++r) reinterpret_cast<double2*>(G.out[r])[first2 + i] = acc;
-    }
-  } else {
-    for (long long i = i0; i < G.band_len; i += stride) {
-      double acc = 0.0;
-      for (int s = 0; s < G.world; ++s) acc += s == G.rank ? G.own[i] : G.slots[(long long)s * G.band_cap + i];
-      for (int r = 0; r < G.world; ++r) G.out[r][G.band_begin + i] = acc;
-    }
-  }
-  // last block done: total cost + phase-1 flags
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x * gridDim.y - 1;
-  __syncthreads();
-  if (last) {
-    if (threadIdx.x == 0) {
-      double acc = 0.0;
-      for (int r = 0; r < G.world; ++r) acc += G.out[G.rank][n + 1 + r];
-      G.out[G.rank][n] = acc;
-      *done_counter = 0;
-    }
-    if (threadIdx.x < G.world) {
-      __threadfence_system();
-      volatile unsigned long long* f =
-          reinterpret_cast<volatile unsigned long long*>(G.out[threadIdx.x] + flag_base) + G.world + G.rank;
-      *f = epoch;
-    }
-  }
-}
-
-// End of a rank's scatter phase, one block: cost = fixed-order sum of the per-CTA partials (as
-// k_finish_partials), posted into slot [rank] of every rank's cost array, then -- after a system
-// fence -- the phase-0 flag of this rank is raised on every rank.  Runs after k_tile on the same
-// stream, i.e. after all of this rank's gradient rows have been stored to their owners.
-__global__ void __launch_bounds__(1024)
-k_peer_finish_scatter(const double* __restrict__ pd, size_t nd, const double* __restrict__ pr, size_t nr,
-                      double* __restrict__ cost, GatherParams G, long long cost_slot_base, long long flag_base,
-                      unsigned long long epoch) {
-  double a = 0.0, b = 0.0;
-  for (size_t i = threadIdx.x; i < nd; i += blockDim.x) a += pd[i];
-  for (size_t i = threadIdx.x; i < nr; i += blockDim.x) b += pr[i];
-  a = block_sum(a);
-  b = block_sum(b);
-  __shared__ double total;
-  if (threadIdx.x == 0) {
-    cost[0] = a;
-    cost[1] = b;
-    cost[2] = total = a + b;
-  }
-  __syncthreads();
-  if (threadIdx.x < G.world) {
-    G.out[threadIdx.x][cost_slot_base + G.rank] = total;
-    __threadfence_system();
-    volatile unsigned long long* f =
-        reinterpret_cast<volatile unsigned long long*>(G.out[threadIdx.x] + flag_base) + G.rank;
-    *f = epoch;
-  }
-}
-
-// Device-side barrier between the ranks, on flags that live behind every rank's gradient buffer:
-// k_peer_signal (after this rank's kernels of the phase, same stream) publishes `epoch` into slot
-// [phase][rank] of every rank; k_peer_wait spins until all ranks have published it.  The spin is
-// bounded: on timeout it records the failure in *err and returns instead of hanging the GPU.
-__global__ void k_peer_wait(const double* out_local, long long flag_base, int phase, int world,
-                            unsigned long long epoch, int* err) {
-  if (threadIdx.x < world) {
-    const volatile unsigned long long* f =
-        reinterpret_cast<const volatile unsigned long long*>(out_local + flag_base) + phase * world + threadIdx.x;
-    unsigned long long spins = 0;
-    while (*f < epoch) {
-      if (++spins > (1ull << 24)) {  // seconds: a rank is missing
-        *err = 1;
-        break;
-      }
-    }
-    __threadfence_system();
-  }
-}
-
-// cost[0] = sum(data partials), cost[1] = sum(reg partials), cost[2] = their sum (also written to
-// *tail when given): fixed-order, deterministic.
-__global__ void __launch_bounds__(1024)
-k_finish_partials(const double* __restrict__ pd, size_t nd, const double* __restrict__ pr, size_t nr,
-                  double* __restrict__ cost, double* __restrict__ tail) {
-  double a = 0.0, b = 0.0;
-  for (size_t i = threadIdx.x; i < nd; i += blockDim.x) a += pd[i];
-  for (size_t i = threadIdx.x; i < nr; i += blockDim.x) b += pr[i];
-  a = block_sum(a);
-  b = block_sum(b);
-  if (threadIdx.x == 0) {
-    cost[0] = a;
-    cost[1] = b;
-    const double t = a + b;
-    cost[2] = t;
-    if (tail) *tail = t;
-  }
-}
-
-
-// ================================================================================================
-// host side
-// ================================================================================================
-struct TileState {
-  bool supported = false;
-  bool frac = false;
-  int KH = 0;
-  double u[9], v[9];
-  TEntry* d_entries = nullptr;
-  int* d_phase_begin = nullptr;
-  int num_entries = 0;
-  int qoff_min_r = 0, qoff_max_r = 0, qoff_min_c = 0, qoff_max_c = 0;
-  BandGeom band{};       // special LR samples
-  BandGeom reach{};      // HR pixels the special samples can reach
-  bool has_band = false;
-  double* d_pooled = nullptr;  // [N][Ct][band.count()]
-  TFast* d_fast[2] = {nullptr, nullptr};  // tile height 32 / 64; NULL when the model does not qualify
-  bool tma_ok = false;
-  int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
-  void* encode = nullptr;  // cuTensorMapEncodeTiled
-  std::string why;         // why the tile kernel does not cover this model
-};
-
-inline TileState*& tile_state(srb_ctx* c) { return reinterpret_cast<TileState*&>(c->fused); }
-inline const TileState* tile_state(const srb_ctx* c) { return reinterpret_cast<const TileState*>(c->fused); }
-inline bool fused_supported(const srb_ctx* c) {
-  const TileState* st = tile_state(c);
-  return st && st->supported;
-}
-
-inline void fused_teardown(srb_ctx* c) {
-  TileState*& st = tile_state(c);
-  if (!st) return;
-  if (st->d_entries) cudaFree(st->d_entries);
-  if (st->d_phase_begin) cudaFree(st->d_phase_begin);
-  if (st->d_pooled) cudaFree(st->d_pooled);
-  for (TFast* f : st->d_fast)
-    if (f) cudaFree(f);
-  delete st;
-  st = nullptr;
-}
-
-// Rank-1 factorisation psf = u v^T (true for blur_module.cpp:20-22's outer-product Gaussian).
-inline bool factor_separable(const std::vector<double>& psf, int K, double* u, double* v) {
-  int bi = 0, bj = 0;
-  double best = 0.0;
-  for (int i = 0; i < K; ++i)
-    for (int j = 0; j < K; ++j)
-      if (std::fabs(psf[i * K + j]) > best) best = std::fabs(psf[i * K + j]), bi = i, bj = j;
-  if (!(best > 0.0)) return false;
-  const double pivot = psf[bi * K + bj];
-  for (int i = 0; i < K; ++i) u[i] = psf[i * K + bj];
-  for (int j = 0; j < K; ++j) v[j] = psf[bi * K + j] / pivot;
-  for (int i = 0; i < K; ++i)
-    for (int j = 0; j < K; ++j)
-      if (std::fabs(psf[i * K + j] - u[i] * v[j]) > 8.0 * 2.220446049250313e-16 * best) return false;
-  return true;
-}
-
-inline int pymod(int a, int b) {
-  int m = a % b;
-  return m < 0 ? m + b : m;
-}
-inline int pydiv(int a, int b) { return (a - pymod(a, b)) / b; }
-
-// Is LR sample q (one dimension; HR size L, half PSF width hk, scale s) "special" for a frame whose
-// quantised forward / transpose warps are n32 / t32 (1/32 px)?  Regular means: commuting the PSF
-// with the shift changes neither the LR prediction nor the back-projected gradient, and every
-// transpose tap lands inside the image or in the Z halo (PSF half width) of a border tile.
-inline bool sample_is_special(int q, int L, int hk, int s, int n32, int t32) {
-  const int n = n32 >> 5, fa = (n32 & 31) ? 1 : 0;
-  const int nt = t32 >> 5, fb = (t32 & 31) ? 1 : 0;
-  const int p0 = s * q;
-  auto in = [L](int p) { return p >= 0 && p < L; };
-  for (int b = 0; b <= fb; ++b)
-    if (p0 - nt - b < -hk || p0 - nt - b >= L + hk) return true;  // beyond the Z halo of the border tiles
-  for (int i = -hk; i <= hk; ++i) {
-    if (in(p0 + i)) continue;
-    for (int a = 0; a <= fa; ++a)
-      if (in(p0 + i + n + a)) return true;   // forward: window tap clipped before, not after, the shift
-    for (int b = 0; b <= fb; ++b)
-      if (in(p0 + i - nt - b)) return true;  // transpose: G outside the image reaches a pixel inside
-  }
-  return false;
-}
-
-inline srb_status fused_setup(srb_ctx* c) {
-  TileState* st = new TileState();
-  tile_state(c) = st;
-  const Geometry& G = c->g;
-  if (G.K > 9) { st->why = "PSF larger than 9x9"; return SRB_OK; }
-  if (G.s > FT_MAX_SCALE) { st->why = "downsampling scale larger than 8"; return SRB_OK; }
-  if (!c->warps_uniform) { st->why = "a shift sits on a fixed-point rounding boundary"; return SRB_OK; }
-  if (!factor_separable(c->psf_h, G.K, st->u, st->v)) { st->why = "PSF is not separable (rank 1)"; return SRB_OK; }
-  st->KH = G.hk;
-  st->frac = !c->warps_integer;
-  const int s = G.s, hk = G.hk;
-  const int FR = st->frac ? 1 : 0;
-
-  // ---- band of special samples (frame independent: the union over frames) -----------------------
-  int lo[2] = {0, 0}, hi[2] = {G.h, G.w};
-  int max_shift = 0;
-  for (int dim = 0; dim < 2; ++dim) {
-    const int L = dim == 0 ? G.H : G.W, l = dim == 0 ? G.h : G.w;
-    for (int k = 0; k < G.N; ++k) {
-      const int n32 = dim == 0 ? c->warp_fwd[k].nY : c->warp_fwd[k].nX;
-      const int t32 = dim == 0 ? c->warp_tr[k].nY : c->warp_tr[k].nX;
-      max_shift = std::max(max_shift, std::max(std::abs(n32 >> 5), std::abs(t32 >> 5)) + 1);
-      for (int q = 0; q < l; ++q) {
-        if (!sample_is_special(q, L, hk, s, n32, t32)) continue;
-        if (2 * q < l) lo[dim] = std::max(lo[dim], q + 1);
-        else hi[dim] = std::min(hi[dim], q);
-      }
-    }
-    if (lo[dim] >= hi[dim]) { st->why = "image too small for the shifts (every sample is a border sample)"; return SRB_OK; }
-  }
-  st->band = BandGeom{G.h, G.w, lo[0], hi[0], lo[1], hi[1]};
-  st->has_band = st->band.count() > 0;
-  {
-    // HR pixels reachable from the band: PSF half width + the largest shift + 1 around its samples
-    const int m = hk + max_shift + 1;
-    BandGeom R{G.H, G.W, 0, G.H, 0, G.W};
-    if (lo[0] > 0) R.lo_r = std::min(G.H, s * (lo[0] - 1) + m + 1);
-    if (hi[0] < G.h) R.hi_r = std::max(0, s * hi[0] - m);
-    if (lo[1] > 0) R.lo_c = std::min(G.W, s * (lo[1] - 1) + m + 1);
-    if (hi[1] < G.w) R.hi_c = std::max(0, s * hi[1] - m);
-    if (R.lo_r >= R.hi_r || R.lo_c >= R.hi_c) { st->why = "image too small for the shifts"; return SRB_OK; }
-    st->reach = R;
-  }
-
-  // ---- phase lists of the regular samples -------------------------------------------------------
-  const int HB = hk + FR;
-  const int BP = (FT_W + 2 * HB) | 1;
-  std::vector<std::vector<TEntry>> lists((size_t)s * s);
-  const long long hw = (long long)G.h * G.w;
-  bool first = true;
-  for (int k = 0; k < G.N; ++k) {
-    const int nY = c->warp_fwd[k].nY, nX = c->warp_fwd[k].nX;
-    const int tY = c->warp_tr[k].nY, tX = c->warp_tr[k].nX;
-    const int n_r = nY >> 5, n_c = nX >> 5, fy = nY & 31, fx = nX & 31;
-    const int t_r = tY >> 5, t_c = tX >> 5, ty = tY & 31, tx = tX & 31;
-    for (int a = 0; a <= (ty ? 1 : 0); ++a)
-      for (int b = 0; b <= (tx ? 1 : 0); ++b)
-        for (int pr = 0; pr < s; ++pr)
-          for (int pc = 0; pc < s; ++pc) {
-            if (pymod(pr + t_r + a, s) != 0 || pymod(pc + t_c + b, s) != 0) continue;
-            const int qoff_r = pydiv(pr + t_r + a, s), qoff_c = pydiv(pc + t_c + b, s);
-            const int dr = t_r + n_r + a, dc = t_c + n_c + b;
-            // the Bx samples (and their bilinear partners) must stay inside the Bx halo
-            if (dr < -FR || dr > 0 || dc < -FR || dc > 0) {
-              st->why = "forward and transpose warps of a frame quantise too far apart";
-              return SRB_OK;
-            }
-            if (std::abs(qoff_r) > 30000 || std::abs(qoff_c) > 30000) { st->why = "shift too large"; return SRB_OK; }
-            TEntry e;
-            e.yoff = (long long)k * G.Ct * hw + (long long)qoff_r * G.w + qoff_c;
-            e.bxoff = (HB - hk + dr) * BP + (HB - hk + dc);
-            e.qoff = (qoff_r & 0xffff) | (qoff_c << 16);
-            const double wy = a ? ty / 32.0 : (32 - ty) / 32.0, wx = b ? tx / 32.0 : (32 - tx) / 32.0;
-            e.wT = wy * wx;
-            e.fy = (short)fy;
-            e.fx = (short)fx;
-            e.owner = (a == 0 && b == 0) ? 1 : 0;
-            lists[(size_t)pr * s + pc].push_back(e);
-            if (first) {
-              st->qoff_min_r = st->qoff_max_r = qoff_r;
-              st->qoff_min_c = st->qoff_max_c = qoff_c;
-              first = false;
-            }
-            st->qoff_min_r = std::min(st->qoff_min_r, qoff_r); st->qoff_max_r = std::max(st->qoff_max_r, qoff_r);
-            st->qoff_min_c = std::min(st->qoff_min_c, qoff_c); st->qoff_max_c = std::max(st->qoff_max_c, qoff_c);
-          }
-  }
-  std::vector<TEntry> flat;
-  std::vector<int> begin((size_t)s * s + 1, 0);
-  for (size_t ph = 0; ph < lists.size(); ++ph) {
-    begin[ph] = (int)flat.size();
-    flat.insert(flat.end(), lists[ph].begin(), lists[ph].end());
-  }
-  begin[(size_t)s * s] = (int)flat.size();
-  st->num_entries = (int)flat.size();
-  if (st->num_entries > FT_MAX_ENTRIES) { st->why = "too many (frame, tap) entries for shared memory"; return SRB_OK; }
-  if (cudaMalloc((void**)&st->d_entries, (flat.size() + 1) * sizeof(TEntry)) != cudaSuccess ||
-      cudaMalloc((void**)&st->d_phase_begin, begin.size() * sizeof(int)) != cudaSuccess)
-    return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
-  SRB_CUDA_CHECK(c, cudaMemcpy(st->d_entries, flat.data(), flat.size() * sizeof(TEntry), cudaMemcpyHostToDevice));
-  SRB_CUDA_CHECK(c, cudaMemcpy(st->d_phase_begin, begin.data(), begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-  if (st->has_band) {
-    const size_t n = (size_t)G.N * G.Ct * (size_t)st->band.count();
-    if (cudaMalloc((void**)&st->d_pooled, n * sizeof(double)) != cudaSuccess)
-      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (border band residuals)");
-  }
-
-  // ---- table-driven residual pass (TFast): integer shifts, one entry per phase, s | tile size ----
-  {
-    bool one_each = !st->frac && (32 % s == 0);
-    for (size_t ph = 0; one_each && ph < lists.size(); ++ph) one_each = lists[ph].size() == 1;
-    for (int v = 0; one_each && v < 2; ++v) {
-      const int TH = v == 0 ? 32 : 64;
-      const int ZW = FT_W + 2 * hk, ZP = ZW | 1;
-      std::vector<TFast> tab;
-      auto item = [&](int r, int c) {  // Z-region pixel (r, c): tile-relative HR position (r-hk, c-hk)
-        const int pr = r - hk, pc = c - hk;
-        const int dmr = pydiv(pr, s), dmc = pydiv(pc, s);
-        const TEntry& e = lists[(size_t)(pr - dmr * s) * s + (pc - dmc * s)][0];
-        TFast f;
-        f.yrel = e.yoff + (long long)dmr * G.w + dmc;
-        f.bxo = r * BP + c + e.bxoff;
-        f.zo = r * ZP + c;
-        tab.push_back(f);
-      };
-      for (int blk = 0; blk < TH / 32; ++blk)          // pass A: id = blk*(FT_W*s) + rho*FT_W + cm
-        for (int rho = 0; rho < s; ++rho)
-          for (int cm = 0; cm < FT_W; ++cm) item(hk + blk * 32 + rho, hk + cm);
-      for (int rr = 0; rr < 2 * hk; ++rr)             // ring: top + bottom halo rows, full width
-        for (int c = 0; c < ZW; ++c) item(rr < hk ? rr : rr + TH, c);
-      for (int rm = 0; rm < TH; ++rm)                 // ring: left / right halo columns
-        for (int hc = 0; hc < 2 * hk; ++hc) item(hk + rm, hc < hk ? hc : hc + FT_W);
-      if (cudaMalloc((void**)&st->d_fast[v], (tab.size() + 1) * sizeof(TFast)) != cudaSuccess)
-        return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
-      SRB_CUDA_CHECK(c, cudaMemcpy(st->d_fast[v], tab.data(), tab.size() * sizeof(TFast), cudaMemcpyHostToDevice));
-    }
-  }
-
-  // ---- TMA: the tensor-map encoder comes from the driver through the runtime ---------------------
-  {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess && fn != nullptr)
-      st->encode = fn;
-    else
-      (void)cudaGetLastError();
-    st->tma_ok = st->encode != nullptr && (G.W % 2 == 0);  // global strides must be multiples of 16 B
-  }
-  if (const char* e = getenv("SRB_TILE_H")) st->tile_h = atoi(e) == 64 ? 64 : 32;
-  st->supported = true;
-  return SRB_OK;
-}
-
-typedef CUresult (*srb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
-// 3-D tensor map over [planes][H][W] doubles with a (box_w x box_h x 1) box, zero fill outside.
-inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* base, int W, int H, int planes,
-                           int box_w, int box_h) {
-  if (((size_t)base & 15) != 0) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-  const cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * H * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = ((srb_encode_tiled_fn)st->encode)(
-      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-template <int KH, bool FRAC, int TH>
-inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
-  using D = TileDims<KH, FRAC, TH>;
-  const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
-  const TileState* st = tile_state(c);
-  CUtensorMap mx, mw;
-  memset(&mx, 0, sizeof mx);
-  memset(&mw, 0, sizeof mw);
-  P.use_tma = 0;
-  if (st->tma_ok) {
-    bool ok = make_plane_map(st, &mx, P.x, P.W, P.H, P.Ca, D::XW, D::XH);
-    if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, P.Ca, D::WW, D::WH);
-    P.use_tma = ok ? 1 : 0;
-  }
-  static const size_t smem_pad = getenv("SRB_SMEM_PAD") ? (size_t)atoi(getenv("SRB_SMEM_PAD")) : 0;  // occupancy experiments
-  const size_t smem = D::smem_bytes(P.num_entries) + smem_pad;
-  static size_t attr_set[64] = {};
-  if (c->device >= 64 || attr_set[c->device] < smem) {
-    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (c->device < 64) attr_set[c->device] = smem;
-  }
-  if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
-  k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
-  if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
-  return SRB_OK;
-}
-
-// Tile height the current model runs with, and the number of (channel, tile row) units.
-inline int tile_height(const srb_ctx* c) {
-  const TileState* st = tile_state(c);
-  return (c->g.H >= 256 && c->g.W >= 256) ? st->tile_h : 32;
-}
-inline int tile_rows_per_channel(const srb_ctx* c) {
-  const int TH = tile_height(c);
-  return (c->g.H + TH - 1) / TH;
-}
-
-struct TileLayout {  // cost-partial slots of one evaluation
-  size_t nblocks, nband;
-  dim3 bgrid;
-};
-inline TileLayout tile_layout(const srb_ctx* c) {
-  const TileState* st = tile_state(c);
-  const Geometry& G = c->g;
-  TileLayout L;
-  L.nblocks = (size_t)((G.W + FT_W - 1) / FT_W) * tile_rows_per_channel(c) * c->Ca();
-  const long long bcount = st->has_band ? st->band.count() : 0;
-  L.bgrid = dim3((unsigned)((bcount + 255) / 256), (unsigned)(G.N * c->Ca()));
-  L.nband = st->has_band ? (size_t)L.bgrid.x * L.bgrid.y : 0;
-  return L;
-}
-
-// Data term (+ 2-D TV term when fused) of the (channel, tile row) units [unit_begin, unit_end) of
-// the active channel range: writes their gradient rows and their cost partial sums.
-inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, int unit_begin,
-                                   int unit_end, bool* reg_done) {
-  const TileState* st = tile_state(c);
-  const Geometry& G = c->g;
-  const int Ca = c->Ca();
-  TileParams P;
-  P.H = G.H; P.W = G.W; P.h = G.h; P.w = G.w; P.s = G.s; P.Ct = G.Ct; P.c0 = c->c0; P.Ca = Ca;
-  P.sshift = -1;
-  for (int b = 0; b < 4; ++b)
-    if ((1 << b) == G.s) P.sshift = b;
-  P.x = d_x; P.y = c->d_y; P.g = d_g; P.wts = c->d_w;
-  P.entries = st->d_entries; P.phase_begin = st->d_phase_begin; P.num_entries = st->num_entries;
-  P.qoff_min_r = st->qoff_min_r; P.qoff_max_r = st->qoff_max_r;
-  P.qoff_min_c = st->qoff_min_c; P.qoff_max_c = st->qoff_max_c;
-  P.lo_r = st->band.lo_r; P.hi_r = st->band.hi_r; P.lo_c = st->band.lo_c; P.hi_c = st->band.hi_c;
-  for (int i = 0; i < 9; ++i) P.u[i] = i < G.K ? st->u[i] : 0.0, P.v[i] = i < G.K ? st->v[i] : 0.0;
-  P.s2 = (double)G.s * G.s;
-  P.two_s2 = 2.0 * P.s2;
-  P.two_lambda = 2.0 * c->lambda;
-  P.reg_fused = (do_reg && c->reg_kind == SRB_REG_TV) ? 1 : 0;
-  P.row0 = c->reg_row0; P.row1 = c->reg_row1;
-  *reg_done = P.reg_fused != 0;
-  const int TH = tile_height(c);
-  P.tile_rows = tile_rows_per_channel(c);
-  P.fast = st->d_fast[TH == 64 ? 1 : 0];
-  P.unit_begin = unit_begin;
-  const TileLayout L = tile_layout(c);
-  const size_t need = 2 * L.nblocks + L.nband;
-  if (need > c->partial_capacity) {
-    if (c->d_partial) cudaFree(c->d_partial);
-    c->d_partial = nullptr;
-    c->partial_capacity = 0;
-    if (cudaMalloc((void**)&c->d_partial, need * sizeof(double)) != cudaSuccess)
-      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (cost partials)");
-    c->partial_capacity = need;
-  }
-  // layout: [data partials of the tiles][data partials of the band][reg partials of the tiles]
-  P.part_data = c->d_partial;
-  P.part_reg = c->d_partial + L.nblocks + L.nband;
-  srb_status rc = SRB_OK;
-  const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
-  switch (key) {
-#define SRB_TILE_CASE(KH_, FR_)                                                                    \
-    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P, unit_end); break;  \
-    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P, unit_end); break;
-    SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
-    SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
-#undef SRB_TILE_CASE
-    default: return c->fail(SRB_ERR_STATE, "tile kernel: unsupported PSF size");
-  }
-  if (rc != SRB_OK) return rc;
-  c->timing.kernel_launches += 1;
-  return SRB_OK;
-}
-
-// After every unit has been evaluated: the border band (exact, reference order) and the cost.
-// Leaves the data cost in d_cost[0], the fused regularization cost in d_cost[1] and their sum in
-// d_cost[2] (and *tail).
-inline srb_status fused_eval_finish(srb_ctx* c, const double* d_x, double* d_g, double* tail) {
-  const TileState* st = tile_state(c);
-  const Geometry& G = c->g;
-  const int Ca = c->Ca();
-  const TileLayout L = tile_layout(c);
-  if (st->has_band) {
-    GenericParams GP;
-    GP.H = G.H; GP.W = G.W; GP.h = G.h; GP.w = G.w; GP.s = G.s; GP.K = G.K; GP.hk = G.hk;
-    GP.N = G.N; GP.Ca = Ca; GP.Ct = G.Ct; GP.c0 = c->c0;
-    GP.src_r = c->d_src_r; GP.src_c = c->d_src_c; GP.psf = c->d_psf;
-    GP.rowY = c->d_rowY_fwd; GP.nX = c->d_nX_fwd;
-    k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, d_x, c->d_y, st->d_pooled,
-                                                   c->d_partial + L.nblocks);
-    c->timing.kernel_launches += 1;
-    if (d_g) {
-      GP.rowY = c->d_rowY_tr; GP.nX = c->d_nX_tr;
-      const dim3 rgrid((unsigned)((st->reach.count() + 255) / 256), (unsigned)Ca);
-      k_band_adjoint<<<rgrid, 256, 0, c->stream>>>(GP, st->band, st->reach, st->d_pooled, d_g);
-      c->timing.kernel_launches += 1;
-    }
-  }
-  k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, L.nblocks + L.nband,
-                                               c->d_partial + L.nblocks + L.nband, L.nblocks, c->d_cost, tail);
-  c->timing.kernel_launches += 1;
-  return SRB_OK;
-}
-
-inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, double* tail,
-                             bool* reg_done) {
-  const int units = tile_rows_per_channel(c) * c->Ca();
-  srb_status st = fused_eval_units(c, d_x, d_g, do_reg, 0, units, reg_done);
-  if (st != SRB_OK) return st;
-  return fused_eval_finish(c, d_x, d_g, tail);
 }
 
 }  // namespace srb

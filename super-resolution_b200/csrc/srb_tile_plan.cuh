@@ -1,0 +1,468 @@
+// srb_tile_plan.cuh -- host side of the fused tile kernel: planning (which samples are regular, the
+// (frame, tap) entry lists per sub-pixel phase, the border band, the table-driven residual pass),
+// device upload, tensor maps and launches.  plan_tile_model() is pure host code (no CUDA calls) and
+// is what srb_plan() exposes for the CPU tests.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "srb_common.cuh"
+#include "srb_kernels_band.cuh"
+#include "srb_kernels_tile.cuh"
+
+namespace srb {
+
+// ================================================================================================
+// host side
+// ================================================================================================
+// Everything the tile kernel needs to know about a model, computed on the host without touching CUDA.
+struct TilePlan {
+  bool supported = false;
+  std::string why;         // why the tile kernel does not cover this model
+  bool frac = false;       // some shift is fractional: bilinear forward / transpose taps
+  int KH = 0;              // PSF half width
+  double u[9], v[9];       // psf[i][j] = u[i] * v[j]
+  std::vector<TEntry> entries;   // (frame, tap) entries, grouped by sub-pixel phase
+  std::vector<int> phase_begin;  // [s*s + 1]
+  int qoff_min_r = 0, qoff_max_r = 0, qoff_min_c = 0, qoff_max_c = 0;
+  BandGeom band{};         // special LR samples
+  BandGeom reach{};        // HR pixels the special samples can reach
+  bool has_band = false;
+  std::vector<TFast> fast[2];    // table-driven residual pass, tile height 32 / 64 (empty: not applicable)
+};
+
+struct TileState {
+  TilePlan plan;
+  bool supported = false;
+  bool frac = false;
+  int KH = 0;
+  double u[9], v[9];
+  TEntry* d_entries = nullptr;
+  int* d_phase_begin = nullptr;
+  int num_entries = 0;
+  int qoff_min_r = 0, qoff_max_r = 0, qoff_min_c = 0, qoff_max_c = 0;
+  BandGeom band{};       // special LR samples
+  BandGeom reach{};      // HR pixels the special samples can reach
+  bool has_band = false;
+  double* d_pooled = nullptr;  // [N][Ct][band.count()]
+  TFast* d_fast[2] = {nullptr, nullptr};  // tile height 32 / 64; NULL when the model does not qualify
+  bool tma_ok = false;
+  int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
+  void* encode = nullptr;  // cuTensorMapEncodeTiled
+  std::string why;         // why the tile kernel does not cover this model
+};
+
+inline TileState*& tile_state(srb_ctx* c) { return reinterpret_cast<TileState*&>(c->fused); }
+inline const TileState* tile_state(const srb_ctx* c) { return reinterpret_cast<const TileState*>(c->fused); }
+inline bool fused_supported(const srb_ctx* c) {
+  const TileState* st = tile_state(c);
+  return st && st->supported;
+}
+
+inline void fused_teardown(srb_ctx* c) {
+  TileState*& st = tile_state(c);
+  if (!st) return;
+  if (st->d_entries) cudaFree(st->d_entries);
+  if (st->d_phase_begin) cudaFree(st->d_phase_begin);
+  if (st->d_pooled) cudaFree(st->d_pooled);
+  for (TFast* f : st->d_fast)
+    if (f) cudaFree(f);
+  delete st;
+  st = nullptr;
+}
+
+// Rank-1 factorisation psf = u v^T (true for blur_module.cpp:20-22's outer-product Gaussian).
+inline bool factor_separable(const std::vector<double>& psf, int K, double* u, double* v) {
+  int bi = 0, bj = 0;
+  double best = 0.0;
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j)
+      if (std::fabs(psf[i * K + j]) > best) best = std::fabs(psf[i * K + j]), bi = i, bj = j;
+  if (!(best > 0.0)) return false;
+  const double pivot = psf[bi * K + bj];
+  for (int i = 0; i < K; ++i) u[i] = psf[i * K + bj];
+  for (int j = 0; j < K; ++j) v[j] = psf[bi * K + j] / pivot;
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j < K; ++j)
+      if (std::fabs(psf[i * K + j] - u[i] * v[j]) > 8.0 * 2.220446049250313e-16 * best) return false;
+  return true;
+}
+
+inline int pymod(int a, int b) {
+  int m = a % b;
+  return m < 0 ? m + b : m;
+}
+inline int pydiv(int a, int b) { return (a - pymod(a, b)) / b; }
+
+// Is LR sample q (one dimension; HR size L, half PSF width hk, scale s) "special" for a frame whose
+// quantised forward / transpose warps are n32 / t32 (1/32 px)?  Regular means: commuting the PSF
+// with the shift changes neither the LR prediction nor the back-projected gradient, and every
+// transpose tap lands inside the image or in the Z halo (PSF half width) of a border tile.
+inline bool sample_is_special(int q, int L, int hk, int s, int n32, int t32) {
+  const int n = n32 >> 5, fa = (n32 & 31) ? 1 : 0;
+  const int nt = t32 >> 5, fb = (t32 & 31) ? 1 : 0;
+  const int p0 = s * q;
+  auto in = [L](int p) { return p >= 0 && p < L; };
+  for (int b = 0; b <= fb; ++b)
+    if (p0 - nt - b < -hk || p0 - nt - b >= L + hk) return true;  // beyond the Z halo of the border tiles
+  for (int i = -hk; i <= hk; ++i) {
+    if (in(p0 + i)) continue;
+    for (int a = 0; a <= fa; ++a)
+      if (in(p0 + i + n + a)) return true;   // forward: window tap clipped before, not after, the shift
+    for (int b = 0; b <= fb; ++b)
+      if (in(p0 + i - nt - b)) return true;  // transpose: G outside the image reaches a pixel inside
+  }
+  return false;
+}
+
+// Pure host planning.  warp_fwd / warp_tr are the quantised forward / transpose warps per frame.
+inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h, const std::vector<WarpQ>& warp_fwd,
+                            const std::vector<WarpQ>& warp_tr, bool warps_uniform, bool warps_integer, TilePlan* st) {
+  if (G.K > 9) { st->why = "PSF larger than 9x9"; return; }
+  if (G.s > FT_MAX_SCALE) { st->why = "downsampling scale larger than 8"; return; }
+  if (!warps_uniform) { st->why = "a shift sits on a fixed-point rounding boundary"; return; }
+  if (!factor_separable(psf_h, G.K, st->u, st->v)) { st->why = "PSF is not separable (rank 1)"; return; }
+  st->KH = G.hk;
+  st->frac = !warps_integer;
+  const int s = G.s, hk = G.hk;
+  const int FR = st->frac ? 1 : 0;
+
+  // ---- band of special samples (frame independent: the union over frames) -----------------------
+  int lo[2] = {0, 0}, hi[2] = {G.h, G.w};
+  int max_shift = 0;
+  for (int dim = 0; dim < 2; ++dim) {
+    const int L = dim == 0 ? G.H : G.W, l = dim == 0 ? G.h : G.w;
+    for (int k = 0; k < G.N; ++k) {
+      const int n32 = dim == 0 ? warp_fwd[k].nY : warp_fwd[k].nX;
+      const int t32 = dim == 0 ? warp_tr[k].nY : warp_tr[k].nX;
+      max_shift = std::max(max_shift, std::max(std::abs(n32 >> 5), std::abs(t32 >> 5)) + 1);
+      for (int q = 0; q < l; ++q) {
+        if (!sample_is_special(q, L, hk, s, n32, t32)) continue;
+        if (2 * q < l) lo[dim] = std::max(lo[dim], q + 1);
+        else hi[dim] = std::min(hi[dim], q);
+      }
+    }
+    if (lo[dim] >= hi[dim]) { st->why = "image too small for the shifts (every sample is a border sample)"; return; }
+  }
+  st->band = BandGeom{G.h, G.w, lo[0], hi[0], lo[1], hi[1]};
+  st->has_band = st->band.count() > 0;
+  {
+    // HR pixels reachable from the band: PSF half width + the largest shift + 1 around its samples
+    const int m = hk + max_shift + 1;
+    BandGeom R{G.H, G.W, 0, G.H, 0, G.W};
+    if (lo[0] > 0) R.lo_r = std::min(G.H, s * (lo[0] - 1) + m + 1);
+    if (hi[0] < G.h) R.hi_r = std::max(0, s * hi[0] - m);
+    if (lo[1] > 0) R.lo_c = std::min(G.W, s * (lo[1] - 1) + m + 1);
+    if (hi[1] < G.w) R.hi_c = std::max(0, s * hi[1] - m);
+    if (R.lo_r >= R.hi_r || R.lo_c >= R.hi_c) { st->why = "image too small for the shifts"; return; }
+    st->reach = R;
+  }
+
+  // ---- phase lists of the regular samples -------------------------------------------------------
+  const int HB = hk + FR;
+  const int BP = (FT_W + 2 * HB) | 1;
+  std::vector<std::vector<TEntry>> lists((size_t)s * s);
+  const long long hw = (long long)G.h * G.w;
+  bool first = true;
+  for (int k = 0; k < G.N; ++k) {
+    const int nY = warp_fwd[k].nY, nX = warp_fwd[k].nX;
+    const int tY = warp_tr[k].nY, tX = warp_tr[k].nX;
+    const int n_r = nY >> 5, n_c = nX >> 5, fy = nY & 31, fx = nX & 31;
+    const int t_r = tY >> 5, t_c = tX >> 5, ty = tY & 31, tx = tX & 31;
+    for (int a = 0; a <= (ty ? 1 : 0); ++a)
+      for (int b = 0; b <= (tx ? 1 : 0); ++b)
+        for (int pr = 0; pr < s; ++pr)
+          for (int pc = 0; pc < s; ++pc) {
+            if (pymod(pr + t_r + a, s) != 0 || pymod(pc + t_c + b, s) != 0) continue;
+            const int qoff_r = pydiv(pr + t_r + a, s), qoff_c = pydiv(pc + t_c + b, s);
+            const int dr = t_r + n_r + a, dc = t_c + n_c + b;
+            // the Bx samples (and their bilinear partners) must stay inside the Bx halo
+            if (dr < -FR || dr > 0 || dc < -FR || dc > 0) {
+              st->why = "forward and transpose warps of a frame quantise too far apart";
+              return;
+            }
+            if (std::abs(qoff_r) > 30000 || std::abs(qoff_c) > 30000) { st->why = "shift too large"; return; }
+            TEntry e;
+            e.yoff = (long long)k * G.Ct * hw + (long long)qoff_r * G.w + qoff_c;
+            e.bxoff = (HB - hk + dr) * BP + (HB - hk + dc);
+            e.qoff = (qoff_r & 0xffff) | (qoff_c << 16);
+            const double wy = a ? ty / 32.0 : (32 - ty) / 32.0, wx = b ? tx / 32.0 : (32 - tx) / 32.0;
+            e.wT = wy * wx;
+            e.fy = (short)fy;
+            e.fx = (short)fx;
+            e.owner = (a == 0 && b == 0) ? 1 : 0;
+            lists[(size_t)pr * s + pc].push_back(e);
+            if (first) {
+              st->qoff_min_r = st->qoff_max_r = qoff_r;
+              st->qoff_min_c = st->qoff_max_c = qoff_c;
+              first = false;
+            }
+            st->qoff_min_r = std::min(st->qoff_min_r, qoff_r); st->qoff_max_r = std::max(st->qoff_max_r, qoff_r);
+            st->qoff_min_c = std::min(st->qoff_min_c, qoff_c); st->qoff_max_c = std::max(st->qoff_max_c, qoff_c);
+          }
+  }
+  std::vector<TEntry>& flat = st->entries;
+  std::vector<int>& begin = st->phase_begin;
+  begin.assign((size_t)s * s + 1, 0);
+  for (size_t ph = 0; ph < lists.size(); ++ph) {
+    begin[ph] = (int)flat.size();
+    flat.insert(flat.end(), lists[ph].begin(), lists[ph].end());
+  }
+  begin[(size_t)s * s] = (int)flat.size();
+  if ((int)flat.size() > FT_MAX_ENTRIES) { st->why = "too many (frame, tap) entries for shared memory"; return; }
+
+  // ---- table-driven residual pass (TFast): integer shifts, one entry per phase, s | tile size ----
+  {
+    bool one_each = !st->frac && (32 % s == 0);
+    for (size_t ph = 0; one_each && ph < lists.size(); ++ph) one_each = lists[ph].size() == 1;
+    for (int v = 0; one_each && v < 2; ++v) {
+      const int TH = v == 0 ? 32 : 64;
+      const int ZW = FT_W + 2 * hk, ZP = ZW | 1;
+      std::vector<TFast> tab;
+      auto item = [&](int r, int c) {  // Z-region pixel (r, c): tile-relative HR position (r-hk, c-hk)
+        const int pr = r - hk, pc = c - hk;
+        const int dmr = pydiv(pr, s), dmc = pydiv(pc, s);
+        const TEntry& e = lists[(size_t)(pr - dmr * s) * s + (pc - dmc * s)][0];
+        TFast f;
+        f.yrel = e.yoff + (long long)dmr * G.w + dmc;
+        f.bxo = r * BP + c + e.bxoff;
+        f.zo = r * ZP + c;
+        tab.push_back(f);
+      };
+      for (int blk = 0; blk < TH / 32; ++blk)          // pass A: id = blk*(FT_W*s) + rho*FT_W + cm
+        for (int rho = 0; rho < s; ++rho)
+          for (int cm = 0; cm < FT_W; ++cm) item(hk + blk * 32 + rho, hk + cm);
+      for (int rr = 0; rr < 2 * hk; ++rr)             // ring: top + bottom halo rows, full width
+        for (int c = 0; c < ZW; ++c) item(rr < hk ? rr : rr + TH, c);
+      for (int rm = 0; rm < TH; ++rm)                 // ring: left / right halo columns
+        for (int hc = 0; hc < 2 * hk; ++hc) item(hk + rm, hc < hk ? hc : hc + FT_W);
+      st->fast[v] = tab;
+    }
+  }
+
+  st->supported = true;
+}
+
+// Plans the model and uploads the tables.  A model the tile kernel does not cover leaves
+// supported == false (the reference-order kernels run instead) and is not an error.
+inline srb_status fused_setup(srb_ctx* c) {
+  TileState* st = new TileState();
+  tile_state(c) = st;
+  const Geometry& G = c->g;
+  TilePlan& plan = st->plan;
+  plan_tile_model(G, c->psf_h, c->warp_fwd, c->warp_tr, c->warps_uniform, c->warps_integer, &plan);
+  st->why = plan.why;
+  if (!plan.supported) return SRB_OK;
+  st->frac = plan.frac;
+  st->KH = plan.KH;
+  for (int i = 0; i < 9; ++i) st->u[i] = plan.u[i], st->v[i] = plan.v[i];
+  st->num_entries = (int)plan.entries.size();
+  st->qoff_min_r = plan.qoff_min_r; st->qoff_max_r = plan.qoff_max_r;
+  st->qoff_min_c = plan.qoff_min_c; st->qoff_max_c = plan.qoff_max_c;
+  st->band = plan.band;
+  st->reach = plan.reach;
+  st->has_band = plan.has_band;
+  if (cudaMalloc((void**)&st->d_entries, (plan.entries.size() + 1) * sizeof(TEntry)) != cudaSuccess ||
+      cudaMalloc((void**)&st->d_phase_begin, plan.phase_begin.size() * sizeof(int)) != cudaSuccess)
+    return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
+  SRB_CUDA_CHECK(c, cudaMemcpy(st->d_entries, plan.entries.data(), plan.entries.size() * sizeof(TEntry), cudaMemcpyHostToDevice));
+  SRB_CUDA_CHECK(c, cudaMemcpy(st->d_phase_begin, plan.phase_begin.data(), plan.phase_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (st->has_band) {
+    const size_t n = (size_t)G.N * G.Ct * (size_t)st->band.count();
+    if (cudaMalloc((void**)&st->d_pooled, n * sizeof(double)) != cudaSuccess)
+      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (border band residuals)");
+  }
+  for (int v = 0; v < 2; ++v) {
+    if (plan.fast[v].empty()) continue;
+    if (cudaMalloc((void**)&st->d_fast[v], (plan.fast[v].size() + 1) * sizeof(TFast)) != cudaSuccess)
+      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
+    SRB_CUDA_CHECK(c, cudaMemcpy(st->d_fast[v], plan.fast[v].data(), plan.fast[v].size() * sizeof(TFast), cudaMemcpyHostToDevice));
+  }
+  // ---- TMA: the tensor-map encoder comes from the driver through the runtime ---------------------
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess && fn != nullptr)
+      st->encode = fn;
+    else
+      (void)cudaGetLastError();
+    st->tma_ok = st->encode != nullptr && (G.W % 2 == 0);  // global strides must be multiples of 16 B
+  }
+  if (const char* e = getenv("SRB_TILE_H")) st->tile_h = atoi(e) == 64 ? 64 : 32;
+  st->supported = true;
+  return SRB_OK;
+}
+
+typedef CUresult (*srb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+// 3-D tensor map over [planes][H][W] doubles with a (box_w x box_h x 1) box, zero fill outside.
+inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* base, int W, int H, int planes,
+                           int box_w, int box_h) {
+  if (((size_t)base & 15) != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * H * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = ((srb_encode_tiled_fn)st->encode)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int KH, bool FRAC, int TH>
+inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
+  using D = TileDims<KH, FRAC, TH>;
+  const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
+  const TileState* st = tile_state(c);
+  CUtensorMap mx, mw;
+  memset(&mx, 0, sizeof mx);
+  memset(&mw, 0, sizeof mw);
+  P.use_tma = 0;
+  if (st->tma_ok) {
+    bool ok = make_plane_map(st, &mx, P.x, P.W, P.H, P.Ca, D::XW, D::XH);
+    if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, P.Ca, D::WW, D::WH);
+    P.use_tma = ok ? 1 : 0;
+  }
+  static const size_t smem_pad = getenv("SRB_SMEM_PAD") ? (size_t)atoi(getenv("SRB_SMEM_PAD")) : 0;  // occupancy experiments
+  const size_t smem = D::smem_bytes(P.num_entries) + smem_pad;
+  static size_t attr_set[64] = {};
+  if (c->device >= 64 || attr_set[c->device] < smem) {
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->device < 64) attr_set[c->device] = smem;
+  }
+  if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
+  k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
+  if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
+  return SRB_OK;
+}
+
+// Tile height the current model runs with, and the number of (channel, tile row) units.
+inline int tile_height(const srb_ctx* c) {
+  const TileState* st = tile_state(c);
+  return (c->g.H >= 256 && c->g.W >= 256) ? st->tile_h : 32;
+}
+inline int tile_rows_per_channel(const srb_ctx* c) {
+  const int TH = tile_height(c);
+  return (c->g.H + TH - 1) / TH;
+}
+
+struct TileLayout {  // cost-partial slots of one evaluation
+  size_t nblocks, nband;
+  dim3 bgrid;
+};
+inline TileLayout tile_layout(const srb_ctx* c) {
+  const TileState* st = tile_state(c);
+  const Geometry& G = c->g;
+  TileLayout L;
+  L.nblocks = (size_t)((G.W + FT_W - 1) / FT_W) * tile_rows_per_channel(c) * c->Ca();
+  const long long bcount = st->has_band ? st->band.count() : 0;
+  L.bgrid = dim3((unsigned)((bcount + 255) / 256), (unsigned)(G.N * c->Ca()));
+  L.nband = st->has_band ? (size_t)L.bgrid.x * L.bgrid.y : 0;
+  return L;
+}
+
+// Data term (+ 2-D TV term when fused) of the (channel, tile row) units [unit_begin, unit_end) of
+// the active channel range: writes their gradient rows and their cost partial sums.
+inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, int unit_begin,
+                                   int unit_end, bool* reg_done) {
+  const TileState* st = tile_state(c);
+  const Geometry& G = c->g;
+  const int Ca = c->Ca();
+  TileParams P;
+  P.H = G.H; P.W = G.W; P.h = G.h; P.w = G.w; P.s = G.s; P.Ct = G.Ct; P.c0 = c->c0; P.Ca = Ca;
+  P.sshift = -1;
+  for (int b = 0; b < 4; ++b)
+    if ((1 << b) == G.s) P.sshift = b;
+  P.x = d_x; P.y = c->d_y; P.g = d_g; P.wts = c->d_w;
+  P.entries = st->d_entries; P.phase_begin = st->d_phase_begin; P.num_entries = st->num_entries;
+  P.qoff_min_r = st->qoff_min_r; P.qoff_max_r = st->qoff_max_r;
+  P.qoff_min_c = st->qoff_min_c; P.qoff_max_c = st->qoff_max_c;
+  P.lo_r = st->band.lo_r; P.hi_r = st->band.hi_r; P.lo_c = st->band.lo_c; P.hi_c = st->band.hi_c;
+  for (int i = 0; i < 9; ++i) P.u[i] = i < G.K ? st->u[i] : 0.0, P.v[i] = i < G.K ? st->v[i] : 0.0;
+  P.s2 = (double)G.s * G.s;
+  P.two_s2 = 2.0 * P.s2;
+  P.two_lambda = 2.0 * c->lambda;
+  P.reg_fused = (do_reg && c->reg_kind == SRB_REG_TV) ? 1 : 0;
+  P.row0 = c->reg_row0; P.row1 = c->reg_row1;
+  *reg_done = P.reg_fused != 0;
+  const int TH = tile_height(c);
+  P.tile_rows = tile_rows_per_channel(c);
+  P.fast = st->d_fast[TH == 64 ? 1 : 0];
+  P.unit_begin = unit_begin;
+  const TileLayout L = tile_layout(c);
+  const size_t need = 2 * L.nblocks + L.nband;
+  if (need > c->partial_capacity) {
+    if (c->d_partial) cudaFree(c->d_partial);
+    c->d_partial = nullptr;
+    c->partial_capacity = 0;
+    if (cudaMalloc((void**)&c->d_partial, need * sizeof(double)) != cudaSuccess)
+      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (cost partials)");
+    c->partial_capacity = need;
+  }
+  // layout: [data partials of the tiles][data partials of the band][reg partials of the tiles]
+  P.part_data = c->d_partial;
+  P.part_reg = c->d_partial + L.nblocks + L.nband;
+  srb_status rc = SRB_OK;
+  const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
+  switch (key) {
+#define SRB_TILE_CASE(KH_, FR_)                                                                    \
+    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P, unit_end); break;  \
+    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P, unit_end); break;
+    SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
+    SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
+#undef SRB_TILE_CASE
+    default: return c->fail(SRB_ERR_STATE, "tile kernel: unsupported PSF size");
+  }
+  if (rc != SRB_OK) return rc;
+  c->timing.kernel_launches += 1;
+  return SRB_OK;
+}
+
+// After every unit has been evaluated: the border band (exact, reference order) and the cost.
+// Leaves the data cost in d_cost[0], the fused regularization cost in d_cost[1] and their sum in
+// d_cost[2] (and *tail).
+inline srb_status fused_eval_finish(srb_ctx* c, const double* d_x, double* d_g, double* tail) {
+  const TileState* st = tile_state(c);
+  const Geometry& G = c->g;
+  const int Ca = c->Ca();
+  const TileLayout L = tile_layout(c);
+  if (st->has_band) {
+    GenericParams GP;
+    GP.H = G.H; GP.W = G.W; GP.h = G.h; GP.w = G.w; GP.s = G.s; GP.K = G.K; GP.hk = G.hk;
+    GP.N = G.N; GP.Ca = Ca; GP.Ct = G.Ct; GP.c0 = c->c0;
+    GP.src_r = c->d_src_r; GP.src_c = c->d_src_c; GP.psf = c->d_psf;
+    GP.rowY = c->d_rowY_fwd; GP.nX = c->d_nX_fwd;
+    k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, d_x, c->d_y, st->d_pooled,
+                                                   c->d_partial + L.nblocks);
+    c->timing.kernel_launches += 1;
+    if (d_g) {
+      GP.rowY = c->d_rowY_tr; GP.nX = c->d_nX_tr;
+      const dim3 rgrid((unsigned)((st->reach.count() + 255) / 256), (unsigned)Ca);
+      k_band_adjoint<<<rgrid, 256, 0, c->stream>>>(GP, st->band, st->reach, st->d_pooled, d_g);
+      c->timing.kernel_launches += 1;
+    }
+  }
+  k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, L.nblocks + L.nband,
+                                               c->d_partial + L.nblocks + L.nband, L.nblocks, c->d_cost, tail);
+  c->timing.kernel_launches += 1;
+  return SRB_OK;
+}
+
+inline srb_status fused_eval(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, double* tail,
+                             bool* reg_done) {
+  const int units = tile_rows_per_channel(c) * c->Ca();
+  srb_status st = fused_eval_units(c, d_x, d_g, do_reg, 0, units, reg_done);
+  if (st != SRB_OK) return st;
+  return fused_eval_finish(c, d_x, d_g, tail);
+}
+
+
+}  // namespace srb

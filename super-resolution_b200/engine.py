@@ -23,6 +23,9 @@ _STATUS = {0: "SRB_OK", 1: "SRB_ERR_INVALID", 2: "SRB_ERR_CUDA", 3: "SRB_ERR_GEO
 SIGNATURES = {
     "srb_version": (C.c_char_p, []),
     "srb_device_count": (C.c_int, []),
+    "srb_plan": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "srb_quantize_shift": (C.c_int, [C.c_double]),
+    "srb_sample_is_special": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "srb_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_ctx_p)]),
     "srb_destroy": (None, [_ctx_p]),
     "srb_last_error": (C.c_char_p, [_ctx_p]),
@@ -80,6 +83,15 @@ class Timing(C.Structure):
                 ("last_eval_d2h_ms", C.c_double), ("num_evals", C.c_ulonglong),
                 ("kernel_launches", C.c_ulonglong), ("algorithmic_bytes_per_eval", C.c_ulonglong),
                 ("last_main_kernel_ms", C.c_double)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("hr_height", C.c_int), ("hr_width", C.c_int), ("warps_uniform", C.c_int),
+                ("warps_integer", C.c_int), ("fused", C.c_int), ("fractional", C.c_int),
+                ("psf_half", C.c_int), ("num_entries", C.c_int), ("min_entries_per_phase", C.c_int),
+                ("max_entries_per_phase", C.c_int), ("band_lo_r", C.c_int), ("band_hi_r", C.c_int),
+                ("band_lo_c", C.c_int), ("band_hi_c", C.c_int), ("table_driven", C.c_int),
+                ("why", C.c_char * 160)]
 
 
 class SrbError(RuntimeError):
@@ -393,3 +405,30 @@ def ipc_open(handle):
 
 def ipc_close(ptr):
     load_library().srb_ipc_close(C.c_void_p(ptr))
+
+
+def plan(lr_shape, scale, psf=None, shifts=None):
+    """srb_plan: what srb_create would decide for this model -- host only, no CUDA device needed.
+    Returns a dict; raises SrbError for descriptions the reference would CHECK-fail on."""
+    lib = load_library()
+    N, Cn, h, w = (int(v) for v in lr_shape)
+    psf_a = None if psf is None else _f64(psf)
+    sh = None if shifts is None else _f64(shifts).reshape(-1, 2)
+    desc = ModelDesc(h, w, Cn, N, int(scale), 0 if psf_a is None else psf_a.shape[0],
+                     None if psf_a is None else psf_a.ctypes.data_as(_dp),
+                     None if sh is None else sh.ctypes.data_as(_dp))
+    info = PlanInfo()
+    st = lib.srb_plan(C.byref(desc), C.byref(info))
+    if st != 0:
+        raise SrbError(st, info.why.decode())
+    out = {name: getattr(info, name) for name, _ in PlanInfo._fields_}
+    out["why"] = info.why.decode()
+    return out
+
+
+def quantize_shift(d):
+    return load_library().srb_quantize_shift(float(d))
+
+
+def sample_is_special(q, hr_size, psf_half, scale, shift):
+    return bool(load_library().srb_sample_is_special(int(q), int(hr_size), int(psf_half), int(scale), float(shift)))

@@ -1,0 +1,101 @@
+"""Host logic of the fused path, on CPU (no GPU needed): srb_plan / srb_quantize_shift /
+srb_sample_is_special are pure host code in libsrb200.so.
+
+The fused tile kernel commutes the PSF with the shift, which is exact only for
+"regular" LR samples; the planner must flag every sample for which it is not.  That rule is checked
+here against brute force with the CPU oracle: a sample is TRULY special when moving the blur across
+the warp changes its LR prediction (forward) or its back-projected HR image (transpose)."""
+import importlib
+
+import numpy as np
+import pytest
+
+srb = importlib.import_module("super-resolution_b200")
+wl = importlib.import_module("super-resolution_b200.workloads")
+
+
+def test_warp_quantisation_matches_the_oracle(oracle):
+    """cv::warpAffine's fixed-point translation: library host code == oracle (pinned against cv2)."""
+    rng = np.random.default_rng(0)
+    shifts = np.concatenate([np.linspace(-3, 3, 1201), rng.uniform(-40, 40, 500), [0.015625, -0.015625, 1 / 64 + 1e-12]])
+    for d in shifts:
+        # the library quantises the FORWARD warp of shift d: source offset of -d
+        assert srb.quantize_shift(d) == oracle.warp_quantize(d), d
+
+
+def test_plans_of_the_baseline_configurations():
+    expect = {1: dict(frac=0, kh=1, per_phase=(1, 1), table=1),
+              2: dict(frac=0, kh=2, per_phase=(0, 1), table=0),     # 9 frames over 16 phases
+              3: dict(frac=0, kh=3, per_phase=(1, 1), table=1),
+              4: dict(frac=0, kh=2, per_phase=(2, 2), table=0),     # 8 frames over 4 phases
+              5: dict(frac=0, kh=4, per_phase=(4, 4), table=0)}     # 64 frames over 16 phases
+    for cfg, ex in expect.items():
+        cf = wl.CONFIGS[cfg]
+        s = cf["s"]
+        shifts = np.array(cf["shifts"], float) if "shifts" in cf else wl.default_shifts(cf["N"], s)
+        p = srb.plan((cf["N"], cf["C"], cf["H"] // s, cf["W"] // s), s, wl.gaussian_psf(cf["K"], cf["sigma"]), shifts)
+        assert p["fused"] == 1, (cfg, p["why"])
+        assert (p["hr_height"], p["hr_width"]) == (cf["H"], cf["W"])
+        assert p["fractional"] == ex["frac"] and p["psf_half"] == ex["kh"]
+        assert (p["min_entries_per_phase"], p["max_entries_per_phase"]) == ex["per_phase"], (cfg, p)
+        assert p["table_driven"] == ex["table"]
+        assert p["num_entries"] == cf["N"]
+        # default shifts are >= 0 and at most s - 1: at most a thin band at the top / left
+        assert p["band_hi_r"] >= cf["H"] // s - 2 and p["band_hi_c"] >= cf["W"] // s - 2
+        assert p["band_lo_r"] <= 1 and p["band_lo_c"] <= 1
+
+
+def test_models_the_tile_kernel_does_not_cover_are_reported_not_failed():
+    psf = wl.gaussian_psf(5, 1.5)
+    rough = psf.copy()
+    rough[0, 1] += 0.01                                   # not rank 1
+    p = srb.plan((2, 1, 16, 16), 2, rough, [(0, 0), (1, 0)])
+    assert p["fused"] == 0 and "separable" in p["why"]
+    p = srb.plan((2, 1, 16, 16), 2, wl.gaussian_psf(11, 3.0), [(0, 0), (1, 0)])
+    assert p["fused"] == 0 and "9x9" in p["why"]
+    p = srb.plan((2, 1, 4, 4), 2, psf, [(0, 0), (7, 0)])  # shift larger than the image allows
+    assert p["fused"] == 0 and "small" in p["why"]
+    with pytest.raises(srb.SrbError):                      # the reference CHECK-fails on these
+        srb.plan((0, 1, 4, 4), 2, psf, None)
+    with pytest.raises(srb.SrbError):
+        srb.plan((1, 1, 4, 4), 2, wl.gaussian_psf(4, 1.0), None)
+
+
+@pytest.mark.parametrize("s,K", [(2, 5), (4, 7), (3, 3), (2, 9)])
+def test_special_sample_rule_covers_brute_force(oracle, s, K):
+    """Vertical shifts only: for every LR row q, (truly special by brute force) => (planner flags it)."""
+    o = oracle
+    h, w = 14, 6
+    H, W = h * s, w * s
+    hk = K // 2
+    psf = wl.gaussian_psf(K, 0.4 * K)
+    rng = np.random.default_rng(s * 10 + K)
+    x = rng.random((H, W)) + 0.5
+    flagged_total = truly_total = 0
+    P = s * (hk + 6)                                  # zero margin, a multiple of s
+    xp = np.pad(x, P)                                 # the kernel blurs the zero-EXTENDED estimate ...
+    bx_ext = o.filter2d(xp, psf)                      # ... so Bx also exists just outside the image
+    for dy in [0.0, 1.0, -1.0, 2.0, -3.0, float(hk), float(-hk), hk + 1.0, -(hk + 2.0), 0.3, -0.3, 1.7, -2.4, 0.5]:
+        m = o.Model(s, psf, [(0.0, dy)])
+        # forward: D B M x (reference) vs D M (B x) evaluated on the extended domain (tile kernel)
+        exact = o.forward(m, 0, x)
+        commuted = o.warp_shift(bx_ext, 0.0, dy)[P:P + H:s, P:P + W:s]
+        fwd_special = np.abs(exact - commuted).max(axis=1) > 1e-12
+        # transpose: M^T B^T D^T e_q (reference) vs B^T (M^T D^T e_q) on the extended domain, cropped
+        tr_special = np.zeros(h, bool)
+        for q in range(h):
+            e = np.zeros((h, w))
+            e[q, 2] = 1.0                             # column 2: away from the left / right border
+            exact_t = o.transpose(m, 0, e)
+            up = np.zeros((H + 2 * P, W + 2 * P))
+            up[P + s * q, P + s * 2] = 1.0            # zero insertion
+            commuted_t = o.filter2d(o.warp_shift(up, 0.0, -dy), psf.T.copy())[P:P + H, P:P + W]
+            tr_special[q] = np.abs(exact_t - commuted_t).max() > 1e-12
+        for q in range(h):
+            flagged = srb.sample_is_special(q, H, hk, s, dy)
+            truly = bool(fwd_special[q] or tr_special[q])
+            assert flagged or not truly, (s, K, dy, q)
+            flagged_total += flagged
+            truly_total += truly
+    assert truly_total > 0                      # the cases do exercise the rule ...
+    assert flagged_total <= 4 * truly_total + 40  # ... and the rule stays a thin band, not everything
