@@ -230,7 +230,8 @@ def main():
         try:
             with torch.cuda.stream(stream):
                 peer = sharding.PeerObjective(eng, n, dist, srb)
-        except srb.SrbError as err:
+        except Exception as err:   # all ranks raise together (sharding.PeerObjective)
+            peer = None
             if rank == 0:
                 print("peer path not available (%s); using the NCCL allreduce path" % err, file=sys.stderr)
 
@@ -332,8 +333,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cf["name"], "frames_per_gpu": n_local, "frames_total": n_total,
                        "partition": ("single GPU" if world == 1 else
-                                     "frame shard; reduce-scatter fused into the tile kernel over NVLink peer "
-                                     "memory + gather (C*P+1 f64 per step)" if peer is not None else
+                                     "frame shard; band-pipelined tile kernel + copy-engine reduce-scatter over "
+                                     "NVLink peer memory + sum/all-gather kernel (C*P+1 f64 per step)" if peer is not None else
                                      "frame shard + 1 NCCL allreduce(C*P+1 f64) per step, pipelined in %d slices"
                                      % args.chunks),
                        "kernel_path": path_name,

@@ -131,13 +131,16 @@ class _DevArray:
 
 
 class PeerObjective:
-    """cost + gradient of the full objective with the reduce-scatter FUSED into the tile kernel:
-    each rank's kernel stores its partial gradient rows directly into the memory of the rank that
-    owns them (CUDA-IPC peer mappings over NVLink / NVSwitch), the owners sum their band in fixed
-    rank order and store the result into every rank's gradient buffer (the all-gather half).  The
-    two barriers between the phases are flags in peer memory (k_peer_signal / k_peer_wait, bounded
-    spin); SRB_PEER_NCCL_BARRIER=1 adds one-element NCCL allreduces as well.  Raises SrbError(SRB_ERR_STATE) at construction when the model does not qualify
-    (border band, non-fused regularizer) -- use ShardedObjective then.
+    """cost + gradient of the full objective over NVLink peer memory (srb_peer_* in srb200.h).
+    Every rank owns a contiguous band of the gradient.  The tile kernel evaluates the partial
+    gradient band by band, other ranks' bands first; each finished band is pushed by a copy engine
+    into the owner's slot array (CUDA-IPC peer mappings over NVLink / NVSwitch) while the SMs compute
+    the next band.  The owners then sum their band in fixed rank order and store the result into every
+    rank's gradient buffer (the all-gather half).  The barriers between the phases are flags in peer
+    memory (bounded spin, no host synchronisation); SRB_PEER_NCCL_BARRIER=1 adds one-element NCCL
+    allreduces as well.  Construction is all-or-nothing across the ranks: it raises on EVERY rank when
+    the model does not qualify on some rank (border band, non-fused regularizer) or a peer buffer
+    cannot be mapped -- use ShardedObjective then.
 
     evaluate(x): on return (stream-ordered) `self.out[:n]` holds the full gradient and
     `self.out[n]` the full cost on every rank."""
@@ -165,16 +168,33 @@ class PeerObjective:
         dist.all_gather_object(handles, mine, group=group)
         self._opened = []
         slot_ptrs, out_ptrs = [], []
-        for o, (hs, ho) in enumerate(handles):
-            if o == self.rank:
-                slot_ptrs.append(self._slots)
-                out_ptrs.append(self._out)
-            else:
-                ps, po = pkg.ipc_open(hs), pkg.ipc_open(ho)
-                self._opened += [ps, po]
-                slot_ptrs.append(ps)
-                out_ptrs.append(po)
-        engine.peer_setup(self.rank, self.world, slot_ptrs, out_ptrs)
+        try:
+            for o, (hs, ho) in enumerate(handles):
+                if o == self.rank:
+                    slot_ptrs.append(self._slots)
+                    out_ptrs.append(self._out)
+                else:
+                    ps = pkg.ipc_open(hs)
+                    self._opened.append(ps)
+                    po = pkg.ipc_open(ho)
+                    self._opened.append(po)
+                    slot_ptrs.append(ps)
+                    out_ptrs.append(po)
+            engine.peer_setup(self.rank, self.world, slot_ptrs, out_ptrs)
+            err = None
+        except Exception as exc:   # e.g. no peer access between two of the GPUs
+            err = exc
+        # again all or nothing: a rank that could not map a peer must not leave the others waiting
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok[0]) == 0:
+            for p in self._opened:
+                pkg.ipc_close(p)
+            self._opened = []
+            dist.barrier(group=group)
+            pkg.dev_free(self._slots)
+            pkg.dev_free(self._out)
+            raise err if err is not None else pkg.SrbError(2, "another rank could not map the peer buffers")
         self.slot_ptrs, self.out_ptrs = slot_ptrs, out_ptrs
         self.out = torch.as_tensor(_DevArray(self._out, self.n + 1 + 3 * self.world), device="cuda")
         import os
