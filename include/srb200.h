@@ -81,7 +81,8 @@ typedef struct {
   int psf_half;
   int num_entries, min_entries_per_phase, max_entries_per_phase;
   int band_lo_r, band_hi_r, band_lo_c, band_hi_c;
-  int table_driven;          /* interior tiles use the precomputed residual table */
+  int table_driven;          /* interior tiles use the precomputed residual table: frames per
+                                sub-pixel phase it is specialised for (1, 2 or 4), 0 = generic pass */
   char why[160];             /* reason when fused == 0, or the validation error */
 } srb_plan_info;
 srb_status srb_plan(const srb_model_desc* desc, srb_plan_info* out);

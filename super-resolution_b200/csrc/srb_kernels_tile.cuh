@@ -82,6 +82,9 @@ struct TileParams {
   int row0, row1;      // HR row band of the regularizer term on this rank
   int use_tma;
   const TFast* fast;   // NULL: generic residual pass only
+  const long long* fast_y;  // observation offsets of entries 1 .. fast_E-1: [e-1][fast_items]
+  int fast_E;          // (frame, tap) entries per sub-pixel phase in the table-driven pass (1, 2 or 4)
+  int fast_items;      // items in the table (pass A + ring)
   int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
@@ -254,6 +257,70 @@ __device__ __forceinline__ void slide_correlate(const double* __restrict__ coef,
   }
 }
 
+// Table-driven residual pass for models with E > 1 frames per sub-pixel phase (integer shifts, so all
+// entries of a phase sample the same Bx element): z = sum_e (Bx - y_e), cost += sum_e (Bx - y_e)^2.
+// Entry 0 comes from the TFast item, entries 1..E-1 from P.fast_y.  Lives in its own kernel
+// instantiations (k_tile<..., FE>): its register needs must not disturb the one-frame-per-phase path.
+template <int KH, bool FRAC, int TH, int E>
+__device__ __forceinline__ double fast_residuals_multi(const TileParams& P, const double* __restrict__ bx,
+                                                       double* __restrict__ zs, const double* __restrict__ ytile,
+                                                       int tid) {
+  using D = TileDims<KH, FRAC, TH>;
+  constexpr int NT = D::NT;
+  constexpr int NRING = 2 * KH * D::ZW + TH * 2 * KH;
+  constexpr int RB = (4 / E) > 0 ? (4 / E) : 1;  // rows per batch (4 loads in flight per thread)
+  const int s = P.s, sh = P.sshift;
+  const int nitem_a = FT_W * (TH / 32) * s;
+  const int nj = 32 >> sh;
+  const int bstep = s * D::BP, zstep = s * D::ZP;
+  const size_t ystep = (size_t)P.w;
+  const int4* __restrict__ tab = reinterpret_cast<const int4*>(P.fast);
+  double cost = 0.0;
+  for (int id = tid; id < nitem_a; id += NT) {
+    const int4 f = __ldg(tab + id);
+    const double* yp[E];
+    yp[0] = ytile + (((long long)f.y << 32) | (unsigned)f.x);
+#pragma unroll
+    for (int e = 1; e < E; ++e) yp[e] = ytile + __ldg(P.fast_y + (size_t)(e - 1) * P.fast_items + id);
+    const double* __restrict__ bp = bx + f.z;
+    double* __restrict__ zp = zs + f.w;
+    for (int j = 0; j < nj; j += RB) {
+      double o[E][RB];
+#pragma unroll
+      for (int t = 0; t < RB; ++t)
+#pragma unroll
+        for (int e = 0; e < E; ++e) o[e][t] = (j + t < nj) ? __ldg(yp[e] + (size_t)(j + t) * ystep) : 0.0;
+#pragma unroll
+      for (int t = 0; t < RB; ++t) {
+        if (j + t < nj) {
+          const double b = bp[(j + t) * bstep];
+          double z = 0.0;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const double r = b - o[e][t];
+            z += r;
+            cost = fma(r, r, cost);
+          }
+          zp[(j + t) * zstep] = z;
+        }
+      }
+    }
+  }
+  for (int id = tid; id < NRING; id += NT) {
+    const int4 f = __ldg(tab + nitem_a + id);
+    double o[E];
+    o[0] = __ldg(ytile + (((long long)f.y << 32) | (unsigned)f.x));
+#pragma unroll
+    for (int e = 1; e < E; ++e) o[e] = __ldg(ytile + __ldg(P.fast_y + (size_t)(e - 1) * P.fast_items + nitem_a + id));
+    const double b = bx[f.z];
+    double z = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) z += b - o[e];
+    zs[f.w] = z;
+  }
+  return cost;
+}
+
 // IRLS-weighted 2-D TV gradient + cost of this thread's EL pixels (column ec, rows er0..).
 //   BORDER: the tile touches the right / bottom image border or the edge of the regularizer row
 //   band, so neighbours and outputs are checked per pixel.
@@ -302,7 +369,7 @@ __device__ __forceinline__ void tile_tv(const TileParams& P, const double* __res
   cost_reg = 0.5 * cost;
 }
 
-template <int KH, bool FRAC, int TH>
+template <int KH, bool FRAC, int TH, int FE>
 __global__ void __launch_bounds__(TH * (FT_W / 8), TH == 32 ? (KH <= 3 ? 4 : 3) : 2)
 k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
        const __grid_constant__ CUtensorMap map_w) {
@@ -337,7 +404,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
                         mc_lo + P.qoff_min_c >= P.lo_c && mc_hi + P.qoff_max_c < P.hi_c &&
                         ty0 - KH >= 0 && tx0 - KH >= 0 && ty0 + FT_H + KH <= P.H && tx0 + FT_W + KH <= P.W;
   const double* __restrict__ ych = P.y + (size_t)(P.c0 + ch) * ((size_t)P.h * P.w);
-  const bool fastpath = !FRAC && interior && P.fast != nullptr;
+  const bool fastpath = !FRAC && interior && P.fast != nullptr && P.fast_E == FE;
 
   // ---- 0. stage the x tile + halo and the IRLS weights (zero outside the image) ------------------
   if (P.use_tma) {
@@ -442,7 +509,10 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   //           sub-pixel phase, i.e. one entry list; walking down its rows walks down LR rows
   //   pass B: the halo ring of the Z region (not owned unless outside the image), pixel by pixel
   double cost_data = 0.0;
-  if (fastpath) {
+  if (FE > 1 && fastpath) {
+    const double* __restrict__ ytile = ych + ((long long)(ty0 >> sh) * P.w + (tx0 >> sh));
+    cost_data += fast_residuals_multi<KH, FRAC, TH, (FE > 1 ? FE : 2)>(P, bx, zs, ytile, tid);
+  } else if (fastpath) {
     // interior tile of a one-entry-per-phase model: table-driven work items (see TFast)
     const double* __restrict__ ytile = ych + ((long long)(ty0 >> sh) * P.w + (tx0 >> sh));
     constexpr int NITEM_A_PER_S = FT_W * (FT_H / 32);

@@ -33,6 +33,8 @@ struct TilePlan {
   BandGeom reach{};        // HR pixels the special samples can reach
   bool has_band = false;
   std::vector<TFast> fast[2];    // table-driven residual pass, tile height 32 / 64 (empty: not applicable)
+  std::vector<long long> fast_y[2];  // observation offsets of entries 1 .. fast_E-1, [e-1][items]
+  int fast_E = 0;                // entries per sub-pixel phase in the table-driven pass (1, 2 or 4)
 };
 
 struct TileState {
@@ -50,6 +52,7 @@ struct TileState {
   bool has_band = false;
   double* d_pooled = nullptr;  // [N][Ct][band.count()]
   TFast* d_fast[2] = {nullptr, nullptr};  // tile height 32 / 64; NULL when the model does not qualify
+  long long* d_fast_y[2] = {nullptr, nullptr};
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -70,6 +73,8 @@ inline void fused_teardown(srb_ctx* c) {
   if (st->d_phase_begin) cudaFree(st->d_phase_begin);
   if (st->d_pooled) cudaFree(st->d_pooled);
   for (TFast* f : st->d_fast)
+    if (f) cudaFree(f);
+  for (long long* f : st->d_fast_y)
     if (f) cudaFree(f);
   delete st;
   st = nullptr;
@@ -215,23 +220,30 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
   begin[(size_t)s * s] = (int)flat.size();
   if ((int)flat.size() > FT_MAX_ENTRIES) { st->why = "too many (frame, tap) entries for shared memory"; return; }
 
-  // ---- table-driven residual pass (TFast): integer shifts, one entry per phase, s | tile size ----
+  // ---- table-driven residual pass (TFast): integer shifts, the same number E in {1, 2, 4} of frames
+  //      on every sub-pixel phase, s | tile size ----------------------------------------------------
   {
-    bool one_each = !st->frac && (32 % s == 0);
-    for (size_t ph = 0; one_each && ph < lists.size(); ++ph) one_each = lists[ph].size() == 1;
-    for (int v = 0; one_each && v < 2; ++v) {
+    const int E = (int)lists[0].size();
+    bool balanced = !st->frac && (32 % s == 0) && (E == 1 || E == 2 || E == 4);
+    for (size_t ph = 0; balanced && ph < lists.size(); ++ph) {
+      balanced = (int)lists[ph].size() == E;
+      for (const TEntry& e : lists[ph]) balanced = balanced && e.bxoff == lists[ph][0].bxoff;
+    }
+    for (int v = 0; balanced && v < 2; ++v) {
       const int TH = v == 0 ? 32 : 64;
       const int ZW = FT_W + 2 * hk, ZP = ZW | 1;
       std::vector<TFast> tab;
+      std::vector<std::vector<long long>> extra((size_t)std::max(E - 1, 0));
       auto item = [&](int r, int c) {  // Z-region pixel (r, c): tile-relative HR position (r-hk, c-hk)
         const int pr = r - hk, pc = c - hk;
         const int dmr = pydiv(pr, s), dmc = pydiv(pc, s);
-        const TEntry& e = lists[(size_t)(pr - dmr * s) * s + (pc - dmc * s)][0];
+        const std::vector<TEntry>& le = lists[(size_t)(pr - dmr * s) * s + (pc - dmc * s)];
         TFast f;
-        f.yrel = e.yoff + (long long)dmr * G.w + dmc;
-        f.bxo = r * BP + c + e.bxoff;
+        f.yrel = le[0].yoff + (long long)dmr * G.w + dmc;
+        f.bxo = r * BP + c + le[0].bxoff;
         f.zo = r * ZP + c;
         tab.push_back(f);
+        for (int e = 1; e < E; ++e) extra[(size_t)e - 1].push_back(le[(size_t)e].yoff + (long long)dmr * G.w + dmc);
       };
       for (int blk = 0; blk < TH / 32; ++blk)          // pass A: id = blk*(FT_W*s) + rho*FT_W + cm
         for (int rho = 0; rho < s; ++rho)
@@ -241,6 +253,9 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
       for (int rm = 0; rm < TH; ++rm)                 // ring: left / right halo columns
         for (int hc = 0; hc < 2 * hk; ++hc) item(hk + rm, hc < hk ? hc : hc + FT_W);
       st->fast[v] = tab;
+      st->fast_y[v].clear();
+      for (const auto& ex : extra) st->fast_y[v].insert(st->fast_y[v].end(), ex.begin(), ex.end());
+      st->fast_E = E;
     }
   }
 
@@ -281,6 +296,11 @@ inline srb_status fused_setup(srb_ctx* c) {
     if (cudaMalloc((void**)&st->d_fast[v], (plan.fast[v].size() + 1) * sizeof(TFast)) != cudaSuccess)
       return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
     SRB_CUDA_CHECK(c, cudaMemcpy(st->d_fast[v], plan.fast[v].data(), plan.fast[v].size() * sizeof(TFast), cudaMemcpyHostToDevice));
+    if (!plan.fast_y[v].empty()) {
+      if (cudaMalloc((void**)&st->d_fast_y[v], plan.fast_y[v].size() * sizeof(long long)) != cudaSuccess)
+        return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (tile kernel tables)");
+      SRB_CUDA_CHECK(c, cudaMemcpy(st->d_fast_y[v], plan.fast_y[v].data(), plan.fast_y[v].size() * sizeof(long long), cudaMemcpyHostToDevice));
+    }
   }
   // ---- TMA: the tensor-map encoder comes from the driver through the runtime ---------------------
   {
@@ -317,7 +337,7 @@ inline bool make_plane_map(const TileState* st, CUtensorMap* map, const double* 
   return r == CUDA_SUCCESS;
 }
 
-template <int KH, bool FRAC, int TH>
+template <int KH, bool FRAC, int TH, int FE>
 inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   using D = TileDims<KH, FRAC, TH>;
   const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
@@ -335,11 +355,11 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   const size_t smem = D::smem_bytes(P.num_entries) + smem_pad;
   static size_t attr_set[64] = {};
   if (c->device >= 64 || attr_set[c->device] < smem) {
-    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile<KH, FRAC, TH, FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = smem;
   }
   if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
-  k_tile<KH, FRAC, TH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
+  k_tile<KH, FRAC, TH, FE><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
   if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
   return SRB_OK;
 }
@@ -395,7 +415,11 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   *reg_done = P.reg_fused != 0;
   const int TH = tile_height(c);
   P.tile_rows = tile_rows_per_channel(c);
-  P.fast = st->d_fast[TH == 64 ? 1 : 0];
+  static const bool no_table = getenv("SRB_NO_TABLE") != nullptr;  // A/B: generic residual pass everywhere
+  P.fast = no_table ? nullptr : st->d_fast[TH == 64 ? 1 : 0];
+  P.fast_y = st->d_fast_y[TH == 64 ? 1 : 0];
+  P.fast_E = st->plan.fast_E;
+  P.fast_items = (int)st->plan.fast[TH == 64 ? 1 : 0].size();
   P.unit_begin = unit_begin;
   const TileLayout L = tile_layout(c);
   const size_t need = 2 * L.nblocks + L.nband;
@@ -411,14 +435,20 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   P.part_data = c->d_partial;
   P.part_reg = c->d_partial + L.nblocks + L.nband;
   srb_status rc = SRB_OK;
-  const int key = (st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0);
+  // kernel instantiation: PSF half width x fractional x tile height, and for integer shifts the number of
+  // frames per sub-pixel phase the table-driven residual pass is specialised for (1, 2 or 4)
+  const int fe = (!st->frac && P.fast != nullptr && (P.fast_E == 2 || P.fast_E == 4)) ? P.fast_E : 1;
+  const int key = ((st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0)) * 3 + (fe == 1 ? 0 : fe == 2 ? 1 : 2);
   switch (key) {
-#define SRB_TILE_CASE(KH_, FR_)                                                                    \
-    case ((KH_) * 2 + (FR_)) * 2: rc = tile_launch<KH_, (FR_) != 0, 32>(c, P, unit_end); break;  \
-    case ((KH_) * 2 + (FR_)) * 2 + 1: rc = tile_launch<KH_, (FR_) != 0, 64>(c, P, unit_end); break;
-    SRB_TILE_CASE(0, 0) SRB_TILE_CASE(0, 1) SRB_TILE_CASE(1, 0) SRB_TILE_CASE(1, 1) SRB_TILE_CASE(2, 0)
-    SRB_TILE_CASE(2, 1) SRB_TILE_CASE(3, 0) SRB_TILE_CASE(3, 1) SRB_TILE_CASE(4, 0) SRB_TILE_CASE(4, 1)
+#define SRB_TILE_CASE_FE(KH_, FR_, TH_, FE_, IDX_) \
+    case (((KH_) * 2 + (FR_)) * 2 + ((TH_) == 64 ? 1 : 0)) * 3 + (IDX_): rc = tile_launch<KH_, (FR_) != 0, TH_, FE_>(c, P, unit_end); break;
+#define SRB_TILE_CASE(KH_)                                                                          \
+    SRB_TILE_CASE_FE(KH_, 0, 32, 1, 0) SRB_TILE_CASE_FE(KH_, 0, 32, 2, 1) SRB_TILE_CASE_FE(KH_, 0, 32, 4, 2) \
+    SRB_TILE_CASE_FE(KH_, 0, 64, 1, 0) SRB_TILE_CASE_FE(KH_, 0, 64, 2, 1) SRB_TILE_CASE_FE(KH_, 0, 64, 4, 2) \
+    SRB_TILE_CASE_FE(KH_, 1, 32, 1, 0) SRB_TILE_CASE_FE(KH_, 1, 64, 1, 0)
+    SRB_TILE_CASE(0) SRB_TILE_CASE(1) SRB_TILE_CASE(2) SRB_TILE_CASE(3) SRB_TILE_CASE(4)
 #undef SRB_TILE_CASE
+#undef SRB_TILE_CASE_FE
     default: return c->fail(SRB_ERR_STATE, "tile kernel: unsupported PSF size");
   }
   if (rc != SRB_OK) return rc;

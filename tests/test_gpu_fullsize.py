@@ -101,7 +101,7 @@ def test_cfg4_shaped_hyperspectral_vs_oracle(srb, oracle, kind):
     """Configuration 4 scaled down (many bands, 2x, 5x5 PSF, 8 frames; TV and 3-D TV)."""
     cf = wl.CONFIGS[4]
     rng = np.random.default_rng(44)
-    C, h, w_, s, K, N = 12, 40, 36, cf["s"], cf["K"], cf["N"]
+    C, h, w_, s, K, N = 12, 80, 104, cf["s"], cf["K"], cf["N"]   # 160 x 208 HR: has interior tiles
     psf = wl.gaussian_psf(K, cf["sigma"])
     shifts = wl.default_shifts(N, s)
     x = rng.random((C, h * s, w_ * s))
@@ -123,7 +123,7 @@ def test_cfg5_shaped_many_frames_vs_oracle(srb, oracle):
     """Configuration 5 scaled down: 64 frames (four per sub-pixel phase), 4x, 9x9 PSF, BTV(3, 0.5)."""
     cf = wl.CONFIGS[5]
     rng = np.random.default_rng(55)
-    C, h, w_, s, K, N = 3, 48, 40, cf["s"], cf["K"], cf["N"]
+    C, h, w_, s, K, N = 3, 48, 52, cf["s"], cf["K"], cf["N"]      # 192 x 208 HR: has interior tiles
     psf = wl.gaussian_psf(K, cf["sigma"])
     shifts = wl.default_shifts(N, s)
     x = rng.random((C, h * s, w_ * s))

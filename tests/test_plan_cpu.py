@@ -27,8 +27,8 @@ def test_plans_of_the_baseline_configurations():
     expect = {1: dict(frac=0, kh=1, per_phase=(1, 1), table=1),
               2: dict(frac=0, kh=2, per_phase=(0, 1), table=0),     # 9 frames over 16 phases
               3: dict(frac=0, kh=3, per_phase=(1, 1), table=1),
-              4: dict(frac=0, kh=2, per_phase=(2, 2), table=0),     # 8 frames over 4 phases
-              5: dict(frac=0, kh=4, per_phase=(4, 4), table=0)}     # 64 frames over 16 phases
+              4: dict(frac=0, kh=2, per_phase=(2, 2), table=2),     # 8 frames over 4 phases
+              5: dict(frac=0, kh=4, per_phase=(4, 4), table=4)}     # 64 frames over 16 phases
     for cfg, ex in expect.items():
         cf = wl.CONFIGS[cfg]
         s = cf["s"]
@@ -38,7 +38,7 @@ def test_plans_of_the_baseline_configurations():
         assert (p["hr_height"], p["hr_width"]) == (cf["H"], cf["W"])
         assert p["fractional"] == ex["frac"] and p["psf_half"] == ex["kh"]
         assert (p["min_entries_per_phase"], p["max_entries_per_phase"]) == ex["per_phase"], (cfg, p)
-        assert p["table_driven"] == ex["table"]
+        assert p["table_driven"] == ex["table"]      # frames per phase of the table-driven residual pass (0: generic)
         assert p["num_entries"] == cf["N"]
         # default shifts are >= 0 and at most s - 1: at most a thin band at the top / left
         assert p["band_hi_r"] >= cf["H"] // s - 2 and p["band_hi_c"] >= cf["W"] // s - 2
