@@ -82,12 +82,14 @@ struct TileParams {
   int row0, row1;      // HR row band of the regularizer term on this rank
   int use_tma;
   const TFast* fast;   // NULL: generic residual pass only
-  const long long* fast_y;  // observation offsets of entries 1 .. fast_E-1: [e-1][fast_items]
-  int fast_E;          // (frame, tap) entries per sub-pixel phase in the table-driven pass (1, 2 or 4)
-  int fast_items;      // items in the table (pass A + ring)
   int unit_begin, tile_rows;  // first (channel, tile row) unit of this launch; tile rows per channel
   double* part_data;   // per-CTA partial sums of the data cost
   double* part_reg;    // per-CTA partial sums of the regularization cost
+  // table-driven residual pass with 2 or 4 frames per phase (k_tile<..., FE > 1>); kept at the end so
+  // that the one-frame-per-phase kernels see the parameter layout they were tuned with
+  const long long* fast_y;  // observation offsets of entries 1 .. fast_E-1: [e-1][fast_items]
+  int fast_E;          // (frame, tap) entries per sub-pixel phase in the table-driven pass (1, 2 or 4)
+  int fast_items;      // items in the table (pass A + ring)
 };
 
 template <int KH, bool FRAC, int TH>
@@ -404,7 +406,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
                         mc_lo + P.qoff_min_c >= P.lo_c && mc_hi + P.qoff_max_c < P.hi_c &&
                         ty0 - KH >= 0 && tx0 - KH >= 0 && ty0 + FT_H + KH <= P.H && tx0 + FT_W + KH <= P.W;
   const double* __restrict__ ych = P.y + (size_t)(P.c0 + ch) * ((size_t)P.h * P.w);
-  const bool fastpath = !FRAC && interior && P.fast != nullptr && P.fast_E == FE;
+  const bool fastpath = !FRAC && interior && P.fast != nullptr;  // the host passes the table of THIS FE only
 
   // ---- 0. stage the x tile + halo and the IRLS weights (zero outside the image) ------------------
   if (P.use_tma) {

@@ -438,6 +438,7 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   // kernel instantiation: PSF half width x fractional x tile height, and for integer shifts the number of
   // frames per sub-pixel phase the table-driven residual pass is specialised for (1, 2 or 4)
   const int fe = (!st->frac && P.fast != nullptr && (P.fast_E == 2 || P.fast_E == 4)) ? P.fast_E : 1;
+  if (P.fast_E != fe) P.fast = nullptr;  // a kernel only ever sees the table it is specialised for
   const int key = ((st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0)) * 3 + (fe == 1 ? 0 : fe == 2 ? 1 : 2);
   switch (key) {
 #define SRB_TILE_CASE_FE(KH_, FR_, TH_, FE_, IDX_) \
