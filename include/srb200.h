@@ -223,6 +223,11 @@ srb_status srb_reg_apply_diff(srb_ctx* ctx, const double* x_host, const double* 
  * (image_data.cpp:353-364); the decimation index map is cv::resize's, bit-exact. */
 srb_status srb_forward(srb_ctx* ctx, int frame, const double* hr_host, int H, int W,
                        double* lr_out_host);
+/* ImageModel::ApplyToImage for EVERY frame of the model and every channel of one HR image of the
+ * solver's size (image_model.cpp:76-84 looped over frames, what generate_data.cpp:83-127 and
+ * super_resolution.cpp:286-311 do to synthesise an LR stack, without the additive noise):
+ * hr is [num_channels][H][W], lr_out is [num_frames][num_channels][h][w]; one kernel launch. */
+srb_status srb_forward_all(srb_ctx* ctx, const double* hr_host, double* lr_out_host);
 /* ImageModel::ApplyTransposeToImage for one channel (image_model.cpp:93-101): D^T (zero insert),
  * B^T (correlation with blur_kernel_.t()), M_k^T (warp by the negated shift); input h x w,
  * output (h*s) x (w*s). */

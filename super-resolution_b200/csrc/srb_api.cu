@@ -1014,6 +1014,26 @@ srb_status srb_forward(srb_ctx* c, int frame, const double* hr_host, int H, int 
   return SRB_OK;
 }
 
+srb_status srb_forward_all(srb_ctx* c, const double* hr_host, double* lr_out_host) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!hr_host || !lr_out_host) return c->fail(SRB_ERR_INVALID, "null buffer");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const Geometry& G = c->g;
+  const size_t n_hr = (size_t)G.Ct * c->P, n_lr = (size_t)G.N * G.Ct * c->p;
+  srb_status st = dev_alloc(c, &c->d_pooled, n_lr);  // scratch of the reference-order path, same shape
+  if (st != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, hr_host, n_hr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GenericParams P = make_params(c, false);
+  P.Ca = G.Ct;  // every channel, whatever the active channel range is
+  P.c0 = 0;
+  k_forward_generic<0><<<grid2d(G.w, G.h, G.N * G.Ct), dim3(32, 8), 0, c->stream>>>(P, c->d_x, nullptr, c->d_pooled, nullptr);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(lr_out_host, c->d_pooled, n_lr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
 srb_status srb_transpose(srb_ctx* c, int frame, const double* lr_host, int h, int w, double* hr_out) {
   if (!c) return SRB_ERR_INVALID;
   if (!lr_host || !hr_out || h <= 0 || w <= 0) return c->fail(SRB_ERR_INVALID, "bad image");

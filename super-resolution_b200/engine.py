@@ -61,6 +61,7 @@ SIGNATURES = {
     "srb_reg_apply": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_void_p]),
     "srb_reg_apply_diff": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "srb_forward": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "srb_forward_all": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "srb_transpose": (C.c_int, [_ctx_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "srb_pin_host": (C.c_int, [C.c_void_p, C.c_ulonglong]),
     "srb_unpin_host": (C.c_int, [C.c_void_p]),
@@ -337,6 +338,14 @@ class Engine:
         f = 1.0 / float(self.scale)
         out = np.empty((int(H * f), int(W * f)))
         self._check(self._lib.srb_forward(self._ctx, int(k), _host_ptr(hr), H, W, _host_ptr(out)))
+        return out
+
+    def forward_all(self, hr):
+        """The whole LR stack [N][C][h][w] of an HR image [C][H][W] (ImageModel::ApplyToImage per frame)."""
+        hr = _f64(hr)
+        assert hr.shape == (self.C, self.H, self.W), hr.shape
+        out = np.empty((self.N, self.C, self.h, self.w))
+        self._check(self._lib.srb_forward_all(self._ctx, _host_ptr(hr), _host_ptr(out)))
         return out
 
     def transpose(self, k, lr):

@@ -328,3 +328,21 @@ def test_eval_vs_oracle_all_paths(srb, oracle, seed, C, h, w, s, K, N, frac, kin
             assert np.abs(gr - go).max() <= 1e-11 * np.abs(go).max()
             f2, none = e.eval(x, want_grad=False)
             np.testing.assert_allclose(f2, fo, rtol=COST_RTOL)
+
+
+def test_forward_all_equals_per_frame_forward(srb, oracle):
+    """srb_forward_all (the whole LR stack in one launch) == srb_forward frame by frame == oracle,
+    bit for bit (same kernel, same operation order as the reference)."""
+    rng = np.random.default_rng(77)
+    C, h, w, s, K, N = 3, 21, 17, 3, 5, 6
+    psf = oracle.gaussian_psf(K, 1.3)
+    shifts = np.vstack([rng.integers(-3, 4, size=(3, 2)).astype(np.float64), rng.uniform(-2.5, 2.5, size=(3, 2))])
+    x = rng.random((C, h * s, w * s))
+    m = oracle.Model(s, psf, shifts)
+    with srb.Engine((N, C, h, w), s, psf, shifts) as e:
+        e.set_channel_range(1, 2)          # forward_all ignores the active channel range
+        stack = e.forward_all(x)
+        for k in range(N):
+            for c in range(C):
+                np.testing.assert_array_equal(stack[k, c], e.forward(k, x[c]))
+                np.testing.assert_array_equal(stack[k, c], oracle.forward(m, k, x[c]))
