@@ -327,6 +327,8 @@ def main():
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         path_name = {1: "reference_order", 2: "fused"}[eng.active_path]
+        if path_name == "fused" and eng.zlayout_active:
+            path_name = "fused_zlayout"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -347,8 +349,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                         "kernel": "k_tile (fused tile kernel), one launch per evaluation"
-                                   if path_name == "fused" else "reference-order kernels"},
+                         "kernel": {"fused": "k_tile (fused tile kernel), one launch per evaluation",
+                                    "fused_zlayout": "k_tile_z (fused tile kernel, observations in Z layout), "
+                                                     "one launch per evaluation"}.get(path_name,
+                                                                                      "reference-order kernels")},
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):

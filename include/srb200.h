@@ -132,6 +132,10 @@ srb_status srb_reweight(srb_ctx* ctx, const double* x_host, double* weights_out_
  * the current configuration resolves to. */
 srb_status srb_set_path(srb_ctx* ctx, int path);
 int srb_active_path(const srb_ctx* ctx);
+/* 1 when the fused path evaluates interior tiles from the observations re-laid out on the HR grid
+ * ("Z layout", opt-in with SRB_ZLAYOUT=1 in the environment of srb_create; integer shifts with one
+ * frame per sub-pixel phase only), else 0.  No reference counterpart. */
+int srb_zlayout_active(const srb_ctx* ctx);
 /* Multi-GPU frame sharding: this context holds the frames of one rank.  The data
  * term covers the context's frames; the regularizer term is computed only for HR rows
  * [row_begin, row_end) so that the sum over ranks is the full objective.  Default: all rows. */

@@ -393,6 +393,8 @@ srb_status srb_set_observations(srb_ctx* c, const double* lr_host) {
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_y, lr_host, (size_t)c->g.N * c->g.Ct * c->p * sizeof(double),
                                     cudaMemcpyHostToDevice, c->stream));
+  srb_status zst = fused_observations_changed(c);
+  if (zst != SRB_OK) return zst;
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   c->have_obs = true;
   return SRB_OK;
@@ -404,6 +406,8 @@ srb_status srb_set_observations_dev(srb_ctx* c, const double* lr_dev) {
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_y, lr_dev, (size_t)c->g.N * c->g.Ct * c->p * sizeof(double),
                                     cudaMemcpyDeviceToDevice, c->stream));
+  srb_status zst = fused_observations_changed(c);
+  if (zst != SRB_OK) return zst;
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   c->have_obs = true;
   return SRB_OK;
@@ -493,6 +497,10 @@ srb_status srb_set_path(srb_ctx* c, int path) {
   return SRB_OK;
 }
 int srb_active_path(const srb_ctx* c) { return c ? resolve_path(c) : -1; }
+int srb_zlayout_active(const srb_ctx* c) {
+  const TileState* st = c ? tile_state(c) : nullptr;
+  return (st && st->supported && st->d_yz && st->yz_valid) ? 1 : 0;
+}
 
 srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {
   if (!c) return SRB_ERR_INVALID;

@@ -90,6 +90,8 @@ struct TileParams {
   const long long* fast_y;  // observation offsets of entries 1 .. fast_E-1: [e-1][fast_items]
   int fast_E;          // (frame, tap) entries per sub-pixel phase in the table-driven pass (1, 2 or 4)
   int fast_items;      // items in the table (pass A + ring)
+  // k_tile_z only (kept last for the same reason): the observations re-laid out on the HR grid
+  const double* yz;    // [Ct][H][W]: yz(c, p) = the one regular LR sample that lands on HR pixel p
 };
 
 template <int KH, bool FRAC, int TH>
@@ -151,6 +153,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
         : "memory");
   }
 }
+// mbar_wait that traps instead of spinning forever (a lost TMA must not hang the device).
+__device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, unsigned phase) {
+  unsigned done = 0;
+  const unsigned a = smem_u32(bar);
+  for (unsigned tries = 0; !done; ++tries) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(phase)
+        : "memory");
+    if (!done && tries > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             unsigned long long* bar) {
   asm volatile(
@@ -158,6 +175,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
         "r"(smem_u32(bar))
       : "memory");
+}
+
+// Orders earlier generic-proxy accesses of shared memory before later async-proxy (TMA) ones.
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // sgn(g) * t with sgn(0) = 0 (tv_regularizer.cpp:152-201: the three-way branches on the sign of a
@@ -371,10 +393,9 @@ __device__ __forceinline__ void tile_tv(const TileParams& P, const double* __res
   cost_reg = 0.5 * cost;
 }
 
+// The whole evaluation of one tile (the body of k_tile; k_tile_z runs it for its border tiles).
 template <int KH, bool FRAC, int TH, int FE>
-__global__ void __launch_bounds__(TH * (FT_W / 8), TH == 32 ? (KH <= 3 ? 4 : 3) : 2)
-k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
-       const __grid_constant__ CUtensorMap map_w) {
+__device__ __forceinline__ void tile_body(const TileParams& P, const CUtensorMap& map_x, const CUtensorMap& map_w) {
   using D = TileDims<KH, FRAC, TH>;
   constexpr int K = D::K;
   constexpr int FT_H = TH, FT_NT = D::NT;
@@ -726,6 +747,223 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
     P.part_data[cta] = P.s2 * cost_data;
     P.part_reg[cta] = cost_reg;
   }
+}
+
+template <int KH, bool FRAC, int TH, int FE>
+__global__ void __launch_bounds__(TH * (FT_W / 8), TH == 32 ? (KH <= 3 ? 4 : 3) : 2)
+k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
+       const __grid_constant__ CUtensorMap map_w) {
+  tile_body<KH, FRAC, TH, FE>(P, map_x, map_w);
+}
+
+// ---- "Z layout" variant (opt-in, SRB_ZLAYOUT=1) ---------------------------
+// For models with integer shifts and exactly one frame per sub-pixel phase, every HR pixel receives
+// exactly one regular LR sample, and that sample reads the Bx element under it.  With the
+// observations gathered ONCE (at upload, k_build_yz) onto the HR grid, the residual pass of an
+// interior tile is Z = Bx - yz elementwise, and the yz tile arrives by TMA while the horizontal PSF
+// pass runs instead of being fetched sample by sample afterwards:
+//     x, w boxes -> A, B | TV | vertical pass A -> B | yz box -> A (async)  ||  horizontal pass IN
+//     PLACE in B (the K-1 inputs a thread shares with its right neighbour are read before a
+//     barrier) | Z = B - A in place in B, cost | adjoint horizontal B -> A | adjoint vertical -> g
+// Shared memory and registers are those of k_tile (4 CTAs / SM); tiles that touch the border band run
+// tile_body unchanged.
+template <int KH>
+__global__ void __launch_bounds__(256, KH <= 3 ? 4 : 3)
+k_tile_z(const TileParams P, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+         const __grid_constant__ CUtensorMap map_y) {
+  constexpr int TH = 32;
+  using D = TileDims<KH, false, TH>;
+  constexpr int K = D::K;
+  constexpr int NT = D::NT;
+  static_assert(KH >= 1 && NT == 256, "k_tile_z: PSF of at least 3x3, 256 threads");
+  constexpr int HYC = (KH + 1) & ~1;       // even column halo of the yz box (FLOAT64 TMA alignment)
+  constexpr int YW = FT_W + 2 * HYC;       // yz box, dense
+  constexpr int YH = TH + 2 * KH;
+  static_assert(YH * YW <= D::A_DOUBLES, "yz box fits buffer A");
+  static_assert(D::TR * D::TP <= D::B_DOUBLES && D::ZH * D::T2P <= D::A_DOUBLES, "buffer sizes");
+  static_assert(D::BW == D::ZW && D::TR == D::ZH && D::TR == YH, "integer shifts: Bx region == Z region");
+
+  const int unit = P.unit_begin + blockIdx.y;
+  const int ch = unit / P.tile_rows;
+  const int tx0 = blockIdx.x * FT_W, ty0 = (unit - ch * P.tile_rows) * TH;
+  const int s = P.s, sh = P.sshift;
+  {
+    const int mr_lo = floordiv_scale(ty0 - KH, s, sh), mr_hi = floordiv_scale(ty0 + TH + KH - 1, s, sh);
+    const int mc_lo = floordiv_scale(tx0 - KH, s, sh), mc_hi = floordiv_scale(tx0 + FT_W + KH - 1, s, sh);
+    const bool interior = mr_lo + P.qoff_min_r >= P.lo_r && mr_hi + P.qoff_max_r < P.hi_r &&
+                          mc_lo + P.qoff_min_c >= P.lo_c && mc_hi + P.qoff_max_c < P.hi_c &&
+                          ty0 - KH >= 0 && tx0 - KH >= 0 && ty0 + TH + KH <= P.H && tx0 + FT_W + KH <= P.W;
+    if (!interior) {  // block-uniform
+      tile_body<KH, false, TH, 1>(P, map_x, map_w);
+      return;
+    }
+  }
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* bufA = reinterpret_cast<double*>(smem_raw);  // xs [XH][XW] -> yz [YH][YW] -> t2 [ZH][T2P]
+  double* bufB = bufA + D::A_DOUBLES;                  // ws [WH][WW] -> tmp -> bx -> z, all [TR][TP]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + D::FIXED_BYTES - 16);
+  const int tid = threadIdx.x;
+  const size_t HW = (size_t)P.H * P.W;
+
+  // ---- 0. x tile + halo and IRLS weights by TMA -------------------------------------------------
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, D::X_BYTES + (P.reg_fused ? D::W_BYTES : 0u));
+    tma_load_3d(bufA, &map_x, tx0 - D::HXC, ty0 - D::HX, ch, bar);
+    if (P.reg_fused) tma_load_3d(bufB, &map_w, tx0 - 2, ty0 - 1, ch, bar);
+  }
+  __syncthreads();  // mbarrier initialised before anyone waits on it
+  mbar_wait_bounded(bar, 0);
+
+  // ---- 1. 2-D TV (as in tile_body) ----------------------------------------------------------------
+  constexpr int ESEG = NT / FT_W;  // 4
+  constexpr int EL = TH / ESEG;    // 8
+  const int ec = tid % FT_W, er0 = (tid / FT_W) * EL;
+  const int gc = tx0 + ec;
+  double tvg[EL];
+  double cost_reg = 0.0;
+#pragma unroll
+  for (int l = 0; l < EL; ++l) tvg[l] = 0.0;
+  if (P.reg_fused) {
+    // an interior tile has its right / bottom neighbours (KH >= 1); only the row band can cut it
+    if (ty0 >= P.row0 && ty0 + TH <= P.row1)
+      tile_tv<KH, false, TH, EL, false>(P, bufA, bufB, ty0, gc, ec, er0, tvg, cost_reg);
+    else
+      tile_tv<KH, false, TH, EL, true>(P, bufA, bufB, ty0, gc, ec, er0, tvg, cost_reg);
+    __syncthreads();  // ws (B) is overwritten by the vertical pass
+  }
+
+  // ---- 2a. vertical PSF pass: tmp[r][c] = sum_i u[i] * xs[r+i][c]   (A -> B) ------------------------
+  {
+    constexpr int NSEG = (NT / D::TW) > 0 ? (NT / D::TW) : 1;
+    constexpr int L = (D::TR + NSEG - 1) / NSEG;
+    const double* __restrict__ xo = bufA + D::XOR * D::XW + D::XOC;
+    for (int id = tid; id < D::TW * NSEG; id += NT) {
+      const int c = id % D::TW, seg = id / D::TW;
+      const int r0 = seg * L;
+      const double* __restrict__ src = xo + r0 * D::XW + c;
+      double* __restrict__ dst = bufB + r0 * D::TP + c;
+      slide_correlate<K, L, SRB_SLIDE_B>(P.u, D::TR - r0,
+                                [&](int i) { return src[i * D::XW]; },
+                                [&](int l, double v) { dst[l * D::TP] = v; });
+    }
+  }
+  __syncthreads();
+
+  // x is consumed: the observations of the Z region land in A while the horizontal pass runs
+  if (tid == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(bar, (unsigned)(YH * YW * sizeof(double)));
+    tma_load_3d(bufA, &map_y, tx0 - HYC, ty0 - KH, P.c0 + ch, bar);
+  }
+
+  // ---- 2b. horizontal PSF pass, in place: bx[r][c] = sum_j v[j] * tmp[r][c+j]   (B -> B) ----------
+  {
+    constexpr int NSEG = (NT / D::TR) > 0 ? (NT / D::TR) : 1;
+    constexpr int L = (D::BW + NSEG - 1) / NSEG;
+    static_assert(D::TR * NSEG <= NT && L >= K - 1, "one row segment per thread");
+    const bool active = tid < D::TR * NSEG;
+    const int r = tid % D::TR, seg = tid / D::TR;
+    const int c0 = seg * L;
+    double* row = bufB + r * D::TP + c0;
+    double tail[K - 1];  // inputs [c0+L, c0+L+K-1): the next segment overwrites them
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) tail[i] = (active && c0 + L + i < D::TW) ? row[L + i] : 0.0;
+    __syncthreads();
+    if (active)
+      slide_correlate<K, L, SRB_SLIDE_B>(P.v, D::BW - c0,
+                                [&](int j) { return j < L ? row[j < L ? j : 0] : tail[j < L ? 0 : j - L]; },
+                                [&](int l, double v) { row[l] = v; });
+  }
+  __syncthreads();
+
+  // ---- 3. residuals: Z = Bx - yz, elementwise and in place; cost over the pixels the tile owns ------
+  mbar_wait_bounded(bar, 1);
+  double cost_data = 0.0;
+  {
+    const int c = tid & (FT_W - 1), rq = tid / FT_W;  // rows rq, rq + 4, ...
+    double* __restrict__ bp = bufB + rq * D::TP + KH + c;
+    const double* __restrict__ yp = bufA + rq * YW + HYC + c;
+#pragma unroll
+    for (int it = 0; it < (YH + ESEG - 1) / ESEG; ++it) {
+      const int r = rq + ESEG * it;
+      if (ESEG * it + ESEG - 1 < YH || r < YH) {
+        const double res = bp[it * ESEG * D::TP] - yp[it * ESEG * YW];
+        bp[it * ESEG * D::TP] = res;
+        if (r >= KH && r < KH + TH) cost_data = fma(res, res, cost_data);
+      }
+    }
+    // left / right halo columns of the Z region
+    for (int id = tid; id < 2 * KH * YH; id += NT) {
+      const int r = id / (2 * KH), hc = id - r * (2 * KH);
+      const int cz = hc < KH ? hc : hc + FT_W;
+      bufB[r * D::TP + cz] -= bufA[r * YW + cz - KH + HYC];
+    }
+  }
+  __syncthreads();
+
+  if (P.g != nullptr) {
+    // ---- 4a. adjoint horizontal pass: t2[r][c] = sum_j u[j] * Z[r][c+j]   (B -> A) ----------------
+    {
+      constexpr int NSEG = (NT / D::ZH) > 0 ? (NT / D::ZH) : 1;
+      constexpr int L = (FT_W + NSEG - 1) / NSEG;
+      for (int id = tid; id < D::ZH * NSEG; id += NT) {
+        const int r = id % D::ZH, seg = id / D::ZH;
+        const int c0 = seg * L;
+        const double* __restrict__ src = bufB + r * D::TP + c0;
+        double* __restrict__ dst = bufA + r * D::T2P + c0;
+        slide_correlate<K, L, SRB_SLIDE_B>(P.u, FT_W - c0, [&](int j) { return src[j]; },
+                                  [&](int l, double v) { dst[l] = v; });
+      }
+    }
+    __syncthreads();
+
+    // ---- 4b. adjoint vertical pass + regularizer part + store (the tile is inside the image) ------
+    {
+      const double* __restrict__ t2 = bufA;
+      double win[K];
+#pragma unroll
+      for (int i = 0; i < K - 1; ++i) win[i] = t2[(er0 + i) * D::T2P + ec];
+      double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
+      const size_t gstep = (size_t)P.W;
+#pragma unroll
+      for (int l = 0; l < EL; ++l) {
+        win[K - 1] = t2[(er0 + l + K - 1) * D::T2P + ec];
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc = fma(P.v[i], win[i], acc);
+#pragma unroll
+        for (int i = 0; i < K - 1; ++i) win[i] = win[i + 1];
+        *gp = fma(P.two_s2, acc, tvg[l]);
+        gp += gstep;
+      }
+    }
+  }
+
+  const size_t cta = (size_t)unit * gridDim.x + blockIdx.x;
+  block_sum2<NT>(cost_data, cost_reg);
+  if (tid == 0) {
+    P.part_data[cta] = P.s2 * cost_data;
+    P.part_reg[cta] = cost_reg;
+  }
+}
+
+// yz(c, p) = the observation of the one (frame, LR pixel) sample landing on HR pixel p; 0 where that
+// sample lies outside the LR image (such pixels belong to tiles that never take the Z path).
+// grid: (ceil(W/256), H, Ct)
+__global__ void __launch_bounds__(256)
+k_build_yz(int H, int W, int h, int w, int s, const TEntry* __restrict__ entries,
+           const int* __restrict__ phase_begin, const double* __restrict__ y, double* __restrict__ yz) {
+  const int pc = blockIdx.x * 256 + threadIdx.x, pr = blockIdx.y, c = blockIdx.z;
+  if (pc >= W) return;
+  const int mr = pr / s, mc = pc / s;
+  const TEntry e = entries[phase_begin[(pr - mr * s) * s + (pc - mc * s)]];
+  const int qr = mr + (int)(short)(e.qoff & 0xffff), qc = mc + (e.qoff >> 16);
+  double v = 0.0;
+  if (qr >= 0 && qr < h && qc >= 0 && qc < w)
+    v = y[(size_t)c * ((size_t)h * w) + e.yoff + (long long)mr * w + mc];
+  yz[((size_t)c * H + pr) * W + pc] = v;
 }
 
 }  // namespace srb

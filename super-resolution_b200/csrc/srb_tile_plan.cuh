@@ -53,6 +53,8 @@ struct TileState {
   double* d_pooled = nullptr;  // [N][Ct][band.count()]
   TFast* d_fast[2] = {nullptr, nullptr};  // tile height 32 / 64; NULL when the model does not qualify
   long long* d_fast_y[2] = {nullptr, nullptr};
+  double* d_yz = nullptr;  // observations on the HR grid [Ct][H][W] (k_tile_z; SRB_ZLAYOUT=1), else NULL
+  bool yz_valid = false;   // d_yz matches the observations currently in d_y
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -76,6 +78,7 @@ inline void fused_teardown(srb_ctx* c) {
     if (f) cudaFree(f);
   for (long long* f : st->d_fast_y)
     if (f) cudaFree(f);
+  if (st->d_yz) cudaFree(st->d_yz);
   delete st;
   st = nullptr;
 }
@@ -314,7 +317,31 @@ inline srb_status fused_setup(srb_ctx* c) {
     st->tma_ok = st->encode != nullptr && (G.W % 2 == 0);  // global strides must be multiples of 16 B
   }
   if (const char* e = getenv("SRB_TILE_H")) st->tile_h = atoi(e) == 64 ? 64 : 32;
+  // Z layout (k_tile_z): integer shifts, one frame per sub-pixel phase, PSF of 3x3 .. 9x9, TMA.
+  // SRB_ZLAYOUT=0 keeps k_tile everywhere (A/B).
+  {
+    const char* e = getenv("SRB_ZLAYOUT");
+    const bool wanted = e == nullptr || atoi(e) != 0;
+    if (wanted && !plan.frac && plan.fast_E == 1 && plan.KH >= 1 && plan.KH <= 4 && st->tma_ok &&
+        st->tile_h == 32 && !plan.fast[0].empty()) {
+      if (cudaMalloc((void**)&st->d_yz, (size_t)G.Ct * G.H * G.W * sizeof(double)) != cudaSuccess)
+        return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in Z layout)");
+    }
+  }
   st->supported = true;
+  return SRB_OK;
+}
+
+// After new observations were stored in c->d_y (stream-ordered): refresh their Z-layout copy.
+inline srb_status fused_observations_changed(srb_ctx* c) {
+  TileState* st = tile_state(c);
+  if (!st || !st->supported || !st->d_yz) return SRB_OK;
+  const Geometry& G = c->g;
+  const dim3 grid((unsigned)((G.W + 255) / 256), (unsigned)G.H, (unsigned)G.Ct);
+  k_build_yz<<<grid, 256, 0, c->stream>>>(G.H, G.W, G.h, G.w, G.s, st->d_entries, st->d_phase_begin, c->d_y, st->d_yz);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  st->yz_valid = true;
   return SRB_OK;
 }
 
@@ -360,6 +387,35 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
   }
   if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
   k_tile<KH, FRAC, TH, FE><<<grid, D::NT, smem, c->stream>>>(P, mx, mw);
+  if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
+  return SRB_OK;
+}
+
+// k_tile_z launch (Z layout); returns SRB_ERR_STATE without launching when a tensor map cannot be made
+// (the caller then launches k_tile).
+template <int KH>
+inline srb_status tile_launch_z(srb_ctx* c, TileParams& P, int unit_end) {
+  using D = TileDims<KH, false, 32>;
+  constexpr int HYC = (KH + 1) & ~1;
+  const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
+  const TileState* st = tile_state(c);
+  CUtensorMap mx, mw, my;
+  memset(&mx, 0, sizeof mx);
+  memset(&mw, 0, sizeof mw);
+  memset(&my, 0, sizeof my);
+  bool ok = make_plane_map(st, &mx, P.x, P.W, P.H, P.Ca, D::XW, D::XH);
+  if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, P.Ca, D::WW, D::WH);
+  if (ok) ok = make_plane_map(st, &my, P.yz, P.W, P.H, P.Ct, FT_W + 2 * HYC, 32 + 2 * KH);
+  if (!ok) return SRB_ERR_STATE;
+  P.use_tma = 1;
+  const size_t smem = D::smem_bytes(P.num_entries);
+  static size_t attr_set[64] = {};
+  if (c->device >= 64 || attr_set[c->device] < smem) {
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile_z<KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->device < 64) attr_set[c->device] = smem;
+  }
+  if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
+  k_tile_z<KH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw, my);
   if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
   return SRB_OK;
 }
@@ -420,6 +476,7 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   P.fast_y = st->d_fast_y[TH == 64 ? 1 : 0];
   P.fast_E = st->plan.fast_E;
   P.fast_items = (int)st->plan.fast[TH == 64 ? 1 : 0].size();
+  P.yz = st->yz_valid ? st->d_yz : nullptr;
   P.unit_begin = unit_begin;
   const TileLayout L = tile_layout(c);
   const size_t need = 2 * L.nblocks + L.nband;
@@ -439,6 +496,21 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   // frames per sub-pixel phase the table-driven residual pass is specialised for (1, 2 or 4)
   const int fe = (!st->frac && P.fast != nullptr && (P.fast_E == 2 || P.fast_E == 4)) ? P.fast_E : 1;
   if (P.fast_E != fe) P.fast = nullptr;  // a kernel only ever sees the table it is specialised for
+  if (P.yz != nullptr && TH == 32 && fe == 1 && !st->frac) {  // Z layout (opt-in)
+    srb_status zr = SRB_ERR_STATE;
+    switch (st->KH) {
+      case 1: zr = tile_launch_z<1>(c, P, unit_end); break;
+      case 2: zr = tile_launch_z<2>(c, P, unit_end); break;
+      case 3: zr = tile_launch_z<3>(c, P, unit_end); break;
+      case 4: zr = tile_launch_z<4>(c, P, unit_end); break;
+      default: break;
+    }
+    if (zr == SRB_OK) {
+      c->timing.kernel_launches += 1;
+      return SRB_OK;
+    }
+    if (zr != SRB_ERR_STATE) return zr;
+  }
   const int key = ((st->KH * 2 + (st->frac ? 1 : 0)) * 2 + (TH == 64 ? 1 : 0)) * 3 + (fe == 1 ? 0 : fe == 2 ? 1 : 2);
   switch (key) {
 #define SRB_TILE_CASE_FE(KH_, FR_, TH_, FE_, IDX_) \

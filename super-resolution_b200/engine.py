@@ -37,6 +37,7 @@ SIGNATURES = {
     "srb_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "srb_set_path": (C.c_int, [_ctx_p, C.c_int]),
     "srb_active_path": (C.c_int, [_ctx_p]),
+    "srb_zlayout_active": (C.c_int, [_ctx_p]),
     "srb_set_regularizer_rows": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     "srb_eval": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_eval_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
@@ -234,6 +235,10 @@ class Engine:
     @property
     def active_path(self):
         return self._lib.srb_active_path(self._ctx)
+
+    @property
+    def zlayout_active(self):
+        return bool(self._lib.srb_zlayout_active(self._ctx))
 
     def set_regularizer_rows(self, r0, r1):
         self._check(self._lib.srb_set_regularizer_rows(self._ctx, int(r0), int(r1)))
