@@ -1,0 +1,82 @@
+// cg_host_harness.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+// Instantiates the product's CG restatement (super-resolution_b200/csrc/srb_cg.h) over plain host
+// arrays with ALGLIB's summation orders (ap.cpp:4667-4692 ae_v_dotproduct: groups of four; the
+// hand-written loops of mincgiteration: left to right), so that tests/test_cg_restatement.py can
+// compare it bit for bit with the reference's own ALGLIB (oracle/_ref, ref_mincg).  The product
+// instantiates the same template over device vectors (srb_cg_device.cuh).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../super-resolution_b200/csrc/srb_cg.h"
+
+extern "C" {
+typedef void (*srbcg_fg_cb)(long long n, const double* x, double* f, double* g, void* user);
+}
+
+namespace {
+
+struct HostBackend {
+  using Vec = double*;
+  long long n;
+  srbcg_fg_cb cb;
+  void* user;
+  long long evals = 0;
+
+  long long size() const { return n; }
+  void eval(Vec x, double* f, Vec g) { cb(n, x, f, g, user); ++evals; }
+  void copy(Vec d, Vec s) { std::memcpy(d, s, (size_t)n * sizeof(double)); }
+  void neg_copy(Vec d, Vec s) { for (long long i = 0; i < n; ++i) d[i] = -s[i]; }
+  void scale_to(Vec d, Vec s, double a) { for (long long i = 0; i < n; ++i) d[i] = s[i] * a; }
+  void scale(Vec v, double a) { for (long long i = 0; i < n; ++i) v[i] *= a; }
+  void step_to(Vec d, Vec b, double a, Vec dir) { for (long long i = 0; i < n; ++i) d[i] = b[i] + a * dir[i]; }
+  void add(Vec d, Vec s) { for (long long i = 0; i < n; ++i) d[i] += s[i]; }
+  void add_scaled(Vec d, double a, Vec s) { for (long long i = 0; i < n; ++i) d[i] += a * s[i]; }
+  void zero(Vec v) { for (long long i = 0; i < n; ++i) v[i] = 0.0; }
+  double dot(Vec a, Vec b) {
+    double r = 0;
+    const long long n4 = n / 4;
+    long long i = 0;
+    for (long long k = 0; k < n4; ++k, i += 4) r += a[i] * b[i] + a[i + 1] * b[i + 1] + a[i + 2] * b[i + 2] + a[i + 3] * b[i + 3];
+    for (; i < n; ++i) r += a[i] * b[i];
+    return r;
+  }
+  double sum_sq(Vec a) {
+    double r = 0;
+    for (long long i = 0; i < n; ++i) r = r + a[i] * a[i];
+    return r;
+  }
+  double sum_sq_diff(Vec a, Vec b) {
+    double r = 0;
+    for (long long i = 0; i < n; ++i) r = r + (a[i] - b[i]) * (a[i] - b[i]);
+    return r;
+  }
+  double max_abs(Vec a) {
+    double m = 0;
+    for (long long i = 0; i < n; ++i) m = std::fabs(a[i]) > m ? std::fabs(a[i]) : m;
+    return m;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+// report: [iterations, nfev, termination type, final f, restarts, objective evaluations]
+int srbcg_host_minimize(long long n, double* x_inout, double epsg, double epsf, double epsx, int maxits,
+                        srbcg_fg_cb cb, void* user, double* report) {
+  HostBackend be{n, cb, user};
+  std::vector<double> store((size_t)7 * n);
+  double* scratch[7];
+  for (int i = 0; i < 7; ++i) scratch[i] = store.data() + (size_t)i * n;
+  srb::CgOptions opt;
+  opt.epsg = epsg; opt.epsf = epsf; opt.epsx = epsx; opt.maxits = maxits;
+  const srb::CgReport rep = srb::cg_minimize(be, x_inout, scratch, opt);
+  report[0] = rep.iterations;
+  report[1] = rep.nfev;
+  report[2] = rep.termination;
+  report[3] = rep.f;
+  report[4] = rep.restarts;
+  report[5] = (double)be.evals;
+  return 0;
+}
+}

@@ -351,4 +351,40 @@ int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has
   return 0;
 }
 
+// ---- ALGLIB's mincg on an arbitrary objective (C callback), configured exactly as
+// RunCGSolverAnalyticalDiff does (alglib_objective.cpp:47-75).  The checker of the device-resident
+// CG restatement (super-resolution_b200/csrc/srb_cg.h): tests/test_cg_restatement.py runs both on the
+// same objectives and compares iterates bit for bit.
+typedef void (*ref_fg_cb)(long long n, const double* x, double* f, double* g, void* user);
+namespace {
+struct FgClosure { ref_fg_cb cb; void* user; };
+void FgThunk(const alglib::real_1d_array& x, double& func, alglib::real_1d_array& grad, void* ptr) {
+  const FgClosure* c = reinterpret_cast<const FgClosure*>(ptr);
+  c->cb((long long)x.length(), x.getcontent(), &func, grad.getcontent(), c->user);
+}
+void NoReport(const alglib::real_1d_array&, double, void*) {}
+}  // namespace
+
+// report: [iterations, nfev, termination type, final f (mincgstate.f)]
+int ref_mincg(long long n, double* x_inout, double epsg, double epsf, double epsx, int maxits, ref_fg_cb cb,
+              void* user, double* report) {
+  alglib::real_1d_array x;
+  x.setcontent((alglib::ae_int_t)n, x_inout);
+  alglib::mincgstate state;
+  alglib::mincgreport rep;
+  alglib::mincgcreate(x, state);
+  alglib::mincgsetcond(state, epsg, epsf, epsx, maxits);
+  alglib::mincgsetxrep(state, true);
+  FgClosure closure{cb, user};
+  alglib::mincgoptimize(state, FgThunk, NoReport, &closure);
+  alglib::mincgresults(state, x, rep);
+  std::memcpy(x_inout, x.getcontent(), (size_t)n * sizeof(double));
+  report[0] = (double)rep.iterationscount;
+  report[1] = (double)rep.nfev;
+  report[2] = (double)rep.terminationtype;
+  report[3] = state.f;
+  return 0;
+}
+
 }  // extern "C"
+

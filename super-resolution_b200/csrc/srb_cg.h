@@ -1,0 +1,344 @@
+// srb_cg.h -- nonlinear conjugate gradients with the solver vectors resident wherever the backend
+// keeps them.
+//
+// The reference minimises the MAP objective with ALGLIB's `mincg` (alglib_objective.cpp:47-75:
+// mincgcreate / mincgsetcond / mincgoptimize / mincgresults; ALGLIB 3.x vendored under libs/alglib,
+// optimization.cpp:17137-17850 `mincgiteration`, alglibinternal.cpp:12165-12195 `linminnormalized`,
+// :12313-12640 `mcsrch`, :12972-13232 `mcstep`).  Every evaluation there crosses PCIe twice (x in,
+// g out).  This header restates that algorithm -- the same direction update, line search, safeguards,
+// restart rules and stopping tests, in the same order -- over an abstract vector backend, so that
+// x, g, d, ... never leave the device and only scalars reach the host.  With the host backend of
+// tests/ (sequential sums in ALGLIB's order) the iterates are bit-identical to ALGLIB's; the CUDA
+// backend (srb_cg_device.cuh) differs only in the summation order of its reductions.
+//
+// ALGLIB's defaults as the reference uses them: no preconditioner, unit scales, cgtype = -1 (the
+// min(DY, HS) hybrid clipped at 0), no step bound, analytic gradient, first trial step 1.
+//
+// Backend concept (all vectors have the problem's length n):
+//   using Vec = ...;                       cheap handle
+//   void   eval(Vec x, double* f, Vec g);  objective + gradient at x
+//   void   copy(Vec dst, Vec src);         dst = src
+//   void   neg_copy(Vec dst, Vec src);     dst = -src
+//   void   scale_to(Vec dst, Vec src, double a);            dst = src * a
+//   void   scale(Vec v, double a);                          v *= a
+//   void   step_to(Vec dst, Vec base, double a, Vec dir);   dst = base + a * dir
+//   void   add(Vec dst, Vec src);                           dst += src
+//   void   add_scaled(Vec dst, double a, Vec src);          dst += a * src
+//   void   zero(Vec v);
+//   double dot(Vec a, Vec b);              ALGLIB ae_v_dotproduct
+//   double sum_sq(Vec a);                  sum a_i^2, plain left-to-right loop in ALGLIB
+//   double sum_sq_diff(Vec a, Vec b);      sum (a_i - b_i)^2
+//   double max_abs(Vec a);
+//   long long size();
+#pragma once
+#include <cmath>
+
+namespace srb {
+
+struct CgOptions {  // mincgsetcond (alglib_objective.cpp:57-62)
+  double epsg = 0.0;   // stop when |g| <= epsg
+  double epsf = 0.0;   // stop when f_k - f_{k+1} <= epsf * max(|f_k|, |f_{k+1}|, 1)
+  double epsx = 0.0;   // stop when the step length <= epsx
+  int maxits = 0;      // 0: unlimited
+};
+
+struct CgReport {      // mincgreport + the final cost RunCGSolverAnalyticalDiff returns
+  int iterations = 0;
+  int nfev = 0;
+  int termination = 0;  // 1 epsf, 2 epsx, 4 epsg, 5 maxits, 7 repeated restarts, -8 inf / nan
+  int restarts = 0;     // line searches that did not end on the Wolfe conditions
+  double f = 0.0;       // objective at the last evaluated point (mincgstate.f)
+};
+
+namespace cg_detail {
+
+constexpr double kFtol = 1e-3;                     // sufficient decrease
+constexpr double kGtol = 0.3;                      // curvature condition (mincg's)
+constexpr double kXtol = 100 * 5e-16;               // ALGLIB's ae_machineepsilon is 5e-16 (ap.h:855)
+constexpr int kMaxFev = 20;
+constexpr double kStpMin = 1e-50;
+constexpr double kStpMaxDefault = 1e50;
+constexpr int kRestartCountdown = 10;
+
+inline double max2(double a, double b) { return a > b ? a : b; }
+inline double min2(double a, double b) { return a > b ? b : a; }
+
+// Interval of uncertainty of the More-Thuente search: best step so far (x), other end (y).
+struct Bracket {
+  double stx, fx, dx;
+  double sty, fy, dy;
+  bool bracketed;
+};
+
+// One safeguarded trial-step update from the trial (stp, fp, dp); returns which of the four cases
+// applied (0: inputs inconsistent, nothing changed).
+inline int trial_step(Bracket& b, double& stp, double fp, double dp, double stmin, double stmax) {
+  if ((b.bracketed && (stp <= min2(b.stx, b.sty) || stp >= max2(b.stx, b.sty))) ||
+      b.dx * (stp - b.stx) >= 0.0 || stmax < stmin)
+    return 0;
+  const double sgnd = dp * (b.dx / std::fabs(b.dx));
+  int which;
+  bool bound;
+  double stpf;
+  if (fp > b.fx) {
+    // higher value: minimum bracketed; cubic step if closer to stx, else midway to the quadratic one
+    which = 1;
+    bound = true;
+    const double theta = 3 * (b.fx - fp) / (stp - b.stx) + b.dx + dp;
+    const double s = max2(std::fabs(theta), max2(std::fabs(b.dx), std::fabs(dp)));
+    double gamma = s * std::sqrt((theta / s) * (theta / s) - b.dx / s * (dp / s));
+    if (stp < b.stx) gamma = -gamma;
+    const double p = gamma - b.dx + theta;
+    const double q = gamma - b.dx + gamma + dp;
+    const double r = p / q;
+    const double stpc = b.stx + r * (stp - b.stx);
+    const double stpq = b.stx + b.dx / ((b.fx - fp) / (stp - b.stx) + b.dx) / 2 * (stp - b.stx);
+    stpf = std::fabs(stpc - b.stx) < std::fabs(stpq - b.stx) ? stpc : stpc + (stpq - stpc) / 2;
+    b.bracketed = true;
+  } else if (sgnd < 0.0) {
+    // lower value, derivatives of opposite sign: bracketed; the farther of cubic and secant
+    which = 2;
+    bound = false;
+    const double theta = 3 * (b.fx - fp) / (stp - b.stx) + b.dx + dp;
+    const double s = max2(std::fabs(theta), max2(std::fabs(b.dx), std::fabs(dp)));
+    double gamma = s * std::sqrt((theta / s) * (theta / s) - b.dx / s * (dp / s));
+    if (stp > b.stx) gamma = -gamma;
+    const double p = gamma - dp + theta;
+    const double q = gamma - dp + gamma + b.dx;
+    const double r = p / q;
+    const double stpc = stp + r * (b.stx - stp);
+    const double stpq = stp + dp / (dp - b.dx) * (b.stx - stp);
+    stpf = std::fabs(stpc - stp) > std::fabs(stpq - stp) ? stpc : stpq;
+    b.bracketed = true;
+  } else if (std::fabs(dp) < std::fabs(b.dx)) {
+    // lower value, same sign, derivative shrinking: cubic only if it tends to infinity in the step
+    // direction or its minimum lies beyond stp
+    which = 3;
+    bound = true;
+    const double theta = 3 * (b.fx - fp) / (stp - b.stx) + b.dx + dp;
+    const double s = max2(std::fabs(theta), max2(std::fabs(b.dx), std::fabs(dp)));
+    double gamma = s * std::sqrt(max2(0.0, (theta / s) * (theta / s) - b.dx / s * (dp / s)));
+    if (stp > b.stx) gamma = -gamma;
+    const double p = gamma - dp + theta;
+    const double q = gamma + (b.dx - dp) + gamma;
+    const double r = p / q;
+    double stpc;
+    if (r < 0.0 && gamma != 0.0) stpc = stp + r * (b.stx - stp);
+    else stpc = stp > b.stx ? stmax : stmin;
+    const double stpq = stp + dp / (dp - b.dx) * (b.stx - stp);
+    if (b.bracketed) stpf = std::fabs(stp - stpc) < std::fabs(stp - stpq) ? stpc : stpq;
+    else stpf = std::fabs(stp - stpc) > std::fabs(stp - stpq) ? stpc : stpq;
+  } else {
+    // lower value, same sign, derivative not shrinking
+    which = 4;
+    bound = false;
+    if (b.bracketed) {
+      const double theta = 3 * (fp - b.fy) / (b.sty - stp) + b.dy + dp;
+      const double s = max2(std::fabs(theta), max2(std::fabs(b.dy), std::fabs(dp)));
+      double gamma = s * std::sqrt((theta / s) * (theta / s) - b.dy / s * (dp / s));
+      if (stp > b.sty) gamma = -gamma;
+      const double p = gamma - dp + theta;
+      const double q = gamma - dp + gamma + b.dy;
+      const double r = p / q;
+      stpf = stp + r * (b.sty - stp);
+    } else {
+      stpf = stp > b.stx ? stmax : stmin;
+    }
+  }
+  // the interval update does not depend on the case
+  if (fp > b.fx) {
+    b.sty = stp; b.fy = fp; b.dy = dp;
+  } else {
+    if (sgnd < 0.0) { b.sty = b.stx; b.fy = b.fx; b.dy = b.dx; }
+    b.stx = stp; b.fx = fp; b.dx = dp;
+  }
+  stpf = min2(stmax, stpf);
+  stpf = max2(stmin, stpf);
+  stp = stpf;
+  if (b.bracketed && bound) {
+    const double lim = b.stx + 0.66 * (b.sty - b.stx);
+    stp = b.sty > b.stx ? min2(lim, stp) : max2(lim, stp);
+  }
+  return which;
+}
+
+// Line search along the unit direction d from x0 (More-Thuente, ALGLIB's mcsrch).  On entry f / g
+// are the objective and gradient at x0 and stp the first trial step; on exit x, f, g belong to the
+// last point evaluated and stp is its step.  info: 1 Wolfe conditions hold, 2 interval below xtol,
+// 3 evaluation budget, 4 step at the lower bound, 5 step at the upper bound, 6 rounding / no
+// progress, 0 d is not a descent direction (nothing evaluated, nfev left as it was).
+template <class B>
+void line_search(B& be, typename B::Vec x0, typename B::Vec x, double& f, typename B::Vec g, typename B::Vec d,
+                 double& stp, double stpmax, double trim_threshold, int& info, int& nfev) {
+  if (stpmax == 0.0) stpmax = kStpMaxDefault;
+  if (stp < kStpMin) stp = kStpMin;
+  if (stp > stpmax) stp = stpmax;
+  info = 0;
+  if (stpmax < kStpMin && stpmax > 0.0) {
+    info = 5;
+    stp = stpmax;
+    return;
+  }
+  if (be.size() <= 0 || stp <= 0.0 || stpmax < kStpMin) return;
+  const double dginit = be.dot(g, d);
+  if (dginit >= 0.0) return;
+  Bracket br;
+  br.bracketed = false;
+  bool stage1 = true;
+  int infoc = 1;
+  nfev = 0;
+  const double finit = f;
+  const double dgtest = kFtol * dginit;
+  double width = stpmax - kStpMin;
+  double width1 = width / 0.5;
+  br.stx = 0.0; br.fx = finit; br.dx = dginit;
+  br.sty = 0.0; br.fy = finit; br.dy = dginit;
+  for (;;) {
+    double stmin, stmax;
+    if (br.bracketed) {
+      if (br.stx < br.sty) { stmin = br.stx; stmax = br.sty; }
+      else { stmin = br.sty; stmax = br.stx; }
+    } else {
+      stmin = br.stx;
+      stmax = stp + 4.0 * (stp - br.stx);
+    }
+    if (stp > stpmax) stp = stpmax;
+    if (stp < kStpMin) stp = kStpMin;
+    // unusual termination ahead: fall back to the best step so far
+    if ((br.bracketed && (stp <= stmin || stp >= stmax)) || nfev >= kMaxFev - 1 || infoc == 0 ||
+        (br.bracketed && stmax - stmin <= kXtol * stmax))
+      stp = br.stx;
+    be.step_to(x, x0, stp, d);
+    be.eval(x, &f, g);
+    if (f >= trim_threshold) {  // trimfunction: bounded from above near singularities
+      f = trim_threshold;
+      be.zero(g);
+    }
+    info = 0;
+    nfev += 1;
+    const double dg = be.dot(g, d);
+    const double ftest1 = finit + stp * dgtest;
+    if ((br.bracketed && (stp <= stmin || stp >= stmax)) || infoc == 0) info = 6;
+    if (stp == stpmax && f < finit && f <= ftest1 && dg <= dgtest) info = 5;
+    if (stp == kStpMin && (f >= finit || f > ftest1 || dg >= dgtest)) info = 4;
+    if (nfev >= kMaxFev) info = 3;
+    if (br.bracketed && stmax - stmin <= kXtol * stmax) info = 2;
+    if (f < finit && f <= ftest1 && std::fabs(dg) <= -kGtol * dginit) info = 1;
+    if (info != 0) {
+      if (info == 1 || info == 5) {
+        const double moved = be.sum_sq_diff(x0, x);
+        if (f >= finit || moved == 0.0) info = 6;
+      }
+      return;
+    }
+    if (stage1 && f <= ftest1 && dg >= min2(kFtol, kGtol) * dginit) stage1 = false;
+    if (stage1 && f <= br.fx && f > ftest1) {
+      // not enough decrease yet: work on f(x0 + t d) - f(x0) - ftol * t * dginit
+      Bracket m = br;
+      m.fx = br.fx - br.stx * dgtest; m.fy = br.fy - br.sty * dgtest;
+      m.dx = br.dx - dgtest;          m.dy = br.dy - dgtest;
+      infoc = trial_step(m, stp, f - stp * dgtest, dg - dgtest, stmin, stmax);
+      br.stx = m.stx; br.sty = m.sty; br.bracketed = m.bracketed;
+      br.fx = m.fx + m.stx * dgtest; br.fy = m.fy + m.sty * dgtest;
+      br.dx = m.dx + dgtest;         br.dy = m.dy + dgtest;
+    } else {
+      infoc = trial_step(br, stp, f, dg, stmin, stmax);
+    }
+    if (br.bracketed) {  // force a sufficient decrease of the interval
+      if (std::fabs(br.sty - br.stx) >= 0.66 * width1) stp = br.stx + 0.5 * (br.sty - br.stx);
+      width1 = width;
+      width = std::fabs(br.sty - br.stx);
+    }
+  }
+}
+
+}  // namespace cg_detail
+
+// Minimises the backend's objective from x (overwritten with the result).  Scratch: six vectors
+// of the backend (g, xk / xn, dk / dn, d, yk and the trial point).
+template <class B>
+CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec scratch[7], CgOptions opt) {
+  using namespace cg_detail;
+  using Vec = typename B::Vec;
+  if (opt.epsg == 0.0 && opt.epsf == 0.0 && opt.epsx == 0.0 && opt.maxits == 0) opt.epsx = 1e-6;
+  CgReport rep;
+  Vec g = scratch[0], xk = scratch[1], xn = scratch[2], dk = scratch[3], dn = scratch[4], d = scratch[5],
+      yk = scratch[6];
+  Vec x = x_inout;  // the trial point of the line searches; holds the result on return
+  const long long n = be.size();
+  double f = 0.0;
+  be.copy(xk, x);
+  be.eval(x, &f, g);
+  const double trim_threshold = 10 * (std::fabs(f) + 1);
+  be.neg_copy(dk, g);
+  rep.f = f;
+  if (std::sqrt(be.sum_sq(g)) <= opt.epsg) {
+    rep.termination = 4;
+    return rep;  // x == xk
+  }
+  rep.nfev = 1;
+  double fold = f;
+  double last_good_step = 1.0;
+  int restart_timer = kRestartCountdown;
+  int nfev = 0;  // of the last line search that evaluated anything (mincgstate.nfev)
+  for (;;) {
+    be.neg_copy(yk, g);
+    // unit direction; the first trial step is the length of the previous accepted step
+    double stp = 1.0;
+    {
+      const double mx = be.max_abs(dk);
+      if (mx == 0.0) {
+        be.copy(d, dk);
+      } else {
+        double s = 1 / mx;
+        be.scale_to(d, dk, s);
+        stp = stp / s;
+        s = 1 / std::sqrt(be.dot(d, d));
+        be.scale(d, s);
+        stp = stp / s;
+      }
+    }
+    if (last_good_step != 0.0) stp = last_good_step;
+    int info = 0;
+    line_search(be, xk, x, f, g, d, stp, 0.0, trim_threshold, info, nfev);
+    // (info == 0: nothing was evaluated and x still equals xk, the previous trial point)
+    be.copy(xn, x);
+    double beta = 0.0;
+    if (info == 1) {
+      be.add(yk, g);  // y_k = g_{k+1} - g_k
+      const double dy = be.dot(yk, dk);
+      const double beta_dy = be.dot(g, g) / dy;
+      const double beta_hs = be.dot(g, yk) / dy;
+      beta = max2(0.0, min2(beta_dy, beta_hs));
+    } else {
+      rep.restarts += 1;
+    }
+    if (rep.iterations > 0 && rep.iterations % (3 + n) == 0) beta = 0.0;
+    if (info == 1 || info == 5) restart_timer = kRestartCountdown;
+    else restart_timer -= 1;
+    be.neg_copy(dn, g);
+    be.add_scaled(dn, beta, dk);
+    const double step_len = stp * std::sqrt(be.sum_sq(d));
+    if (info == 1) last_good_step = step_len;
+    const double gg = be.sum_sq(g);
+    rep.f = f;
+    if (!std::isfinite(gg) || !std::isfinite(f)) {
+      rep.termination = -8;
+      break;
+    }
+    rep.nfev += nfev;
+    rep.iterations += 1;
+    if (rep.iterations >= opt.maxits && opt.maxits > 0) { rep.termination = 5; break; }
+    if (std::sqrt(gg) <= opt.epsg) { rep.termination = 4; break; }
+    if (fold - f <= opt.epsf * max2(std::fabs(fold), max2(std::fabs(f), 1.0))) { rep.termination = 1; break; }
+    if (step_len <= opt.epsx) { rep.termination = 2; break; }
+    if (restart_timer <= 0) { rep.termination = 7; break; }
+    Vec t = xk; xk = xn; xn = t;
+    t = dk; dk = dn; dn = t;
+    fold = f;
+  }
+  // mincgresults: x = xn (== the last trial point)
+  return rep;
+}
+
+}  // namespace srb
