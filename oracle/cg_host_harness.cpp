@@ -24,22 +24,30 @@ struct HostBackend {
   long long evals = 0;
 
   long long size() const { return n; }
-  void eval(Vec x, double* f, Vec g) { cb(n, x, f, g, user); ++evals; }
+  void eval(Vec x, Vec g, double* f) { cb(n, x, f, g, user); ++evals; }
+  void eval_with_slope(Vec x, Vec g, Vec d, double* f, double* dg) {
+    eval(x, g, f);
+    *dg = dot(g, d);
+  }
   void copy(Vec d, Vec s) { std::memcpy(d, s, (size_t)n * sizeof(double)); }
   void neg_copy(Vec d, Vec s) { for (long long i = 0; i < n; ++i) d[i] = -s[i]; }
   void scale_to(Vec d, Vec s, double a) { for (long long i = 0; i < n; ++i) d[i] = s[i] * a; }
   void scale(Vec v, double a) { for (long long i = 0; i < n; ++i) v[i] *= a; }
   void step_to(Vec d, Vec b, double a, Vec dir) { for (long long i = 0; i < n; ++i) d[i] = b[i] + a * dir[i]; }
-  void add(Vec d, Vec s) { for (long long i = 0; i < n; ++i) d[i] += s[i]; }
-  void add_scaled(Vec d, double a, Vec s) { for (long long i = 0; i < n; ++i) d[i] += a * s[i]; }
   void zero(Vec v) { for (long long i = 0; i < n; ++i) v[i] = 0.0; }
-  double dot(Vec a, Vec b) {
+  // ae_v_dotproduct: groups of four, then the remainder
+  template <class FA, class FB>
+  double dot4(FA a, FB b) {
     double r = 0;
     const long long n4 = n / 4;
     long long i = 0;
-    for (long long k = 0; k < n4; ++k, i += 4) r += a[i] * b[i] + a[i + 1] * b[i + 1] + a[i + 2] * b[i + 2] + a[i + 3] * b[i + 3];
-    for (; i < n; ++i) r += a[i] * b[i];
+    for (long long k = 0; k < n4; ++k, i += 4)
+      r += a(i) * b(i) + a(i + 1) * b(i + 1) + a(i + 2) * b(i + 2) + a(i + 3) * b(i + 3);
+    for (; i < n; ++i) r += a(i) * b(i);
     return r;
+  }
+  double dot(Vec a, Vec b) {
+    return dot4([a](long long i) { return a[i]; }, [b](long long i) { return b[i]; });
   }
   double sum_sq(Vec a) {
     double r = 0;
@@ -56,6 +64,17 @@ struct HostBackend {
     for (long long i = 0; i < n; ++i) m = std::fabs(a[i]) > m ? std::fabs(a[i]) : m;
     return m;
   }
+  void beta_terms(Vec gn, Vec go, Vec dk, double* dy, double* gg, double* gy) {
+    auto y = [gn, go](long long i) { return -go[i] + gn[i]; };  // yk = -g_old, then yk += g_new
+    *dy = dot4(y, [dk](long long i) { return dk[i]; });
+    *gg = dot(gn, gn);
+    *gy = dot4([gn](long long i) { return gn[i]; }, y);
+  }
+  void direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg) {
+    for (long long i = 0; i < n; ++i) dk[i] = -g[i] + beta * dk[i];
+    *dd = sum_sq(d);
+    *gg = sum_sq(g);
+  }
 };
 
 }  // namespace
@@ -65,9 +84,9 @@ extern "C" {
 int srbcg_host_minimize(long long n, double* x_inout, double epsg, double epsf, double epsx, int maxits,
                         srbcg_fg_cb cb, void* user, double* report) {
   HostBackend be{n, cb, user};
-  std::vector<double> store((size_t)7 * n);
-  double* scratch[7];
-  for (int i = 0; i < 7; ++i) scratch[i] = store.data() + (size_t)i * n;
+  std::vector<double> store((size_t)srb::kCgScratchVectors * n);
+  double* scratch[srb::kCgScratchVectors];
+  for (int i = 0; i < srb::kCgScratchVectors; ++i) scratch[i] = store.data() + (size_t)i * n;
   srb::CgOptions opt;
   opt.epsg = epsg; opt.epsf = epsf; opt.epsx = epsx; opt.maxits = maxits;
   const srb::CgReport rep = srb::cg_minimize(be, x_inout, scratch, opt);

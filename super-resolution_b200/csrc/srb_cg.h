@@ -14,22 +14,26 @@
 // ALGLIB's defaults as the reference uses them: no preconditioner, unit scales, cgtype = -1 (the
 // min(DY, HS) hybrid clipped at 0), no step bound, analytic gradient, first trial step 1.
 //
-// Backend concept (all vectors have the problem's length n):
+// Backend concept (all vectors have the problem's length n; "sum" orders are ALGLIB's on the host
+// backend of the tests, free on the device):
 //   using Vec = ...;                       cheap handle
-//   void   eval(Vec x, double* f, Vec g);  objective + gradient at x
-//   void   copy(Vec dst, Vec src);         dst = src
-//   void   neg_copy(Vec dst, Vec src);     dst = -src
-//   void   scale_to(Vec dst, Vec src, double a);            dst = src * a
-//   void   scale(Vec v, double a);                          v *= a
-//   void   step_to(Vec dst, Vec base, double a, Vec dir);   dst = base + a * dir
-//   void   add(Vec dst, Vec src);                           dst += src
-//   void   add_scaled(Vec dst, double a, Vec src);          dst += a * src
-//   void   zero(Vec v);
-//   double dot(Vec a, Vec b);              ALGLIB ae_v_dotproduct
-//   double sum_sq(Vec a);                  sum a_i^2, plain left-to-right loop in ALGLIB
-//   double sum_sq_diff(Vec a, Vec b);      sum (a_i - b_i)^2
-//   double max_abs(Vec a);
 //   long long size();
+//   void   eval(Vec x, Vec g, double* f);                      objective + gradient at x
+//   void   eval_with_slope(Vec x, Vec g, Vec d, double* f, double* dg);   ... and dg = <g, d>
+//   void   copy(Vec dst, Vec src);
+//   void   neg_copy(Vec dst, Vec src);                         dst = -src
+//   void   scale_to(Vec dst, Vec src, double a);               dst = src * a
+//   void   scale(Vec v, double a);                             v *= a
+//   void   step_to(Vec dst, Vec base, double a, Vec dir);      dst = base + a * dir
+//   void   zero(Vec v);
+//   double dot(Vec a, Vec b);                                  ae_v_dotproduct (ap.cpp:4667-4692)
+//   double sum_sq_diff(Vec a, Vec b);                          sum (a_i - b_i)^2
+//   double max_abs(Vec a);
+//   double sum_sq(Vec a);                                      sum a_i^2 (plain loop in ALGLIB)
+//   void   beta_terms(Vec g_new, Vec g_old, Vec dk, double* dy, double* gg, double* gy);
+//            with y = g_new - g_old:  dy = <y, dk>, gg = <g_new, g_new>, gy = <g_new, y>
+//   void   direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg);
+//            dk = -g + beta * dk (in place);  dd = sum d_i^2, gg = sum g_i^2 (plain loops in ALGLIB)
 #pragma once
 #include <cmath>
 
@@ -162,14 +166,14 @@ inline int trial_step(Bracket& b, double& stp, double fp, double dp, double stmi
   return which;
 }
 
-// Line search along the unit direction d from x0 (More-Thuente, ALGLIB's mcsrch).  On entry f / g
-// are the objective and gradient at x0 and stp the first trial step; on exit x, f, g belong to the
-// last point evaluated and stp is its step.  info: 1 Wolfe conditions hold, 2 interval below xtol,
-// 3 evaluation budget, 4 step at the lower bound, 5 step at the upper bound, 6 rounding / no
-// progress, 0 d is not a descent direction (nothing evaluated, nfev left as it was).
+// Line search along the unit direction d from x0 (More-Thuente, ALGLIB's mcsrch).  On entry f and
+// g0 are the objective and gradient at x0 and stp the first trial step; on exit x, f, g belong to
+// the last point evaluated and stp is its step (g0 is left alone).  info: 1 Wolfe conditions hold,
+// 2 interval below xtol, 3 evaluation budget, 4 step at the lower bound, 5 step at the upper bound,
+// 6 rounding / no progress, 0 d is not a descent direction (nothing evaluated, nfev left as it was).
 template <class B>
-void line_search(B& be, typename B::Vec x0, typename B::Vec x, double& f, typename B::Vec g, typename B::Vec d,
-                 double& stp, double stpmax, double trim_threshold, int& info, int& nfev) {
+void line_search(B& be, typename B::Vec x0, typename B::Vec g0, typename B::Vec x, typename B::Vec g, double& f,
+                 typename B::Vec d, double& stp, double stpmax, double trim_threshold, int& info, int& nfev) {
   if (stpmax == 0.0) stpmax = kStpMaxDefault;
   if (stp < kStpMin) stp = kStpMin;
   if (stp > stpmax) stp = stpmax;
@@ -180,7 +184,7 @@ void line_search(B& be, typename B::Vec x0, typename B::Vec x, double& f, typena
     return;
   }
   if (be.size() <= 0 || stp <= 0.0 || stpmax < kStpMin) return;
-  const double dginit = be.dot(g, d);
+  const double dginit = be.dot(g0, d);
   if (dginit >= 0.0) return;
   Bracket br;
   br.bracketed = false;
@@ -209,14 +213,15 @@ void line_search(B& be, typename B::Vec x0, typename B::Vec x, double& f, typena
         (br.bracketed && stmax - stmin <= kXtol * stmax))
       stp = br.stx;
     be.step_to(x, x0, stp, d);
-    be.eval(x, &f, g);
+    double dg = 0.0;
+    be.eval_with_slope(x, g, d, &f, &dg);
     if (f >= trim_threshold) {  // trimfunction: bounded from above near singularities
       f = trim_threshold;
       be.zero(g);
+      dg = be.dot(g, d);
     }
     info = 0;
     nfev += 1;
-    const double dg = be.dot(g, d);
     const double ftest1 = finit + stp * dgtest;
     if ((br.bracketed && (stp <= stmin || stp >= stmax)) || infoc == 0) info = 6;
     if (stp == stpmax && f < finit && f <= ftest1 && dg <= dgtest) info = 5;
@@ -254,27 +259,29 @@ void line_search(B& be, typename B::Vec x0, typename B::Vec x, double& f, typena
 
 }  // namespace cg_detail
 
-// Minimises the backend's objective from x (overwritten with the result).  Scratch: six vectors
-// of the backend (g, xk / xn, dk / dn, d, yk and the trial point).
+// Minimises the backend's objective from x (overwritten with the result).  Scratch: five vectors
+// (the second point of the x rotation, two gradients, the CG direction, the unit search direction);
+// ALGLIB keeps eleven (xk, xn, dk, dn, x, d, g, yk, work0, work1, s): the copies between them are
+// pointer rotations here, y_k and d_{k+1} are formed on the fly.
+constexpr int kCgScratchVectors = 5;
 template <class B>
-CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec scratch[7], CgOptions opt) {
+CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, CgOptions opt) {
   using namespace cg_detail;
   using Vec = typename B::Vec;
   if (opt.epsg == 0.0 && opt.epsf == 0.0 && opt.epsx == 0.0 && opt.maxits == 0) opt.epsx = 1e-6;
   CgReport rep;
-  Vec g = scratch[0], xk = scratch[1], xn = scratch[2], dk = scratch[3], dn = scratch[4], d = scratch[5],
-      yk = scratch[6];
-  Vec x = x_inout;  // the trial point of the line searches; holds the result on return
+  Vec xk = x_inout, xt = scratch[0];  // current point, trial point of the line search
+  Vec gk = scratch[1], gt = scratch[2];
+  Vec dk = scratch[3], d = scratch[4];
   const long long n = be.size();
   double f = 0.0;
-  be.copy(xk, x);
-  be.eval(x, &f, g);
+  be.eval(xk, gk, &f);
   const double trim_threshold = 10 * (std::fabs(f) + 1);
-  be.neg_copy(dk, g);
+  be.neg_copy(dk, gk);
   rep.f = f;
-  if (std::sqrt(be.sum_sq(g)) <= opt.epsg) {
+  if (std::sqrt(be.sum_sq(gk)) <= opt.epsg) {
     rep.termination = 4;
-    return rep;  // x == xk
+    return rep;
   }
   rep.nfev = 1;
   double fold = f;
@@ -282,7 +289,6 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec scratch[7],
   int restart_timer = kRestartCountdown;
   int nfev = 0;  // of the last line search that evaluated anything (mincgstate.nfev)
   for (;;) {
-    be.neg_copy(yk, g);
     // unit direction; the first trial step is the length of the previous accepted step
     double stp = 1.0;
     {
@@ -300,32 +306,30 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec scratch[7],
     }
     if (last_good_step != 0.0) stp = last_good_step;
     int info = 0;
-    line_search(be, xk, x, f, g, d, stp, 0.0, trim_threshold, info, nfev);
-    // (info == 0: nothing was evaluated and x still equals xk, the previous trial point)
-    be.copy(xn, x);
+    line_search(be, xk, gk, xt, gt, f, d, stp, 0.0, trim_threshold, info, nfev);
+    if (info == 0) {  // nothing was evaluated: the "new" point is the current one
+      be.copy(xt, xk);
+      be.copy(gt, gk);
+    }
     double beta = 0.0;
     if (info == 1) {
-      be.add(yk, g);  // y_k = g_{k+1} - g_k
-      const double dy = be.dot(yk, dk);
-      const double beta_dy = be.dot(g, g) / dy;
-      const double beta_hs = be.dot(g, yk) / dy;
-      beta = max2(0.0, min2(beta_dy, beta_hs));
+      double dy, gg, gy;
+      be.beta_terms(gt, gk, dk, &dy, &gg, &gy);
+      beta = max2(0.0, min2(gg / dy, gy / dy));  // min(Dai-Yuan, Hestenes-Stiefel), clipped at 0
     } else {
       rep.restarts += 1;
     }
     if (rep.iterations > 0 && rep.iterations % (3 + n) == 0) beta = 0.0;
     if (info == 1 || info == 5) restart_timer = kRestartCountdown;
     else restart_timer -= 1;
-    be.neg_copy(dn, g);
-    be.add_scaled(dn, beta, dk);
-    const double step_len = stp * std::sqrt(be.sum_sq(d));
+    double dd, gg;
+    be.direction(dk, gt, beta, d, &dd, &gg);
+    const double step_len = stp * std::sqrt(dd);
     if (info == 1) last_good_step = step_len;
-    const double gg = be.sum_sq(g);
     rep.f = f;
-    if (!std::isfinite(gg) || !std::isfinite(f)) {
-      rep.termination = -8;
-      break;
-    }
+    Vec t = xk; xk = xt; xt = t;  // the accepted point becomes the current one
+    t = gk; gk = gt; gt = t;
+    if (!std::isfinite(gg) || !std::isfinite(f)) { rep.termination = -8; break; }
     rep.nfev += nfev;
     rep.iterations += 1;
     if (rep.iterations >= opt.maxits && opt.maxits > 0) { rep.termination = 5; break; }
@@ -333,11 +337,9 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec scratch[7],
     if (fold - f <= opt.epsf * max2(std::fabs(fold), max2(std::fabs(f), 1.0))) { rep.termination = 1; break; }
     if (step_len <= opt.epsx) { rep.termination = 2; break; }
     if (restart_timer <= 0) { rep.termination = 7; break; }
-    Vec t = xk; xk = xn; xn = t;
-    t = dk; dk = dn; dn = t;
     fold = f;
   }
-  // mincgresults: x = xn (== the last trial point)
+  if (xk != x_inout) be.copy(x_inout, xk);  // mincgresults: the last point of the last line search
   return rep;
 }
 
