@@ -128,6 +128,48 @@ srb_status srb_set_irls_weights(srb_ctx* ctx, const double* weights_host);
  * x_host = NULL re-uses the estimate of the last evaluation; weights_out_host may be NULL. */
 srb_status srb_reweight(srb_ctx* ctx, const double* x_host, double* weights_out_host);
 
+/* ---- device-resident solver ------------------------------------
+ * The reference minimises with ALGLIB's mincg on host arrays (RunCGSolverAnalyticalDiff,
+ * alglib_objective.cpp:47-75), so every evaluation moves x and g across PCIe.  These entry points
+ * run the same algorithm (csrc/srb_cg.h: a restatement of mincgiteration / mcsrch / mcstep, pinned
+ * bit for bit against the reference's ALGLIB on the CPU) with all solver vectors in HBM; only
+ * scalars reach the host.  Thresholds as in MapSolverOptions (map_solver.h:25-60) after
+ * AdjustThresholdsAdaptively; all zero selects ALGLIB's automatic EpsX = 1e-6. */
+typedef struct srb_cg_options {
+  double gradient_norm_threshold;        /* mincgsetcond EpsG */
+  double cost_decrease_threshold;        /* EpsF */
+  double parameter_variation_threshold;  /* EpsX */
+  int max_num_solver_iterations;         /* MaxIts, 0 = unlimited */
+} srb_cg_options;
+typedef struct srb_cg_report {   /* alglib::mincgreport + the cost RunCGSolverAnalyticalDiff returns */
+  int iterations;
+  int num_evaluations;
+  int termination_type;          /* 1 EpsF, 2 EpsX, 4 EpsG, 5 MaxIts, 7 repeated restarts, -8 inf / nan */
+  int num_restarts;
+  double final_cost;
+} srb_cg_report;
+typedef struct srb_irls_report {
+  int num_irls_iterations;
+  int num_solver_iterations;     /* summed over the outer iterations */
+  int num_evaluations;
+  int last_termination_type;
+  double final_cost;
+} srb_irls_report;
+/* RunCGSolverAnalyticalDiff for the active channel range with the current regularizer and IRLS
+ * weights: x (n = (c1-c0)*H*W doubles) is the initial estimate on entry and the solution on return.
+ * options = NULL: all thresholds zero. */
+srb_status srb_cg_minimize(srb_ctx* ctx, double* x_host_inout, const srb_cg_options* options,
+                           srb_cg_report* report);
+srb_status srb_cg_minimize_dev(srb_ctx* ctx, double* x_dev_inout, const srb_cg_options* options,
+                               srb_cg_report* report);
+/* IRLSMapSolver::RunIRLSLoop (irls_map_solver.cpp:45-157) for the active channel range: weights reset
+ * to 1, then { CG solve; w = 1 / max(1e-5, reg(x)) } until the cost of two consecutive outer
+ * iterations differs by less than irls_cost_difference_threshold or max_num_irls_iterations (0 =
+ * unlimited) is reached; a single CG solve when no regularizer is configured. */
+srb_status srb_solve_irls(srb_ctx* ctx, double* x_host_inout, const srb_cg_options* options,
+                          int max_num_irls_iterations, double irls_cost_difference_threshold,
+                          srb_irls_report* report);
+
 /* Which kernel path evaluations take (default SRB_PATH_AUTO); srb_active_path reports the one
  * the current configuration resolves to. */
 srb_status srb_set_path(srb_ctx* ctx, int path);

@@ -225,6 +225,8 @@ srb_status build_host_model(srb_ctx* c, const srb_model_desc* d) {
 
 }  // namespace
 
+#include "srb_cg_device.cuh"  // device-resident CG (needs eval_core)
+
 // ================================================================================================
 extern "C" {
 
@@ -470,19 +472,116 @@ srb_status srb_set_irls_weights(srb_ctx* c, const double* w) {
   return SRB_OK;
 }
 
+// w = 1 / max(1e-5, reg(x)) for a device-resident estimate (irls_map_solver.cpp:128-143), stream-ordered
+static srb_status reweight_dev(srb_ctx* c, const double* d_x) {
+  k_reg_values<1><<<grid2d(c->g.W, c->g.H, c->Ca()), dim3(32, 8), 0, c->stream>>>(
+      make_reg_params(c, c->Ca()), d_x, c->d_w);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  return SRB_OK;
+}
+
 srb_status srb_reweight(srb_ctx* c, const double* x_host, double* w_out) {
   if (!c) return SRB_ERR_INVALID;
   if (!reg_active(c)) return c->fail(SRB_ERR_STATE, "no regularizer configured");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   if (x_host)
     SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, c->n_active() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  k_reg_values<1><<<grid2d(c->g.W, c->g.H, c->Ca()), dim3(32, 8), 0, c->stream>>>(
-      make_reg_params(c, c->Ca()), c->d_x, c->d_w);
-  c->timing.kernel_launches += 1;
-  SRB_CUDA_CHECK(c, cudaGetLastError());
+  srb_status rst = reweight_dev(c, c->d_x);
+  if (rst != SRB_OK) return rst;
   if (w_out)
     SRB_CUDA_CHECK(c, cudaMemcpyAsync(w_out, c->d_w, c->n_active() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+// ---- device-resident solver --------------------------------------------------------
+static CgOptions cg_options_from(const srb_cg_options* o) {
+  CgOptions opt;
+  if (o) {
+    opt.epsg = o->gradient_norm_threshold;
+    opt.epsf = o->cost_decrease_threshold;
+    opt.epsx = o->parameter_variation_threshold;
+    opt.maxits = o->max_num_solver_iterations;
+  }
+  return opt;
+}
+static bool cg_options_valid(const srb_cg_options* o) {
+  // mincgsetcond asserts finite, non-negative thresholds and a non-negative iteration limit
+  return !o || (std::isfinite(o->gradient_norm_threshold) && o->gradient_norm_threshold >= 0 &&
+                std::isfinite(o->cost_decrease_threshold) && o->cost_decrease_threshold >= 0 &&
+                std::isfinite(o->parameter_variation_threshold) && o->parameter_variation_threshold >= 0 &&
+                o->max_num_solver_iterations >= 0);
+}
+static void cg_report_to(const CgReport& r, srb_cg_report* out) {
+  if (!out) return;
+  out->iterations = r.iterations;
+  out->num_evaluations = r.nfev;
+  out->termination_type = r.termination;
+  out->num_restarts = r.restarts;
+  out->final_cost = r.f;
+}
+
+srb_status srb_cg_minimize_dev(srb_ctx* c, double* x_dev, const srb_cg_options* options, srb_cg_report* report) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev) return c->fail(SRB_ERR_INVALID, "null estimate");
+  if (!cg_options_valid(options)) return c->fail(SRB_ERR_INVALID, "invalid solver thresholds");
+  if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  CgReport rep;
+  srb_status st = cg_minimize_dev(c, x_dev, cg_options_from(options), &rep);
+  if (st != SRB_OK) return st;
+  cg_report_to(rep, report);
+  return SRB_OK;
+}
+
+srb_status srb_cg_minimize(srb_ctx* c, double* x_host, const srb_cg_options* options, srb_cg_report* report) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t bytes = c->n_active() * sizeof(double);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  srb_status st = srb_cg_minimize_dev(c, c->d_x, options, report);
+  if (st != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(x_host, c->d_x, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SRB_OK;
+}
+
+srb_status srb_solve_irls(srb_ctx* c, double* x_host, const srb_cg_options* options, int max_num_irls_iterations,
+                          double irls_cost_difference_threshold, srb_irls_report* report) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
+  if (!cg_options_valid(options) || max_num_irls_iterations < 0 || !(irls_cost_difference_threshold >= 0))
+    return c->fail(SRB_ERR_INVALID, "invalid solver options");
+  if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t bytes = c->n_active() * sizeof(double);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  srb_status st = reset_weights(c);  // irls_map_solver.cpp:66-74: all weights 1
+  if (st != SRB_OK) return st;
+  const CgOptions opt = cg_options_from(options);
+  srb_irls_report out{};
+  // irls_map_solver.cpp:45-157
+  double previous_cost = INFINITY;
+  double cost_difference = irls_cost_difference_threshold + 1.0;
+  while (std::fabs(cost_difference) >= irls_cost_difference_threshold) {
+    CgReport rep;
+    if ((st = cg_minimize_dev(c, c->d_x, opt, &rep)) != SRB_OK) return st;
+    out.num_solver_iterations += rep.iterations;
+    out.num_evaluations += rep.nfev;
+    out.last_termination_type = rep.termination;
+    out.final_cost = rep.f;
+    if (!reg_active(c)) break;  // :118-121: nothing to re-weight
+    if ((st = reweight_dev(c, c->d_x)) != SRB_OK) return st;
+    cost_difference = previous_cost - rep.f;
+    previous_cost = rep.f;
+    out.num_irls_iterations += 1;
+    if (max_num_irls_iterations > 0 && out.num_irls_iterations >= max_num_irls_iterations) break;
+  }
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(x_host, c->d_x, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (report) *report = out;
   return SRB_OK;
 }
 

@@ -35,6 +35,9 @@ SIGNATURES = {
     "srb_set_regularizer": (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_double]),
     "srb_set_irls_weights": (C.c_int, [_ctx_p, C.c_void_p]),
     "srb_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_cg_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_cg_minimize_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_solve_irls": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "srb_set_path": (C.c_int, [_ctx_p, C.c_int]),
     "srb_active_path": (C.c_int, [_ctx_p]),
     "srb_zlayout_active": (C.c_int, [_ctx_p]),
@@ -85,6 +88,26 @@ class Timing(C.Structure):
                 ("last_eval_d2h_ms", C.c_double), ("num_evals", C.c_ulonglong),
                 ("kernel_launches", C.c_ulonglong), ("algorithmic_bytes_per_eval", C.c_ulonglong),
                 ("last_main_kernel_ms", C.c_double)]
+
+
+class CgOptions(C.Structure):
+    """srb_cg_options: the thresholds of mincgsetcond (alglib_objective.cpp:57-62)."""
+    _fields_ = [("gradient_norm_threshold", C.c_double), ("cost_decrease_threshold", C.c_double),
+                ("parameter_variation_threshold", C.c_double), ("max_num_solver_iterations", C.c_int)]
+
+
+class CgReport(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("num_evaluations", C.c_int), ("termination_type", C.c_int),
+                ("num_restarts", C.c_int), ("final_cost", C.c_double)]
+
+
+class IrlsReport(C.Structure):
+    _fields_ = [("num_irls_iterations", C.c_int), ("num_solver_iterations", C.c_int),
+                ("num_evaluations", C.c_int), ("last_termination_type", C.c_int), ("final_cost", C.c_double)]
+
+
+def _as_dict(st):
+    return {name: getattr(st, name) for name, _ in st._fields_}
 
 
 class PlanInfo(C.Structure):
@@ -228,6 +251,34 @@ class Engine:
         out = np.empty(self.num_active) if want_weights else None
         self._check(self._lib.srb_reweight(self._ctx, _host_ptr(xa), _host_ptr(out)))
         return None if out is None else out.reshape(self.c1 - self.c0, self.H, self.W)
+
+    # -- device-resident solver
+    @staticmethod
+    def _cg_options(epsg, epsf, epsx, maxits):
+        return CgOptions(float(epsg), float(epsf), float(epsx), int(maxits))
+
+    def cg_minimize(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        """RunCGSolverAnalyticalDiff with the solver vectors on the device.  Returns (x, report dict)."""
+        x = np.array(_f64(x0).reshape(-1), copy=True)
+        assert x.size == self.num_active
+        opt, rep = self._cg_options(epsg, epsf, epsx, maxits), CgReport()
+        self._check(self._lib.srb_cg_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
+        return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
+
+    def cg_minimize_dev(self, x_dev, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        opt, rep = self._cg_options(epsg, epsf, epsx, maxits), CgReport()
+        self._check(self._lib.srb_cg_minimize_dev(self._ctx, _dev_ptr(x_dev), C.byref(opt), C.byref(rep)))
+        return _as_dict(rep)
+
+    def solve_irls(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0, max_irls_iterations=0,
+                   irls_cost_difference_threshold=0.0):
+        """IRLSMapSolver::RunIRLSLoop on the device.  Returns (x, report dict)."""
+        x = np.array(_f64(x0).reshape(-1), copy=True)
+        assert x.size == self.num_active
+        opt, rep = self._cg_options(epsg, epsf, epsx, maxits), IrlsReport()
+        self._check(self._lib.srb_solve_irls(self._ctx, _host_ptr(x), C.byref(opt), int(max_irls_iterations),
+                                             float(irls_cost_difference_threshold), C.byref(rep)))
+        return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
 
     def set_path(self, path):
         self._check(self._lib.srb_set_path(self._ctx, int(path)))

@@ -99,3 +99,23 @@ def test_special_sample_rule_covers_brute_force(oracle, s, K):
             truly_total += truly
     assert truly_total > 0                      # the cases do exercise the rule ...
     assert flagged_total <= 4 * truly_total + 40  # ... and the rule stays a thin band, not everything
+
+
+def test_solver_options_mirror_the_reference_defaults_and_scaling():
+    """IrlsMapSolverOptions: defaults of map_solver.h:54-62 / irls_map_solver.h:27-35 and
+    AdjustThresholdsAdaptively (map_solver.cpp:16-26, irls_map_solver.cpp:161-171): thresholds scale
+    by num_parameters * sum(lambda), up only."""
+    from importlib import import_module
+    solver = import_module("super-resolution_b200.solver")
+    o = solver.IrlsMapSolverOptions()
+    assert (o.max_num_solver_iterations, o.max_num_irls_iterations) == (50, 20)
+    assert (o.gradient_norm_threshold, o.cost_decrease_threshold, o.parameter_variation_threshold,
+            o.irls_cost_difference_threshold) == (1e-6, 1e-6, 1e-6, 1e-5)
+    same = o.adjusted(10, 0.01)             # scale 0.1 < 1: unchanged
+    assert same == o and same is not o
+    up = o.adjusted(2352, 0.01)             # cfg1: 28*28*3 parameters, lambda 0.01
+    assert up.gradient_norm_threshold == 1e-6 * (2352 * 0.01)
+    assert up.cost_decrease_threshold == 1e-6 * (2352 * 0.01)
+    assert up.parameter_variation_threshold == 1e-6 * (2352 * 0.01)
+    assert up.irls_cost_difference_threshold == 1e-5 * (2352 * 0.01)
+    assert (up.max_num_solver_iterations, up.max_num_irls_iterations) == (50, 20)
