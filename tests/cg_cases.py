@@ -35,6 +35,37 @@ def pole(x):
     return float(f), g
 
 
+def lying_gradient(x):
+    """A convex bowl whose reported gradient points uphill: the line search spends its
+    evaluation budget without finding a lower point."""
+    return float(np.sum(x * x)), -2.0 * x
+
+
+def kinked(x):
+    """|x|-like valley with a discontinuous slope: line searches end on the interval / evaluation
+    budget rules instead of the Wolfe conditions."""
+    f = np.sum(np.abs(x) + 0.05 * x * x)
+    return float(f), np.sign(x) + 0.1 * x
+
+
+class NanAfter:
+    """Rosenbrock that turns into NaN after a number of evaluations (termination type -8)."""
+
+    def __init__(self, limit):
+        self.limit = limit
+        self.calls = 0
+
+    def reset(self):
+        self.calls = 0
+
+    def __call__(self, x):
+        self.calls += 1
+        f, g = rosenbrock(x)
+        if self.calls > self.limit:
+            return float("nan"), g
+        return f, g
+
+
 def _sr_objective():
     """The MAP objective itself (oracle): 32 x 40 HR, 2x, 3x3 PSF, 4 frames, TV."""
     from oracle import sr_oracle as o
@@ -66,6 +97,9 @@ def cases():
         ("rosenbrock33_maxits", rosenbrock, rng.standard_normal(33), dict(maxits=25)),
         ("pole_trimmed", pole, np.full(12, 3.0) + rng.random(12), dict(epsg=1e-12, maxits=200)),
         ("map_objective_tv", sr, sr_x0, dict(epsg=1e-8, epsf=1e-14, epsx=1e-12, maxits=40)),
+        ("lying_gradient", lying_gradient, rng.standard_normal(9), dict(epsg=1e-12, maxits=100)),
+        ("kinked_valley", kinked, rng.standard_normal(15) * 3, dict(epsg=1e-9, epsx=1e-13, maxits=60)),
+        ("nan_after_12_evaluations", NanAfter(12), rng.standard_normal(6), dict(epsg=1e-12, maxits=100)),
     ]
 
 
@@ -73,6 +107,8 @@ def run(fn, x0, fg, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
     """Runs one solver entry point (ref_mincg or srbcg_host_minimize).  Returns (x, report, f trace)."""
     fn.restype = C.c_int
     fn.argtypes = ARGTYPES
+    if hasattr(fg, "reset"):
+        fg.reset()
     x = np.array(x0, dtype=np.float64)
     rep = np.zeros(6)
     trace = []
