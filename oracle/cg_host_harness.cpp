@@ -12,6 +12,7 @@
 
 extern "C" {
 typedef void (*srbcg_fg_cb)(long long n, const double* x, double* f, double* g, void* user);
+typedef void (*srbcg_reweight_cb)(long long n, const double* x, void* user);
 }
 
 namespace {
@@ -21,6 +22,7 @@ struct HostBackend {
   long long n;
   srbcg_fg_cb cb;
   void* user;
+  srbcg_reweight_cb rw = nullptr;
   long long evals = 0;
 
   long long size() const { return n; }
@@ -70,6 +72,7 @@ struct HostBackend {
     *gg = dot(gn, gn);
     *gy = dot4([gn](long long i) { return gn[i]; }, y);
   }
+  void reweight(Vec x) { rw(n, x, user); }
   void direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg) {
     for (long long i = 0; i < n; ++i) dk[i] = -g[i] + beta * dk[i];
     *dd = sum_sq(d);
@@ -96,6 +99,28 @@ int srbcg_host_minimize(long long n, double* x_inout, double epsg, double epsf, 
   report[3] = rep.f;
   report[4] = rep.restarts;
   report[5] = (double)be.evals;
+  return 0;
+}
+
+// IRLSMapSolver::RunIRLSLoop over host arrays; `rw` installs the new IRLS weights in the objective.
+// report: [IRLS iterations, CG iterations (summed), nfev (summed), last termination type, final f]
+int srbcg_host_irls(long long n, double* x_inout, double epsg, double epsf, double epsx, int maxits,
+                    int max_irls_iterations, double cost_difference_threshold, int has_regularizer,
+                    srbcg_fg_cb cb, srbcg_reweight_cb rw, void* user, double* report) {
+  HostBackend be{n, cb, user};
+  be.rw = rw;
+  std::vector<double> store((size_t)srb::kCgScratchVectors * n);
+  double* scratch[srb::kCgScratchVectors];
+  for (int i = 0; i < srb::kCgScratchVectors; ++i) scratch[i] = store.data() + (size_t)i * n;
+  srb::CgOptions opt;
+  opt.epsg = epsg; opt.epsf = epsf; opt.epsx = epsx; opt.maxits = maxits;
+  const srb::IrlsReport rep = srb::irls_solve(be, x_inout, scratch, opt, max_irls_iterations,
+                                              cost_difference_threshold, has_regularizer != 0);
+  report[0] = rep.irls_iterations;
+  report[1] = rep.solver_iterations;
+  report[2] = rep.nfev;
+  report[3] = rep.last_termination;
+  report[4] = rep.f;
   return 0;
 }
 }

@@ -223,6 +223,15 @@ srb_status build_host_model(srb_ctx* c, const srb_model_desc* d) {
   return SRB_OK;
 }
 
+// w = 1 / max(1e-5, reg(x)) for a device-resident estimate (irls_map_solver.cpp:128-143), stream-ordered
+srb_status reweight_dev(srb_ctx* c, const double* d_x) {
+  k_reg_values<1><<<grid2d(c->g.W, c->g.H, c->Ca()), dim3(32, 8), 0, c->stream>>>(
+      make_reg_params(c, c->Ca()), d_x, c->d_w);
+  c->timing.kernel_launches += 1;
+  SRB_CUDA_CHECK(c, cudaGetLastError());
+  return SRB_OK;
+}
+
 }  // namespace
 
 #include "srb_cg_device.cuh"  // device-resident CG (needs eval_core)
@@ -472,15 +481,6 @@ srb_status srb_set_irls_weights(srb_ctx* c, const double* w) {
   return SRB_OK;
 }
 
-// w = 1 / max(1e-5, reg(x)) for a device-resident estimate (irls_map_solver.cpp:128-143), stream-ordered
-static srb_status reweight_dev(srb_ctx* c, const double* d_x) {
-  k_reg_values<1><<<grid2d(c->g.W, c->g.H, c->Ca()), dim3(32, 8), 0, c->stream>>>(
-      make_reg_params(c, c->Ca()), d_x, c->d_w);
-  c->timing.kernel_launches += 1;
-  SRB_CUDA_CHECK(c, cudaGetLastError());
-  return SRB_OK;
-}
-
 srb_status srb_reweight(srb_ctx* c, const double* x_host, double* w_out) {
   if (!c) return SRB_ERR_INVALID;
   if (!reg_active(c)) return c->fail(SRB_ERR_STATE, "no regularizer configured");
@@ -560,25 +560,16 @@ srb_status srb_solve_irls(srb_ctx* c, double* x_host, const srb_cg_options* opti
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
   srb_status st = reset_weights(c);  // irls_map_solver.cpp:66-74: all weights 1
   if (st != SRB_OK) return st;
-  const CgOptions opt = cg_options_from(options);
+  IrlsReport rep;
+  st = irls_solve_dev(c, c->d_x, cg_options_from(options), max_num_irls_iterations,
+                      irls_cost_difference_threshold, reg_active(c), &rep);
+  if (st != SRB_OK) return st;
   srb_irls_report out{};
-  // irls_map_solver.cpp:45-157
-  double previous_cost = INFINITY;
-  double cost_difference = irls_cost_difference_threshold + 1.0;
-  while (std::fabs(cost_difference) >= irls_cost_difference_threshold) {
-    CgReport rep;
-    if ((st = cg_minimize_dev(c, c->d_x, opt, &rep)) != SRB_OK) return st;
-    out.num_solver_iterations += rep.iterations;
-    out.num_evaluations += rep.nfev;
-    out.last_termination_type = rep.termination;
-    out.final_cost = rep.f;
-    if (!reg_active(c)) break;  // :118-121: nothing to re-weight
-    if ((st = reweight_dev(c, c->d_x)) != SRB_OK) return st;
-    cost_difference = previous_cost - rep.f;
-    previous_cost = rep.f;
-    out.num_irls_iterations += 1;
-    if (max_num_irls_iterations > 0 && out.num_irls_iterations >= max_num_irls_iterations) break;
-  }
+  out.num_irls_iterations = rep.irls_iterations;
+  out.num_solver_iterations = rep.solver_iterations;
+  out.num_evaluations = rep.nfev;
+  out.last_termination_type = rep.last_termination;
+  out.final_cost = rep.f;
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(x_host, c->d_x, bytes, cudaMemcpyDeviceToHost, c->stream));
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   if (report) *report = out;

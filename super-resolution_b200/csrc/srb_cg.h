@@ -34,6 +34,7 @@
 //            with y = g_new - g_old:  dy = <y, dk>, gg = <g_new, g_new>, gy = <g_new, y>
 //   void   direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg);
 //            dk = -g + beta * dk (in place);  dd = sum d_i^2, gg = sum g_i^2 (plain loops in ALGLIB)
+//   void   reweight(Vec x);                                    irls_solve only: new IRLS weights from x
 #pragma once
 #include <cmath>
 
@@ -341,6 +342,40 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, C
   }
   if (xk != x_inout) be.copy(x_inout, xk);  // mincgresults: the last point of the last line search
   return rep;
+}
+
+// IRLSMapSolver::RunIRLSLoop (irls_map_solver.cpp:45-157): conjugate-gradient solves of the
+// re-weighted least-squares problem until the cost of two consecutive solves differs by less than
+// the threshold.  The backend's objective must use the weights that be.reweight(x) installs
+// (w = 1 / max(1e-5, reg(x)), :128-143); the caller resets them to 1 beforehand (:66-74).
+struct IrlsReport {
+  int irls_iterations = 0;
+  int solver_iterations = 0;  // summed over the outer iterations
+  int nfev = 0;
+  int last_termination = 0;
+  double f = 0.0;             // cost the last CG solve returned
+};
+
+template <class B>
+IrlsReport irls_solve(B& be, typename B::Vec x_inout, typename B::Vec* scratch, const CgOptions& opt,
+                      int max_irls_iterations, double cost_difference_threshold, bool has_regularizer) {
+  IrlsReport out;
+  double previous_cost = INFINITY;
+  double cost_difference = cost_difference_threshold + 1.0;
+  while (std::fabs(cost_difference) >= cost_difference_threshold) {
+    const CgReport rep = cg_minimize(be, x_inout, scratch, opt);
+    out.solver_iterations += rep.iterations;
+    out.nfev += rep.nfev;
+    out.last_termination = rep.termination;
+    out.f = rep.f;
+    if (!has_regularizer) break;  // nothing to re-weight: one solve (:118-121)
+    be.reweight(x_inout);
+    cost_difference = previous_cost - rep.f;
+    previous_cost = rep.f;
+    out.irls_iterations += 1;
+    if (max_irls_iterations > 0 && out.irls_iterations >= max_irls_iterations) break;
+  }
+  return out;
 }
 
 }  // namespace srb

@@ -114,8 +114,8 @@ k_cg_map(double* dst, const double* src, double a, const double* __restrict__ di
   }
 }
 
-// eval_core(ctx, x, g, tail, data term, regularization term, accumulate) is srb_api.cu's evaluation
-// core; this header is included there, after its definition.
+// eval_core(ctx, x, g, tail, data term, regularization term, accumulate) and reweight_dev(ctx, x)
+// are srb_api.cu's; this header is included there, after their definitions.
 
 struct DeviceCgBackend {
   using Vec = double*;
@@ -210,41 +210,73 @@ struct DeviceCgBackend {
     fetch();
     *dd = h_out[0]; *gg = h_out[1];
   }
+  void reweight(Vec x) {  // w = 1 / max(1e-5, reg(x)), irls_map_solver.cpp:128-143 (stream-ordered)
+    if (!ok()) return;
+    const srb_status st = reweight_dev(c, x);
+    if (st != SRB_OK) status = st;
+  }
+};
+
+// Scratch vectors, reduction slots and the pinned scalar mirror of one solve.
+struct DeviceCgWorkspace {
+  double* store = nullptr;
+  double* h_out = nullptr;
+  double* scratch[kCgScratchVectors];
+  ~DeviceCgWorkspace() {
+    if (store) cudaFree(store);
+    if (h_out) cudaFreeHost(h_out);
+  }
+  srb_status init(srb_ctx* c, DeviceCgBackend* be) {
+    const long long n = (long long)c->n_active();
+    const size_t doubles = (size_t)kCgScratchVectors * n + 3 * CG_MAX_BLOCKS + 4;
+    if (cudaMalloc((void**)&store, doubles * sizeof(double)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      store = nullptr;
+      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (CG vectors)");
+    }
+    if (cudaMallocHost((void**)&h_out, 4 * sizeof(double)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      h_out = nullptr;
+      return c->fail(SRB_ERR_NOMEM, "cudaMallocHost failed (CG scalars)");
+    }
+    be->c = c;
+    be->n = n;
+    be->d_part = store + (size_t)kCgScratchVectors * n;
+    be->d_out = be->d_part + 3 * CG_MAX_BLOCKS;
+    be->h_out = h_out;
+    const long long want = (n + CG_NT - 1) / CG_NT;
+    be->nblk = (int)std::max(1LL, std::min<long long>(std::min<long long>(want, (long long)c->num_sms * 8), CG_MAX_BLOCKS));
+    for (int i = 0; i < kCgScratchVectors; ++i) scratch[i] = store + (size_t)i * n;
+    return SRB_OK;
+  }
+  srb_status finish(srb_ctx* c, const DeviceCgBackend& be) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (!be.ok()) return be.status;
+    if (e != cudaSuccess) return c->fail(SRB_ERR_CUDA, std::string("CG: ") + cudaGetErrorString(e));
+    return SRB_OK;
+  }
 };
 
 // RunCGSolverAnalyticalDiff on a device-resident estimate (active channel range, n = Ca * H * W).
 inline srb_status cg_minimize_dev(srb_ctx* c, double* d_x, const CgOptions& opt, CgReport* rep) {
-  const long long n = (long long)c->n_active();
-  double* store = nullptr;
-  double* h_out = nullptr;
-  const size_t doubles = (size_t)kCgScratchVectors * n + 3 * CG_MAX_BLOCKS + 4;
-  if (cudaMalloc((void**)&store, doubles * sizeof(double)) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (CG vectors)");
-  }
-  if (cudaMallocHost((void**)&h_out, 4 * sizeof(double)) != cudaSuccess) {
-    (void)cudaGetLastError();
-    cudaFree(store);
-    return c->fail(SRB_ERR_NOMEM, "cudaMallocHost failed (CG scalars)");
-  }
   DeviceCgBackend be;
-  be.c = c;
-  be.n = n;
-  be.d_part = store + (size_t)kCgScratchVectors * n;
-  be.d_out = be.d_part + 3 * CG_MAX_BLOCKS;
-  be.h_out = h_out;
-  const long long want = (n + CG_NT - 1) / CG_NT;
-  be.nblk = (int)std::max(1LL, std::min<long long>(std::min<long long>(want, (long long)c->num_sms * 8), CG_MAX_BLOCKS));
-  double* scratch[kCgScratchVectors];
-  for (int i = 0; i < kCgScratchVectors; ++i) scratch[i] = store + (size_t)i * n;
-  *rep = cg_minimize(be, d_x, scratch, opt);
-  cudaError_t e = cudaStreamSynchronize(c->stream);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  cudaFree(store);
-  cudaFreeHost(h_out);
-  if (!be.ok()) return be.status;
-  if (e != cudaSuccess) return c->fail(SRB_ERR_CUDA, std::string("CG: ") + cudaGetErrorString(e));
-  return SRB_OK;
+  DeviceCgWorkspace ws;
+  srb_status st = ws.init(c, &be);
+  if (st != SRB_OK) return st;
+  *rep = cg_minimize(be, d_x, ws.scratch, opt);
+  return ws.finish(c, be);
+}
+
+// IRLSMapSolver::RunIRLSLoop on a device-resident estimate; the weights must have been reset to 1.
+inline srb_status irls_solve_dev(srb_ctx* c, double* d_x, const CgOptions& opt, int max_irls_iterations,
+                                 double cost_difference_threshold, bool has_regularizer, IrlsReport* rep) {
+  DeviceCgBackend be;
+  DeviceCgWorkspace ws;
+  srb_status st = ws.init(c, &be);
+  if (st != SRB_OK) return st;
+  *rep = irls_solve(be, d_x, ws.scratch, opt, max_irls_iterations, cost_difference_threshold, has_regularizer);
+  return ws.finish(c, be);
 }
 
 }  // namespace srb

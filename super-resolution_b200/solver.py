@@ -33,28 +33,41 @@ class IrlsMapSolverOptions:
                        irls_cost_difference_threshold=self.irls_cost_difference_threshold * scale)
 
 
-def solve(engine, initial_estimate, options=None, regularization_parameter_sum=0.0):
-    """IRLSMapSolver::Solve on `engine` (model, observations and regularizer already set).
-    initial_estimate: [C][H][W].  Returns (estimate [C][H][W], list of per-round report dicts)."""
+def solve_rounds(round_solver, initial_estimate, options=None, regularization_parameter_sum=0.0):
+    """The round structure of IRLSMapSolver::Solve (irls_map_solver.cpp:192-265) around
+    round_solver(c0, c1, x0_slice, scaled_options) -> (x_slice, report): one round over all channels,
+    or one per channel with split_channels; thresholds scaled for the round's parameter count."""
     opt = options if options is not None else IrlsMapSolverOptions()
     x0 = np.ascontiguousarray(initial_estimate, dtype=np.float64)
     Cn, H, W = x0.shape
-    assert (Cn, H, W) == (engine.C, engine.H, engine.W), x0.shape
-    per_split = 1 if opt.split_channels else Cn               # irls_map_solver.cpp:200-206
+    per_split = 1 if opt.split_channels else Cn               # :200-206
     rounds = Cn // per_split
     scaled = opt.adjusted(per_split * H * W, regularization_parameter_sum)   # :213-216
     out = np.empty_like(x0)
     reports = []
     for i in range(rounds):
         c0, c1 = i * per_split, (i + 1) * per_split
-        engine.set_channel_range(c0, c1)
-        x, rep = engine.solve_irls(x0[c0:c1], epsg=scaled.gradient_norm_threshold,
-                                   epsf=scaled.cost_decrease_threshold,
-                                   epsx=scaled.parameter_variation_threshold,
-                                   maxits=scaled.max_num_solver_iterations,
-                                   max_irls_iterations=scaled.max_num_irls_iterations,
-                                   irls_cost_difference_threshold=scaled.irls_cost_difference_threshold)
+        x, rep = round_solver(c0, c1, x0[c0:c1], scaled)
         out[c0:c1] = x
         reports.append(rep)
-    engine.set_channel_range(0, Cn)
     return out, reports
+
+
+def solve(engine, initial_estimate, options=None, regularization_parameter_sum=0.0):
+    """IRLSMapSolver::Solve on `engine` (model, observations and regularizer already set).
+    initial_estimate: [C][H][W].  Returns (estimate [C][H][W], list of per-round report dicts)."""
+    x0 = np.ascontiguousarray(initial_estimate, dtype=np.float64)
+    assert x0.shape == (engine.C, engine.H, engine.W), x0.shape
+
+    def device_round(c0, c1, x0_slice, scaled):
+        engine.set_channel_range(c0, c1)
+        return engine.solve_irls(x0_slice, epsg=scaled.gradient_norm_threshold,
+                                 epsf=scaled.cost_decrease_threshold,
+                                 epsx=scaled.parameter_variation_threshold,
+                                 maxits=scaled.max_num_solver_iterations,
+                                 max_irls_iterations=scaled.max_num_irls_iterations,
+                                 irls_cost_difference_threshold=scaled.irls_cost_difference_threshold)
+    try:
+        return solve_rounds(device_round, x0, options, regularization_parameter_sum)
+    finally:
+        engine.set_channel_range(0, engine.C)

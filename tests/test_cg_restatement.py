@@ -63,3 +63,68 @@ def test_restatement_reproduces_alglib_live(host_cg, case):
     np.testing.assert_array_equal(rh[:4], rr[:4])
     np.testing.assert_array_equal(th, tr)
     np.testing.assert_array_equal(xh, xr)
+
+
+# ---- the IRLS loop and the round structure of IRLSMapSolver::Solve ------------------------------
+RW = C.CFUNCTYPE(None, C.c_longlong, C.POINTER(C.c_double), C.c_void_p)
+
+
+def _host_irls_round_solver(host_cg, oracle, model, obs_hr, reg_kind, lam):
+    """round_solver for solver.solve_rounds: srb_cg.h's irls_solve over host arrays, the objective
+    and the re-weighting being the oracle's (data term + IRLS-weighted regularizer)."""
+    fn = host_cg.srbcg_host_irls
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_longlong, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                   C.c_double, C.c_int, cg_cases.FG, RW, C.c_void_p, C.POINTER(C.c_double)]
+
+    def round_solver(c0, c1, x0_slice, opt):
+        Cn, H, W = x0_slice.shape
+        state = {"w": np.ones((Cn, H, W))}                      # irls_map_solver.cpp:66-74
+        obs = np.ascontiguousarray(obs_hr[:, c0:c1])
+
+        def fg(n, xp, fp, gp, user):
+            x = np.ctypeslib.as_array(xp, (n,)).reshape(Cn, H, W)
+            f, g = oracle.evaluate(model, x, obs, reg_kind=reg_kind, lam=lam, weights=state["w"])
+            fp[0] = f
+            np.ctypeslib.as_array(gp, (n,))[:] = g.ravel()
+
+        def rw(n, xp, user):
+            x = np.ctypeslib.as_array(xp, (n,)).reshape(Cn, H, W)
+            state["w"] = oracle.reweight(reg_kind, x)
+
+        x = np.array(x0_slice, dtype=np.float64).reshape(-1)
+        rep = np.zeros(5)
+        fn(x.size, x.ctypes.data_as(C.POINTER(C.c_double)), opt.gradient_norm_threshold,
+           opt.cost_decrease_threshold, opt.parameter_variation_threshold, opt.max_num_solver_iterations,
+           opt.max_num_irls_iterations, opt.irls_cost_difference_threshold, 1 if lam > 0 else 0,
+           cg_cases.FG(fg), RW(rw), None, rep.ctypes.data_as(C.POINTER(C.c_double)))
+        return x.reshape(Cn, H, W), rep
+    return round_solver
+
+
+@pytest.mark.parametrize("split_channels", [False, True])
+def test_irls_solve_mirror_reproduces_the_reference_solver(host_cg, oracle, ref, split_channels):
+    """solver.solve_rounds + srb_cg.h's irls_solve + cg_minimize (host backend, oracle objective)
+    against the reference's IRLSMapSolver::Solve (oracle/_ref: irls_map_solver.cpp, ALGLIB, the
+    reference's TV regularizer; data term = oracle): BASELINE configuration 1's shape and defaults
+    (28x28x3, 2x, 3x3 PSF, 4 frames, TV lambda 0.01, 20 IRLS x 50 CG), bit for bit."""
+    from importlib import import_module
+    solver = import_module("super-resolution_b200.solver")
+    wl = import_module("super-resolution_b200.workloads")
+    s, lam = 2, 0.01
+    psf = oracle.gaussian_psf(3, 1.0)
+    shifts = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=np.float64)
+    m = oracle.Model(s, psf, shifts)
+    truth = wl.ground_truth(28, 28, 3, 11)
+    lr = np.stack([[oracle.forward(m, k, truth[c]) for c in range(3)] for k in range(4)])
+    x0 = wl.bilinear_upsample(lr[0], s)
+    opt_ref = ref.default_options()
+    opt_ref.split_channels = 1 if split_channels else 0
+    expect, _ = ref.solve(m, lr, x0, reg_kind=oracle.REG_TV, lam=lam, options=opt_ref)
+    mine = solver.IrlsMapSolverOptions(split_channels=split_channels)
+    obs_hr = oracle.upsample_observations(m, lr)
+    got, reports = solver.solve_rounds(_host_irls_round_solver(host_cg, oracle, m, obs_hr, oracle.REG_TV, lam),
+                                       x0, mine, regularization_parameter_sum=lam)
+    assert len(reports) == (3 if split_channels else 1)
+    assert all(r[0] >= 1 for r in reports)
+    np.testing.assert_array_equal(got, expect)
