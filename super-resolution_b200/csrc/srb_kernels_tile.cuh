@@ -767,7 +767,9 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 //     barrier) | Z = B - A in place in B, cost | adjoint horizontal B -> A | adjoint vertical -> g
 // Shared memory and registers are those of k_tile (4 CTAs / SM); tiles that touch the border band run
 // tile_body unchanged.
-template <int KH>
+//   HOLES (opt-in, SRB_ZLAYOUT=2): sub-pixel phases without a frame (a frame shard of a multi-GPU run
+//   holds N / G of the s^2 phases) are NaN in yz and contribute Z = 0.
+template <int KH, bool HOLES>
 __global__ void __launch_bounds__(256, KH <= 3 ? 4 : 3)
 k_tile_z(const TileParams P, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
          const __grid_constant__ CUtensorMap map_y) {
@@ -889,16 +891,28 @@ k_tile_z(const TileParams P, const __grid_constant__ CUtensorMap map_x, const __
     for (int it = 0; it < (YH + ESEG - 1) / ESEG; ++it) {
       const int r = rq + ESEG * it;
       if (ESEG * it + ESEG - 1 < YH || r < YH) {
-        const double res = bp[it * ESEG * D::TP] - yp[it * ESEG * YW];
-        bp[it * ESEG * D::TP] = res;
-        if (r >= KH && r < KH + TH) cost_data = fma(res, res, cost_data);
+        if (!HOLES) {
+          const double res = bp[it * ESEG * D::TP] - yp[it * ESEG * YW];
+          bp[it * ESEG * D::TP] = res;
+          if (r >= KH && r < KH + TH) cost_data = fma(res, res, cost_data);
+        } else {
+          const double yv = yp[it * ESEG * YW];
+          const double res = (yv == yv) ? bp[it * ESEG * D::TP] - yv : 0.0;
+          bp[it * ESEG * D::TP] = res;
+          if (r >= KH && r < KH + TH) cost_data = fma(res, res, cost_data);
+        }
       }
     }
     // left / right halo columns of the Z region
     for (int id = tid; id < 2 * KH * YH; id += NT) {
       const int r = id / (2 * KH), hc = id - r * (2 * KH);
       const int cz = hc < KH ? hc : hc + FT_W;
-      bufB[r * D::TP + cz] -= bufA[r * YW + cz - KH + HYC];
+      if (!HOLES) {
+        bufB[r * D::TP + cz] -= bufA[r * YW + cz - KH + HYC];
+      } else {
+        const double yv = bufA[r * YW + cz - KH + HYC];
+        bufB[r * D::TP + cz] = (yv == yv) ? bufB[r * D::TP + cz] - yv : 0.0;
+      }
     }
   }
   __syncthreads();
@@ -950,7 +964,8 @@ k_tile_z(const TileParams P, const __grid_constant__ CUtensorMap map_x, const __
 }
 
 // yz(c, p) = the observation of the one (frame, LR pixel) sample landing on HR pixel p; 0 where that
-// sample lies outside the LR image (such pixels belong to tiles that never take the Z path).
+// sample lies outside the LR image (such pixels belong to tiles that never take the Z path), NaN
+// where the pixel's sub-pixel phase has no frame at all.
 // grid: (ceil(W/256), H, Ct)
 __global__ void __launch_bounds__(256)
 k_build_yz(int H, int W, int h, int w, int s, const TEntry* __restrict__ entries,
@@ -958,11 +973,16 @@ k_build_yz(int H, int W, int h, int w, int s, const TEntry* __restrict__ entries
   const int pc = blockIdx.x * 256 + threadIdx.x, pr = blockIdx.y, c = blockIdx.z;
   if (pc >= W) return;
   const int mr = pr / s, mc = pc / s;
-  const TEntry e = entries[phase_begin[(pr - mr * s) * s + (pc - mc * s)]];
-  const int qr = mr + (int)(short)(e.qoff & 0xffff), qc = mc + (e.qoff >> 16);
+  const int ph = (pr - mr * s) * s + (pc - mc * s);
   double v = 0.0;
-  if (qr >= 0 && qr < h && qc >= 0 && qc < w)
-    v = y[(size_t)c * ((size_t)h * w) + e.yoff + (long long)mr * w + mc];
+  if (phase_begin[ph + 1] == phase_begin[ph]) {
+    v = __longlong_as_double(0x7ff8000000000000LL);  // no frame on this phase (k_tile_z<.., HOLES>)
+  } else {
+    const TEntry e = entries[phase_begin[ph]];
+    const int qr = mr + (int)(short)(e.qoff & 0xffff), qc = mc + (e.qoff >> 16);
+    if (qr >= 0 && qr < h && qc >= 0 && qc < w)
+      v = y[(size_t)c * ((size_t)h * w) + e.yoff + (long long)mr * w + mc];
+  }
   yz[((size_t)c * H + pr) * W + pc] = v;
 }
 

@@ -55,6 +55,7 @@ struct TileState {
   long long* d_fast_y[2] = {nullptr, nullptr};
   double* d_yz = nullptr;  // observations on the HR grid [Ct][H][W] (k_tile_z; SRB_ZLAYOUT=1), else NULL
   bool yz_valid = false;   // d_yz matches the observations currently in d_y
+  bool yz_holes = false;   // some sub-pixel phases have no frame (NaN in d_yz; k_tile_z<.., true>)
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -319,13 +320,21 @@ inline srb_status fused_setup(srb_ctx* c) {
   if (const char* e = getenv("SRB_TILE_H")) st->tile_h = atoi(e) == 64 ? 64 : 32;
   // Z layout (k_tile_z): integer shifts, one frame per sub-pixel phase, PSF of 3x3 .. 9x9, TMA.
   // SRB_ZLAYOUT=0 keeps k_tile everywhere (A/B).
+  // SRB_ZLAYOUT=2 (opt-in, not yet run on a GPU) also takes models where some phases have no frame at
+  // all -- the frame shards of a multi-GPU run.
   {
     const char* e = getenv("SRB_ZLAYOUT");
-    const bool wanted = e == nullptr || atoi(e) != 0;
-    if (wanted && !plan.frac && plan.fast_E == 1 && plan.KH >= 1 && plan.KH <= 4 && st->tma_ok &&
-        st->tile_h == 32 && !plan.fast[0].empty()) {
+    const int mode = e == nullptr ? 1 : atoi(e);
+    bool one_per_phase = plan.fast_E == 1 && !plan.fast[0].empty();
+    bool at_most_one = !plan.entries.empty();
+    for (size_t ph = 0; ph + 1 < plan.phase_begin.size(); ++ph)
+      at_most_one = at_most_one && plan.phase_begin[ph + 1] - plan.phase_begin[ph] <= 1;
+    const bool holes = mode >= 2 && !one_per_phase && at_most_one;
+    if (mode != 0 && !plan.frac && (one_per_phase || holes) && plan.KH >= 1 && plan.KH <= 4 && st->tma_ok &&
+        st->tile_h == 32) {
       if (cudaMalloc((void**)&st->d_yz, (size_t)G.Ct * G.H * G.W * sizeof(double)) != cudaSuccess)
         return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in Z layout)");
+      st->yz_holes = holes;
     }
   }
   st->supported = true;
@@ -393,7 +402,7 @@ inline srb_status tile_launch(srb_ctx* c, TileParams& P, int unit_end) {
 
 // k_tile_z launch (Z layout); returns SRB_ERR_STATE without launching when a tensor map cannot be made
 // (the caller then launches k_tile).
-template <int KH>
+template <int KH, bool HOLES>
 inline srb_status tile_launch_z(srb_ctx* c, TileParams& P, int unit_end) {
   using D = TileDims<KH, false, 32>;
   constexpr int HYC = (KH + 1) & ~1;
@@ -411,11 +420,11 @@ inline srb_status tile_launch_z(srb_ctx* c, TileParams& P, int unit_end) {
   const size_t smem = D::smem_bytes(P.num_entries);
   static size_t attr_set[64] = {};
   if (c->device >= 64 || attr_set[c->device] < smem) {
-    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile_z<KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile_z<KH, HOLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = smem;
   }
   if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
-  k_tile_z<KH><<<grid, D::NT, smem, c->stream>>>(P, mx, mw, my);
+  k_tile_z<KH, HOLES><<<grid, D::NT, smem, c->stream>>>(P, mx, mw, my);
   if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
   return SRB_OK;
 }
@@ -498,11 +507,15 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   if (P.fast_E != fe) P.fast = nullptr;  // a kernel only ever sees the table it is specialised for
   if (P.yz != nullptr && TH == 32 && fe == 1 && !st->frac) {  // Z layout (opt-in)
     srb_status zr = SRB_ERR_STATE;
-    switch (st->KH) {
-      case 1: zr = tile_launch_z<1>(c, P, unit_end); break;
-      case 2: zr = tile_launch_z<2>(c, P, unit_end); break;
-      case 3: zr = tile_launch_z<3>(c, P, unit_end); break;
-      case 4: zr = tile_launch_z<4>(c, P, unit_end); break;
+    switch (st->KH * 2 + (st->yz_holes ? 1 : 0)) {
+      case 2: zr = tile_launch_z<1, false>(c, P, unit_end); break;
+      case 3: zr = tile_launch_z<1, true>(c, P, unit_end); break;
+      case 4: zr = tile_launch_z<2, false>(c, P, unit_end); break;
+      case 5: zr = tile_launch_z<2, true>(c, P, unit_end); break;
+      case 6: zr = tile_launch_z<3, false>(c, P, unit_end); break;
+      case 7: zr = tile_launch_z<3, true>(c, P, unit_end); break;
+      case 8: zr = tile_launch_z<4, false>(c, P, unit_end); break;
+      case 9: zr = tile_launch_z<4, true>(c, P, unit_end); break;
       default: break;
     }
     if (zr == SRB_OK) {

@@ -114,3 +114,33 @@ def test_zlayout_declines_models_it_does_not_cover(srb):
     sh = np.array([[0.0, 0.0], [1.0, 0.0], [0.5, 1.0], [1.0, 1.0]])
     with _engine(srb, True, lr, 2, psf, sh) as e:                            # a fractional shift
         assert not e.zlayout_active
+
+
+@pytest.mark.skipif(os.environ.get("SRB_RUN_PENDING") != "1",
+                    reason="k_tile_z<.., HOLES> (SRB_ZLAYOUT=2) not yet run on a GPU (set SRB_RUN_PENDING=1)")
+@pytest.mark.parametrize("frames", [[0, 1, 2, 3, 4, 5, 6, 7], [8, 9, 10, 11], [3, 12]])
+def test_zlayout_with_empty_phases_matches_oracle(srb, oracle, frames):
+    """A frame shard of cfg3's model (some sub-pixel phases carry no frame): SRB_ZLAYOUT=2 keeps the Z
+    layout with NaN holes; cost and gradient of the shard against the oracle."""
+    K, s, sigma, C, h, w = 7, 4, 1.5, 2, 48, 80
+    psf, shifts, lr, x = _model(K, s, sigma, C, h, w, seed=21)
+    shifts, lr = shifts[frames], np.ascontiguousarray(lr[frames])
+    m = oracle.Model(s, psf, shifts)
+    obs_hr = oracle.upsample_observations(m, lr)
+    cost_ref, g_ref = oracle.evaluate(m, x, obs_hr, reg_kind=oracle.REG_TV, lam=0.01)
+    old = os.environ.get("SRB_ZLAYOUT")
+    os.environ["SRB_ZLAYOUT"] = "2"
+    try:
+        e = srb.Engine(lr.shape, s, psf, shifts)
+    finally:
+        if old is None:
+            del os.environ["SRB_ZLAYOUT"]
+        else:
+            os.environ["SRB_ZLAYOUT"] = old
+    with e:
+        e.set_observations(lr)
+        assert e.zlayout_active
+        e.set_regularizer(srb.REG_TV, 0.01)
+        c, g = e.eval(x)
+    assert abs(c - cost_ref) <= REL_L2 * abs(cost_ref)
+    assert rel_l2(g, g_ref) <= REL_L2

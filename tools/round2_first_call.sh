@@ -10,6 +10,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 (SRB_RUN_PENDING=1 timeout 300 python -m pytest tests/test_gpu_cg.py -q -x -s 2>&1 | tail -40) > gpurun_out/r2_cg_tests.log
+(SRB_RUN_PENDING=1 timeout 300 python -m pytest tests/test_gpu_zlayout.py -q -s 2>&1 | tail -20) > gpurun_out/r2_zholes_tests.log
 (timeout 900 python -m pytest tests -q -x -m gpu --durations=15 2>&1 | tail -40) > gpurun_out/r2_gpu_tests.log
 (timeout 120 python tools/ab_zlayout.py 60 2>&1) > gpurun_out/r2_ab_zlayout.log
 (timeout 300 python bench.py 2>gpurun_out/r2_bench.err) > gpurun_out/r2_bench.json
@@ -17,6 +18,6 @@ export PYTHONUNBUFFERED=1
     --log-file gpurun_out/r2_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline) > gpurun_out/r2_ncu_launch.log 2>&1
 (timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_z -s 3 -c 1 \
     -o gpurun_out/r2_k_tile_z python bench.py --steps 2 --warmup 3 --no-cpu-baseline) > gpurun_out/r2_ncu_full.log 2>&1
-tail -5 gpurun_out/r2_cg_tests.log gpurun_out/r2_gpu_tests.log
+tail -5 gpurun_out/r2_cg_tests.log gpurun_out/r2_zholes_tests.log gpurun_out/r2_gpu_tests.log
 cat gpurun_out/r2_ab_zlayout.log | head -30
 cat gpurun_out/r2_bench.json
