@@ -27,10 +27,6 @@ struct HostBackend {
 
   long long size() const { return n; }
   void eval(Vec x, Vec g, double* f) { cb(n, x, f, g, user); ++evals; }
-  void eval_with_slope(Vec x, Vec g, Vec d, double* f, double* dg) {
-    eval(x, g, f);
-    *dg = dot(g, d);
-  }
   void copy(Vec d, Vec s) { std::memcpy(d, s, (size_t)n * sizeof(double)); }
   void neg_copy(Vec d, Vec s) { for (long long i = 0; i < n; ++i) d[i] = -s[i]; }
   void scale_to(Vec d, Vec s, double a) { for (long long i = 0; i < n; ++i) d[i] = s[i] * a; }
@@ -73,10 +69,32 @@ struct HostBackend {
     *gy = dot4([gn](long long i) { return gn[i]; }, y);
   }
   void reweight(Vec x) { rw(n, x, user); }
-  void direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg) {
+  void direction(Vec dk, Vec g, double beta, double* gg, double* mx) {
     for (long long i = 0; i < n; ++i) dk[i] = -g[i] + beta * dk[i];
-    *dd = sum_sq(d);
     *gg = sum_sq(g);
+    *mx = max_abs(dk);
+  }
+  // linminnormalized (alglibinternal.cpp:12165-12195) + the slope mcsrch computes first + the
+  // squared length mincgiteration computes after the line search
+  void normalize_to(Vec d, Vec dk, double mx, Vec g0, double* stp, double* slope, double* dd) {
+    if (mx == 0.0) {
+      copy(d, dk);
+    } else {
+      double s = 1 / mx;
+      scale_to(d, dk, s);
+      *stp = *stp / s;
+      s = 1 / std::sqrt(dot(d, d));
+      scale(d, s);
+      *stp = *stp / s;
+    }
+    *slope = dot(g0, d);
+    *dd = sum_sq(d);
+  }
+  void trial(Vec x, Vec x0, double stp, Vec d, Vec g, double* f, double* dg, double* moved) {
+    step_to(x, x0, stp, d);
+    eval(x, g, f);
+    *dg = dot(g, d);
+    *moved = sum_sq_diff(x0, x);
   }
 };
 

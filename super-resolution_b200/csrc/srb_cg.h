@@ -15,25 +15,27 @@
 // min(DY, HS) hybrid clipped at 0), no step bound, analytic gradient, first trial step 1.
 //
 // Backend concept (all vectors have the problem's length n; "sum" orders are ALGLIB's on the host
-// backend of the tests, free on the device):
+// backend of the tests, free on the device).  The operations are the fused groups the CUDA backend
+// runs as one or two streaming kernels each:
 //   using Vec = ...;                       cheap handle
 //   long long size();
 //   void   eval(Vec x, Vec g, double* f);                      objective + gradient at x
-//   void   eval_with_slope(Vec x, Vec g, Vec d, double* f, double* dg);   ... and dg = <g, d>
-//   void   copy(Vec dst, Vec src);
 //   void   neg_copy(Vec dst, Vec src);                         dst = -src
-//   void   scale_to(Vec dst, Vec src, double a);               dst = src * a
-//   void   scale(Vec v, double a);                             v *= a
-//   void   step_to(Vec dst, Vec base, double a, Vec dir);      dst = base + a * dir
+//   void   copy(Vec dst, Vec src);
 //   void   zero(Vec v);
 //   double dot(Vec a, Vec b);                                  ae_v_dotproduct (ap.cpp:4667-4692)
-//   double sum_sq_diff(Vec a, Vec b);                          sum (a_i - b_i)^2
-//   double max_abs(Vec a);
 //   double sum_sq(Vec a);                                      sum a_i^2 (plain loop in ALGLIB)
+//   double max_abs(Vec a);
+//   void   normalize_to(Vec d, Vec dk, double mx, Vec g0, double* stp, double* slope, double* dd);
+//            linminnormalized with mx = max |dk_i|: d = (dk * s1) * s2, s1 = 1 / mx,
+//            s2 = 1 / sqrt(<dk * s1, dk * s1>), *stp = *stp / s1 / s2  (d = dk, *stp unchanged when
+//            mx == 0);  *slope = <g0, d>;  *dd = sum d_i^2
+//   void   trial(Vec x, Vec x0, double stp, Vec d, Vec g, double* f, double* dg, double* moved);
+//            x = x0 + stp * d;  f, g = objective at x;  dg = <g, d>;  moved = sum (x0_i - x_i)^2
 //   void   beta_terms(Vec g_new, Vec g_old, Vec dk, double* dy, double* gg, double* gy);
 //            with y = g_new - g_old:  dy = <y, dk>, gg = <g_new, g_new>, gy = <g_new, y>
-//   void   direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg);
-//            dk = -g + beta * dk (in place);  dd = sum d_i^2, gg = sum g_i^2 (plain loops in ALGLIB)
+//   void   direction(Vec dk, Vec g, double beta, double* gg, double* mx);
+//            dk = -g + beta * dk (in place);  gg = sum g_i^2;  mx = max |dk_i| of the new direction
 //   void   reweight(Vec x);                                    irls_solve only: new IRLS weights from x
 #pragma once
 #include <cmath>
@@ -168,12 +170,12 @@ inline int trial_step(Bracket& b, double& stp, double fp, double dp, double stmi
 }
 
 // Line search along the unit direction d from x0 (More-Thuente, ALGLIB's mcsrch).  On entry f and
-// g0 are the objective and gradient at x0 and stp the first trial step; on exit x, f, g belong to
-// the last point evaluated and stp is its step (g0 is left alone).  info: 1 Wolfe conditions hold,
+// dginit = <g(x0), d> are the objective and its slope at x0 and stp the first trial step; on exit
+// x, f, g belong to the last point evaluated and stp is its step.  info: 1 Wolfe conditions hold,
 // 2 interval below xtol, 3 evaluation budget, 4 step at the lower bound, 5 step at the upper bound,
 // 6 rounding / no progress, 0 d is not a descent direction (nothing evaluated, nfev left as it was).
 template <class B>
-void line_search(B& be, typename B::Vec x0, typename B::Vec g0, typename B::Vec x, typename B::Vec g, double& f,
+void line_search(B& be, typename B::Vec x0, double dginit, typename B::Vec x, typename B::Vec g, double& f,
                  typename B::Vec d, double& stp, double stpmax, double trim_threshold, int& info, int& nfev) {
   if (stpmax == 0.0) stpmax = kStpMaxDefault;
   if (stp < kStpMin) stp = kStpMin;
@@ -185,7 +187,6 @@ void line_search(B& be, typename B::Vec x0, typename B::Vec g0, typename B::Vec 
     return;
   }
   if (be.size() <= 0 || stp <= 0.0 || stpmax < kStpMin) return;
-  const double dginit = be.dot(g0, d);
   if (dginit >= 0.0) return;
   Bracket br;
   br.bracketed = false;
@@ -213,9 +214,8 @@ void line_search(B& be, typename B::Vec x0, typename B::Vec g0, typename B::Vec 
     if ((br.bracketed && (stp <= stmin || stp >= stmax)) || nfev >= kMaxFev - 1 || infoc == 0 ||
         (br.bracketed && stmax - stmin <= kXtol * stmax))
       stp = br.stx;
-    be.step_to(x, x0, stp, d);
-    double dg = 0.0;
-    be.eval_with_slope(x, g, d, &f, &dg);
+    double dg = 0.0, moved = 0.0;
+    be.trial(x, x0, stp, d, g, &f, &dg, &moved);
     if (f >= trim_threshold) {  // trimfunction: bounded from above near singularities
       f = trim_threshold;
       be.zero(g);
@@ -231,10 +231,7 @@ void line_search(B& be, typename B::Vec x0, typename B::Vec g0, typename B::Vec 
     if (br.bracketed && stmax - stmin <= kXtol * stmax) info = 2;
     if (f < finit && f <= ftest1 && std::fabs(dg) <= -kGtol * dginit) info = 1;
     if (info != 0) {
-      if (info == 1 || info == 5) {
-        const double moved = be.sum_sq_diff(x0, x);
-        if (f >= finit || moved == 0.0) info = 6;
-      }
+      if ((info == 1 || info == 5) && (f >= finit || moved == 0.0)) info = 6;
       return;
     }
     if (stage1 && f <= ftest1 && dg >= min2(kFtol, kGtol) * dginit) stage1 = false;
@@ -289,25 +286,14 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, C
   double last_good_step = 1.0;
   int restart_timer = kRestartCountdown;
   int nfev = 0;  // of the last line search that evaluated anything (mincgstate.nfev)
+  double mx = be.max_abs(dk);
   for (;;) {
     // unit direction; the first trial step is the length of the previous accepted step
-    double stp = 1.0;
-    {
-      const double mx = be.max_abs(dk);
-      if (mx == 0.0) {
-        be.copy(d, dk);
-      } else {
-        double s = 1 / mx;
-        be.scale_to(d, dk, s);
-        stp = stp / s;
-        s = 1 / std::sqrt(be.dot(d, d));
-        be.scale(d, s);
-        stp = stp / s;
-      }
-    }
+    double stp = 1.0, dginit = 0.0, dd = 0.0;
+    be.normalize_to(d, dk, mx, gk, &stp, &dginit, &dd);
     if (last_good_step != 0.0) stp = last_good_step;
     int info = 0;
-    line_search(be, xk, gk, xt, gt, f, d, stp, 0.0, trim_threshold, info, nfev);
+    line_search(be, xk, dginit, xt, gt, f, d, stp, 0.0, trim_threshold, info, nfev);
     if (info == 0) {  // nothing was evaluated: the "new" point is the current one
       be.copy(xt, xk);
       be.copy(gt, gk);
@@ -323,8 +309,8 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, C
     if (rep.iterations > 0 && rep.iterations % (3 + n) == 0) beta = 0.0;
     if (info == 1 || info == 5) restart_timer = kRestartCountdown;
     else restart_timer -= 1;
-    double dd, gg;
-    be.direction(dk, gt, beta, d, &dd, &gg);
+    double gg;
+    be.direction(dk, gt, beta, &gg, &mx);
     const double step_len = stp * std::sqrt(dd);
     if (info == 1) last_good_step = step_len;
     rep.f = f;

@@ -1,7 +1,7 @@
 // srb_cg_device.cuh -- CUDA vector backend of the CG restatement (srb_cg.h): the solver vectors of
 // ALGLIB's mincg (x, g, d, ...; alglib_objective.cpp:47-75 hands ALGLIB host arrays) live in HBM,
-// the objective is eval_core() on device pointers, and per line-search step only two scalars
-// (f and <g, d>) reach the host, in one 32-byte copy.  All kernels are HBM-bound streaming passes
+// the objective is eval_core() on device pointers, and per line-search step only three scalars
+// (f, <g, d> and |x - x0|^2) reach the host, in one 32-byte copy.  All kernels are HBM-bound streaming passes
 // (grid = 8 CTAs per SM, grid-stride); reductions are two-stage with a fixed order (one slot per
 // CTA, then one CTA sums the slots), hence deterministic run to run.
 #pragma once
@@ -56,40 +56,88 @@ k_cg_reduce(const double* __restrict__ a, const double* __restrict__ b, const do
   cg_block_store3(s0, s1, s2, part, gridDim.x);
 }
 
-// dk = -g + beta * dk (rounded like ALGLIB's two statements: product, then sum); sum d^2, sum g^2
-__global__ void __launch_bounds__(CG_NT)
-k_cg_direction(double* __restrict__ dk, const double* __restrict__ g, double beta, const double* __restrict__ d,
-               long long n, double* __restrict__ part) {
-  double s0 = 0.0, s1 = 0.0;
-  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
-    const double gi = g[i], di = d[i];
-    dk[i] = __dadd_rn(-gi, __dmul_rn(beta, dk[i]));
-    s0 = fma(di, di, s0);
-    s1 = fma(gi, gi, s1);
+// Block maximum of m -> slot[blockIdx.x] (fmax drops NaN: a NaN vector is caught by the isfinite
+// test on |g| in cg_minimize).
+__device__ __forceinline__ void cg_block_store_max(double m, double* slot) {
+  __shared__ double smx[CG_NT / 32];
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) smx[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < CG_NT / 32; ++w) m = fmax(m, smx[w]);
+    slot[blockIdx.x] = m;
   }
-  cg_block_store3(s0, s1, 0.0, part, gridDim.x);
+}
+
+// dk = -g + beta * dk (rounded like ALGLIB's two statements: product, then sum); sum g^2; max |dk|
+__global__ void __launch_bounds__(CG_NT)
+k_cg_direction(double* dk, const double* __restrict__ g, double beta, long long n, double* __restrict__ part) {
+  double s0 = 0.0, m = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    const double gi = g[i];
+    const double v = __dadd_rn(-gi, __dmul_rn(beta, dk[i]));
+    dk[i] = v;
+    s0 = fma(gi, gi, s0);
+    m = fmax(m, fabs(v));
+  }
+  cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
+  cg_block_store_max(m, part + gridDim.x);  // slot 1 <- max (overwrites the zero sum written above)
 }
 
 __global__ void __launch_bounds__(CG_NT)
 k_cg_max_abs(const double* __restrict__ a, long long n, double* __restrict__ part) {
   double m = 0.0;
   for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT)
-    m = fmax(m, fabs(a[i]));  // fmax drops NaN: a NaN direction is caught by the isfinite test on |g|
-  __shared__ double sm[CG_NT / 32];
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < CG_NT / 32; ++w) m = fmax(m, sm[w]);
-    part[blockIdx.x] = m;
-  }
+    m = fmax(m, fabs(a[i]));
+  cg_block_store_max(m, part);
 }
 
-// out[k] = sum (or max) of part[k * nblk + 0 .. nblk), fixed order; one CTA
+// linminnormalized, pass 1: sum (a_i * s1)^2, the product rounded as ALGLIB's in-place scaling does
 __global__ void __launch_bounds__(CG_NT)
-k_cg_finish(const double* __restrict__ part, int nblk, int nsums, int is_max, double* __restrict__ out) {
+k_cg_scaled_sumsq(const double* __restrict__ a, double s1, long long n, double* __restrict__ part) {
+  double s0 = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    const double t = __dmul_rn(a[i], s1);
+    s0 = fma(t, t, s0);
+  }
+  cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
+}
+
+// linminnormalized, pass 2: d = (dk * s1) * s2; <g0, d>; sum d^2
+__global__ void __launch_bounds__(CG_NT)
+k_cg_normalize(double* __restrict__ d, const double* __restrict__ dk, double s1, double s2,
+               const double* __restrict__ g0, long long n, double* __restrict__ part) {
+  double s0 = 0.0, sq = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    const double v = __dmul_rn(__dmul_rn(dk[i], s1), s2);
+    d[i] = v;
+    s0 = fma(g0[i], v, s0);
+    sq = fma(v, v, sq);
+  }
+  cg_block_store3(s0, sq, 0.0, part, gridDim.x);
+}
+
+// trial point x = x0 + stp * d (product, then sum) and sum (x0 - x)^2
+__global__ void __launch_bounds__(CG_NT)
+k_cg_step(double* __restrict__ x, const double* __restrict__ x0, double stp, const double* __restrict__ d,
+          long long n, double* __restrict__ part) {
+  double s0 = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    const double b = x0[i];
+    const double v = __dadd_rn(b, __dmul_rn(stp, d[i]));
+    x[i] = v;
+    const double t = b - v;
+    s0 = fma(t, t, s0);
+  }
+  cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
+}
+
+// out[k] = sum (or max, where bit k of max_mask is set) of part[k * nblk + 0 .. nblk), fixed order
+__global__ void __launch_bounds__(CG_NT)
+k_cg_finish(const double* __restrict__ part, int nblk, int nsums, int max_mask, double* __restrict__ out) {
   __shared__ double sm[CG_NT];
   for (int k = 0; k < nsums; ++k) {
+    const bool is_max = (max_mask >> k) & 1;
     double v = 0.0;
     for (int i = threadIdx.x; i < nblk; i += CG_NT) v = is_max ? fmax(v, part[k * nblk + i]) : v + part[k * nblk + i];
     sm[threadIdx.x] = v;
@@ -103,15 +151,10 @@ k_cg_finish(const double* __restrict__ part, int nblk, int nsums, int is_max, do
   }
 }
 
-// MODE 0: dst = -src   1: dst = src * a   2: dst = base(src) + a * dir (product, then sum)
-template <int MODE>
 __global__ void __launch_bounds__(CG_NT)
-k_cg_map(double* dst, const double* src, double a, const double* __restrict__ dir, long long n) {
-  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
-    if (MODE == 0) dst[i] = -src[i];
-    if (MODE == 1) dst[i] = __dmul_rn(src[i], a);
-    if (MODE == 2) dst[i] = __dadd_rn(src[i], __dmul_rn(a, dir[i]));
-  }
+k_cg_neg_copy(double* __restrict__ dst, const double* __restrict__ src, long long n) {
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT)
+    dst[i] = -src[i];
 }
 
 // eval_core(ctx, x, g, tail, data term, regularization term, accumulate) and reweight_dev(ctx, x)
@@ -140,8 +183,9 @@ struct DeviceCgBackend {
     check(cudaStreamSynchronize(c->stream), "cg synchronize");
     if (!ok()) h_out[0] = h_out[1] = h_out[2] = h_out[3] = NAN;
   }
-  void finish(int nsums, int is_max = 0) {
-    k_cg_finish<<<1, CG_NT, 0, c->stream>>>(d_part, nblk, nsums, is_max, d_out);
+  // partial sums of the kernel just launched -> d_out[offset .. offset + nsums)
+  void finish(int nsums, int max_mask = 0, int offset = 0) {
+    k_cg_finish<<<1, CG_NT, 0, c->stream>>>(d_part, nblk, nsums, max_mask, d_out + offset);
     c->timing.kernel_launches += 2;
   }
 
@@ -154,25 +198,13 @@ struct DeviceCgBackend {
     fetch();
     *f = h_out[3];
   }
-  void eval_with_slope(Vec x, Vec g, Vec d, double* f, double* dg) {
-    if (ok()) {
-      const srb_status st = eval_core(c, x, g, d_out + 3, true, true, false);
-      if (st != SRB_OK) status = st;
-    }
-    ++evals;
-    k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(g, d, nullptr, n, d_part);
-    finish(1);
-    fetch();
-    *f = h_out[3];
-    *dg = h_out[0];
-  }
   void copy(Vec dst, Vec src) {
     check(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream), "cg copy");
   }
-  void neg_copy(Vec dst, Vec src) { k_cg_map<0><<<nblk, CG_NT, 0, c->stream>>>(dst, src, 0.0, nullptr, n); c->timing.kernel_launches += 1; }
-  void scale_to(Vec dst, Vec src, double a) { k_cg_map<1><<<nblk, CG_NT, 0, c->stream>>>(dst, src, a, nullptr, n); c->timing.kernel_launches += 1; }
-  void scale(Vec v, double a) { scale_to(v, v, a); }
-  void step_to(Vec dst, Vec base, double a, Vec dir) { k_cg_map<2><<<nblk, CG_NT, 0, c->stream>>>(dst, base, a, dir, n); c->timing.kernel_launches += 1; }
+  void neg_copy(Vec dst, Vec src) {
+    k_cg_neg_copy<<<nblk, CG_NT, 0, c->stream>>>(dst, src, n);
+    c->timing.kernel_launches += 1;
+  }
   void zero(Vec v) { check(cudaMemsetAsync(v, 0, (size_t)n * sizeof(double), c->stream), "cg zero"); }
   double dot(Vec a, Vec b) {
     k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(a, b, nullptr, n, d_part);
@@ -186,17 +218,46 @@ struct DeviceCgBackend {
     fetch();
     return h_out[0];
   }
-  double sum_sq_diff(Vec a, Vec b) {
-    k_cg_reduce<2><<<nblk, CG_NT, 0, c->stream>>>(a, b, nullptr, n, d_part);
-    finish(1);
-    fetch();
-    return h_out[0];
-  }
   double max_abs(Vec a) {
     k_cg_max_abs<<<nblk, CG_NT, 0, c->stream>>>(a, n, d_part);
     finish(1, 1);
     fetch();
     return h_out[0];
+  }
+  void normalize_to(Vec d, Vec dk, double mx, Vec g0, double* stp, double* slope, double* dd) {
+    if (mx == 0.0) {  // zero direction: d = dk, slope and length are zero
+      copy(d, dk);
+      *slope = 0.0;
+      *dd = 0.0;
+      return;
+    }
+    const double s1 = 1 / mx;
+    k_cg_scaled_sumsq<<<nblk, CG_NT, 0, c->stream>>>(dk, s1, n, d_part);
+    finish(1);
+    fetch();
+    const double s2 = 1 / std::sqrt(h_out[0]);
+    k_cg_normalize<<<nblk, CG_NT, 0, c->stream>>>(d, dk, s1, s2, g0, n, d_part);
+    finish(2);
+    fetch();
+    *stp = *stp / s1;
+    *stp = *stp / s2;
+    *slope = h_out[0];
+    *dd = h_out[1];
+  }
+  void trial(Vec x, Vec x0, double stp, Vec d, Vec g, double* f, double* dg, double* moved) {
+    k_cg_step<<<nblk, CG_NT, 0, c->stream>>>(x, x0, stp, d, n, d_part);
+    finish(1, 0, 2);  // moved -> d_out[2]
+    if (ok()) {
+      const srb_status st = eval_core(c, x, g, d_out + 3, true, true, false);
+      if (st != SRB_OK) status = st;
+    }
+    ++evals;
+    k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(g, d, nullptr, n, d_part);
+    finish(1);        // <g, d> -> d_out[0]
+    fetch();
+    *f = h_out[3];
+    *dg = h_out[0];
+    *moved = h_out[2];
   }
   void beta_terms(Vec gn, Vec go, Vec dk, double* dy, double* gg, double* gy) {
     k_cg_reduce<3><<<nblk, CG_NT, 0, c->stream>>>(gn, go, dk, n, d_part);
@@ -204,11 +265,11 @@ struct DeviceCgBackend {
     fetch();
     *dy = h_out[0]; *gg = h_out[1]; *gy = h_out[2];
   }
-  void direction(Vec dk, Vec g, double beta, Vec d, double* dd, double* gg) {
-    k_cg_direction<<<nblk, CG_NT, 0, c->stream>>>(dk, g, beta, d, n, d_part);
-    finish(2);
+  void direction(Vec dk, Vec g, double beta, double* gg, double* mx) {
+    k_cg_direction<<<nblk, CG_NT, 0, c->stream>>>(dk, g, beta, n, d_part);
+    finish(2, 2);     // slot 0: sum g^2, slot 1: max |dk|
     fetch();
-    *dd = h_out[0]; *gg = h_out[1];
+    *gg = h_out[0]; *mx = h_out[1];
   }
   void reweight(Vec x) {  // w = 1 / max(1e-5, reg(x)), irls_map_solver.cpp:128-143 (stream-ordered)
     if (!ok()) return;
