@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="HR side of the CPU-baseline crop")
     ap.add_argument("--chunks", type=int, default=4, help="allreduce pipeline depth (N > 1)")
+    ap.add_argument("--solve-iters", type=int, default=0,
+                    help="N = 1 only, off by default: also time one device-resident CG solve of this many "
+                         "iterations through srb_cg_minimize (host x in, host x out) and add it as \"solve\"")
     return ap.parse_args()
 
 
@@ -360,6 +363,16 @@ def main():
                 line["roofline"]["traffic"] = json.load(open(prof)).get(path_name)
             except Exception:
                 pass
+        if args.solve_iters > 0 and world == 1:
+            # the whole inner solve behind one C-ABI call; x crosses PCIe once each way
+            import time
+            t0 = time.perf_counter()
+            _, rep = eng.cg_minimize(h_x.numpy(), maxits=args.solve_iters)
+            dt = time.perf_counter() - t0
+            line["solve"] = {"api": "srb_cg_minimize", "iterations": rep["iterations"],
+                             "evaluations": rep["num_evaluations"], "termination_type": rep["termination_type"],
+                             "seconds": dt, "value": units * rep["num_evaluations"] / dt, "unit": UNIT,
+                             "h2d_bytes": n * 8, "d2h_bytes": n * 8, "final_cost": rep["final_cost"]}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             val, dt, desc, kind = cpu_reference_run(args.config, args.cpu_sample, 3, 1, cores)
