@@ -14,10 +14,11 @@ export PYTHONUNBUFFERED=1
 (timeout 900 python -m pytest tests -q -x -m gpu --durations=15 2>&1 | tail -40) > gpurun_out/r2_gpu_tests.log
 (timeout 120 python tools/ab_zlayout.py 60 2>&1) > gpurun_out/r2_ab_zlayout.log
 (timeout 300 python bench.py 2>gpurun_out/r2_bench.err) > gpurun_out/r2_bench.json
+(timeout 300 python bench.py --steps 20 --no-cpu-baseline --solve-iters 20 2>gpurun_out/r2_bench_solve.err) > gpurun_out/r2_bench_solve.json
 (timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
     --log-file gpurun_out/r2_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline) > gpurun_out/r2_ncu_launch.log 2>&1
 (timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_z -s 3 -c 1 \
     -o gpurun_out/r2_k_tile_z python bench.py --steps 2 --warmup 3 --no-cpu-baseline) > gpurun_out/r2_ncu_full.log 2>&1
 tail -5 gpurun_out/r2_cg_tests.log gpurun_out/r2_zholes_tests.log gpurun_out/r2_gpu_tests.log
 cat gpurun_out/r2_ab_zlayout.log | head -30
-cat gpurun_out/r2_bench.json
+cat gpurun_out/r2_bench.json gpurun_out/r2_bench_solve.json
