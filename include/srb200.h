@@ -140,6 +140,9 @@ typedef struct srb_cg_options {
   double cost_decrease_threshold;        /* EpsF */
   double parameter_variation_threshold;  /* EpsX */
   int max_num_solver_iterations;         /* MaxIts, 0 = unlimited */
+  int num_lbfgs_hessian_corrections;     /* srb_solve_irls: 0 = CG_SOLVER (the reference's default), m > 0 =
+                                            LBFGS_SOLVER with m pairs (map_solver.h:20-23, :51);
+                                            srb_lbfgs_minimize: m, 1..64; srb_cg_minimize ignores it */
 } srb_cg_options;
 typedef struct srb_cg_report {   /* alglib::mincgreport + the cost RunCGSolverAnalyticalDiff returns */
   int iterations;
@@ -162,6 +165,13 @@ srb_status srb_cg_minimize(srb_ctx* ctx, double* x_host_inout, const srb_cg_opti
                            srb_cg_report* report);
 srb_status srb_cg_minimize_dev(srb_ctx* ctx, double* x_dev_inout, const srb_cg_options* options,
                                srb_cg_report* report);
+/* RunLBFGSSolverAnalyticalDiff (alglib_objective.cpp:111-140): ALGLIB's minlbfgs
+ * (optimization.cpp:21640-22330) restated the same way (csrc/srb_cg.h: lbfgs_minimize, bit-identical to
+ * ALGLIB on the CPU); termination type -2 = rounding errors prevent further progress. */
+srb_status srb_lbfgs_minimize(srb_ctx* ctx, double* x_host_inout, const srb_cg_options* options,
+                              srb_cg_report* report);
+srb_status srb_lbfgs_minimize_dev(srb_ctx* ctx, double* x_dev_inout, const srb_cg_options* options,
+                                  srb_cg_report* report);
 /* IRLSMapSolver::RunIRLSLoop (irls_map_solver.cpp:45-157) for the active channel range: weights reset
  * to 1, then { CG solve; w = 1 / max(1e-5, reg(x)) } until the cost of two consecutive outer
  * iterations differs by less than irls_cost_difference_threshold or max_num_irls_iterations (0 =

@@ -33,6 +33,9 @@ struct HostBackend {
   void scale(Vec v, double a) { for (long long i = 0; i < n; ++i) v[i] *= a; }
   void step_to(Vec d, Vec b, double a, Vec dir) { for (long long i = 0; i < n; ++i) d[i] = b[i] + a * dir[i]; }
   void zero(Vec v) { for (long long i = 0; i < n; ++i) v[i] = 0.0; }
+  void add(Vec d, Vec s) { for (long long i = 0; i < n; ++i) d[i] += s[i]; }               // ae_v_add
+  void add_scaled(Vec d, double a, Vec s) { for (long long i = 0; i < n; ++i) d[i] += a * s[i]; }  // ae_v_addd
+  void sub_scaled(Vec d, double a, Vec s) { for (long long i = 0; i < n; ++i) d[i] -= a * s[i]; }  // ae_v_subd
   // ae_v_dotproduct: groups of four, then the remainder
   template <class FA, class FB>
   double dot4(FA a, FB b) {
@@ -124,21 +127,44 @@ int srbcg_host_minimize(long long n, double* x_inout, double epsg, double epsf, 
 // report: [IRLS iterations, CG iterations (summed), nfev (summed), last termination type, final f]
 int srbcg_host_irls(long long n, double* x_inout, double epsg, double epsf, double epsx, int maxits,
                     int max_irls_iterations, double cost_difference_threshold, int has_regularizer,
-                    srbcg_fg_cb cb, srbcg_reweight_cb rw, void* user, double* report) {
+                    int lbfgs_corrections, srbcg_fg_cb cb, srbcg_reweight_cb rw, void* user, double* report) {
   HostBackend be{n, cb, user};
   be.rw = rw;
-  std::vector<double> store((size_t)srb::kCgScratchVectors * n);
-  double* scratch[srb::kCgScratchVectors];
-  for (int i = 0; i < srb::kCgScratchVectors; ++i) scratch[i] = store.data() + (size_t)i * n;
+  const int nv = lbfgs_corrections > 0 ? srb::lbfgs_scratch_vectors(lbfgs_corrections) : srb::kCgScratchVectors;
+  std::vector<double> store((size_t)nv * n);
+  std::vector<double*> scratch_v(nv);
+  for (int i = 0; i < nv; ++i) scratch_v[i] = store.data() + (size_t)i * n;
+  double** scratch = scratch_v.data();
   srb::CgOptions opt;
   opt.epsg = epsg; opt.epsf = epsf; opt.epsx = epsx; opt.maxits = maxits;
   const srb::IrlsReport rep = srb::irls_solve(be, x_inout, scratch, opt, max_irls_iterations,
-                                              cost_difference_threshold, has_regularizer != 0);
+                                              cost_difference_threshold, has_regularizer != 0, lbfgs_corrections);
   report[0] = rep.irls_iterations;
   report[1] = rep.solver_iterations;
   report[2] = rep.nfev;
   report[3] = rep.last_termination;
   report[4] = rep.f;
+  return 0;
+}
+
+// ALGLIB minlbfgs restated (srb_cg.h: lbfgs_minimize) over host arrays.
+// report: [iterations, nfev, termination type, final f, restarts, objective evaluations]
+int srbcg_host_lbfgs(long long n, double* x_inout, int m, double epsg, double epsf, double epsx, int maxits,
+                     srbcg_fg_cb cb, void* user, double* report) {
+  HostBackend be{n, cb, user};
+  const int nv = srb::lbfgs_scratch_vectors(m);
+  std::vector<double> store((size_t)nv * n);
+  std::vector<double*> scratch(nv);
+  for (int i = 0; i < nv; ++i) scratch[i] = store.data() + (size_t)i * n;
+  srb::CgOptions opt;
+  opt.epsg = epsg; opt.epsf = epsf; opt.epsx = epsx; opt.maxits = maxits;
+  const srb::CgReport rep = srb::lbfgs_minimize(be, x_inout, scratch.data(), m, opt);
+  report[0] = rep.iterations;
+  report[1] = rep.nfev;
+  report[2] = rep.termination;
+  report[3] = rep.f;
+  report[4] = rep.restarts;
+  report[5] = (double)be.evals;
   return 0;
 }
 }

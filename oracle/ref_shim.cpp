@@ -386,5 +386,27 @@ int ref_mincg(long long n, double* x_inout, double epsg, double epsf, double eps
   return 0;
 }
 
+// ALGLIB's minlbfgs configured as RunLBFGSSolverAnalyticalDiff does (alglib_objective.cpp:111-140).
+// report: [iterations, nfev, termination type, final f (minlbfgsstate.f)]
+int ref_minlbfgs(long long n, double* x_inout, int m, double epsg, double epsf, double epsx, int maxits,
+                 ref_fg_cb cb, void* user, double* report) {
+  alglib::real_1d_array x;
+  x.setcontent((alglib::ae_int_t)n, x_inout);
+  alglib::minlbfgsstate state;
+  alglib::minlbfgsreport rep;
+  alglib::minlbfgscreate(m, x, state);
+  alglib::minlbfgssetcond(state, epsg, epsf, epsx, maxits);
+  alglib::minlbfgssetxrep(state, true);
+  FgClosure closure{cb, user};
+  alglib::minlbfgsoptimize(state, FgThunk, NoReport, &closure);
+  alglib::minlbfgsresults(state, x, rep);
+  std::memcpy(x_inout, x.getcontent(), (size_t)n * sizeof(double));
+  report[0] = (double)rep.iterationscount;
+  report[1] = (double)rep.nfev;
+  report[2] = (double)rep.terminationtype;
+  report[3] = state.f;
+  return 0;
+}
+
 }  // extern "C"
 

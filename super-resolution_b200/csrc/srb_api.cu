@@ -508,7 +508,8 @@ static CgOptions cg_options_from(const srb_cg_options* o) {
 }
 static bool cg_options_valid(const srb_cg_options* o) {
   // mincgsetcond asserts finite, non-negative thresholds and a non-negative iteration limit
-  return !o || (std::isfinite(o->gradient_norm_threshold) && o->gradient_norm_threshold >= 0 &&
+  return !o || (o->num_lbfgs_hessian_corrections >= 0 && o->num_lbfgs_hessian_corrections <= 64 &&
+                std::isfinite(o->gradient_norm_threshold) && o->gradient_norm_threshold >= 0 &&
                 std::isfinite(o->cost_decrease_threshold) && o->cost_decrease_threshold >= 0 &&
                 std::isfinite(o->parameter_variation_threshold) && o->parameter_variation_threshold >= 0 &&
                 o->max_num_solver_iterations >= 0);
@@ -532,6 +533,35 @@ srb_status srb_cg_minimize_dev(srb_ctx* c, double* x_dev, const srb_cg_options* 
   srb_status st = cg_minimize_dev(c, x_dev, cg_options_from(options), &rep);
   if (st != SRB_OK) return st;
   cg_report_to(rep, report);
+  return SRB_OK;
+}
+
+srb_status srb_lbfgs_minimize_dev(srb_ctx* c, double* x_dev, const srb_cg_options* options, srb_cg_report* report) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev) return c->fail(SRB_ERR_INVALID, "null estimate");
+  if (!options || !cg_options_valid(options) || options->num_lbfgs_hessian_corrections < 1)
+    return c->fail(SRB_ERR_INVALID, "invalid solver options (L-BFGS needs 1..64 correction pairs)");
+  if ((long long)options->num_lbfgs_hessian_corrections > (long long)c->n_active())
+    return c->fail(SRB_ERR_INVALID, "more correction pairs than parameters");  // minlbfgscreate asserts M <= N
+  if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  CgReport rep;
+  srb_status st = lbfgs_minimize_dev(c, x_dev, options->num_lbfgs_hessian_corrections, cg_options_from(options), &rep);
+  if (st != SRB_OK) return st;
+  cg_report_to(rep, report);
+  return SRB_OK;
+}
+
+srb_status srb_lbfgs_minimize(srb_ctx* c, double* x_host, const srb_cg_options* options, srb_cg_report* report) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  const size_t bytes = c->n_active() * sizeof(double);
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  srb_status st = srb_lbfgs_minimize_dev(c, c->d_x, options, report);
+  if (st != SRB_OK) return st;
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(x_host, c->d_x, bytes, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   return SRB_OK;
 }
 
@@ -562,7 +592,8 @@ srb_status srb_solve_irls(srb_ctx* c, double* x_host, const srb_cg_options* opti
   if (st != SRB_OK) return st;
   IrlsReport rep;
   st = irls_solve_dev(c, c->d_x, cg_options_from(options), max_num_irls_iterations,
-                      irls_cost_difference_threshold, reg_active(c), &rep);
+                      irls_cost_difference_threshold, reg_active(c),
+                      options ? options->num_lbfgs_hessian_corrections : 0, &rep);
   if (st != SRB_OK) return st;
   srb_irls_report out{};
   out.num_irls_iterations = rep.irls_iterations;

@@ -37,6 +37,11 @@
 //   void   direction(Vec dk, Vec g, double beta, double* gg, double* mx);
 //            dk = -g + beta * dk (in place);  gg = sum g_i^2;  mx = max |dk_i| of the new direction
 //   void   reweight(Vec x);                                    irls_solve only: new IRLS weights from x
+//   lbfgs_minimize only:
+//   void   add(Vec dst, Vec src);                              dst += src
+//   void   add_scaled(Vec dst, double a, Vec src);             dst += a * src   (ae_v_addd)
+//   void   sub_scaled(Vec dst, double a, Vec src);             dst -= a * src   (ae_v_subd)
+//   void   scale(Vec v, double a);                             v *= a
 #pragma once
 #include <cmath>
 
@@ -61,6 +66,7 @@ namespace cg_detail {
 
 constexpr double kFtol = 1e-3;                     // sufficient decrease
 constexpr double kGtol = 0.3;                      // curvature condition (mincg's)
+constexpr double kGtolLbfgs = 0.4;                 // minlbfgs's (optimization.cpp:8941)
 constexpr double kXtol = 100 * 5e-16;               // ALGLIB's ae_machineepsilon is 5e-16 (ap.h:855)
 constexpr int kMaxFev = 20;
 constexpr double kStpMin = 1e-50;
@@ -176,7 +182,8 @@ inline int trial_step(Bracket& b, double& stp, double fp, double dp, double stmi
 // 6 rounding / no progress, 0 d is not a descent direction (nothing evaluated, nfev left as it was).
 template <class B>
 void line_search(B& be, typename B::Vec x0, double dginit, typename B::Vec x, typename B::Vec g, double& f,
-                 typename B::Vec d, double& stp, double stpmax, double trim_threshold, int& info, int& nfev) {
+                 typename B::Vec d, double& stp, double stpmax, double gtol, double trim_threshold, int& info,
+                 int& nfev) {
   if (stpmax == 0.0) stpmax = kStpMaxDefault;
   if (stp < kStpMin) stp = kStpMin;
   if (stp > stpmax) stp = stpmax;
@@ -229,12 +236,12 @@ void line_search(B& be, typename B::Vec x0, double dginit, typename B::Vec x, ty
     if (stp == kStpMin && (f >= finit || f > ftest1 || dg >= dgtest)) info = 4;
     if (nfev >= kMaxFev) info = 3;
     if (br.bracketed && stmax - stmin <= kXtol * stmax) info = 2;
-    if (f < finit && f <= ftest1 && std::fabs(dg) <= -kGtol * dginit) info = 1;
+    if (f < finit && f <= ftest1 && std::fabs(dg) <= -gtol * dginit) info = 1;
     if (info != 0) {
       if ((info == 1 || info == 5) && (f >= finit || moved == 0.0)) info = 6;
       return;
     }
-    if (stage1 && f <= ftest1 && dg >= min2(kFtol, kGtol) * dginit) stage1 = false;
+    if (stage1 && f <= ftest1 && dg >= min2(kFtol, gtol) * dginit) stage1 = false;
     if (stage1 && f <= br.fx && f > ftest1) {
       // not enough decrease yet: work on f(x0 + t d) - f(x0) - ftol * t * dginit
       Bracket m = br;
@@ -293,7 +300,7 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, C
     be.normalize_to(d, dk, mx, gk, &stp, &dginit, &dd);
     if (last_good_step != 0.0) stp = last_good_step;
     int info = 0;
-    line_search(be, xk, dginit, xt, gt, f, d, stp, 0.0, trim_threshold, info, nfev);
+    line_search(be, xk, dginit, xt, gt, f, d, stp, 0.0, kGtol, trim_threshold, info, nfev);
     if (info == 0) {  // nothing was evaluated: the "new" point is the current one
       be.copy(xt, xk);
       be.copy(gt, gk);
@@ -330,6 +337,100 @@ CgReport cg_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, C
   return rep;
 }
 
+// ALGLIB's minlbfgs as the reference configures it (RunLBFGSSolverAnalyticalDiff,
+// alglib_objective.cpp:111-140; optimization.cpp:21640-22330): m correction pairs, default
+// preconditioner (gamma_k scaling), no step bound, the same line search with gtol = 0.4.  First
+// step min(1/|g|, 1), later ones 1; a line search that does not end on the Wolfe conditions
+// restarts from the antigradient WITHOUT advancing the pair counter.  Scratch: 5 + 2 m vectors.
+// Termination types as in CgReport plus -2 (s'y or y'y rounded to zero).
+inline int lbfgs_scratch_vectors(int m) { return 5 + 2 * m; }
+
+template <class B>
+CgReport lbfgs_minimize(B& be, typename B::Vec x_inout, typename B::Vec* scratch, int m, CgOptions opt) {
+  using namespace cg_detail;
+  using Vec = typename B::Vec;
+  if (opt.epsg == 0.0 && opt.epsf == 0.0 && opt.epsx == 0.0 && opt.maxits == 0) opt.epsx = 1e-6;
+  CgReport rep;
+  Vec xk = x_inout, xt = scratch[0];   // current point (x0 of the line search), trial point
+  Vec g = scratch[1];
+  Vec d = scratch[2], du = scratch[3];  // search direction and its normalised copy
+  Vec work = scratch[4];
+  Vec* sk = scratch + 5;
+  Vec* yk = scratch + 5 + m;
+  double rho[64], theta[64];
+  if (m < 1 || m > 64) { rep.termination = -1; return rep; }
+  double f = 0.0;
+  be.eval(xk, g, &f);
+  const double trim_threshold = 10 * (std::fabs(f) + 1);
+  rep.nfev = 1;
+  rep.f = f;
+  double fold = f;
+  if (std::sqrt(be.sum_sq(g)) <= opt.epsg) {
+    rep.termination = 4;
+    return rep;
+  }
+  be.neg_copy(d, g);
+  double stp = min2(1.0 / std::sqrt(be.dot(g, g)), 1.0);
+  int k = 0;
+  int nfev = 0;
+  for (;;) {
+    const int p = k % m;
+    const int q = k < m - 1 ? k : m - 1;
+    be.neg_copy(sk[p], xk);
+    be.neg_copy(yk[p], g);
+    if (k != 0) stp = 1.0;
+    double dginit = 0.0, dd = 0.0;
+    be.normalize_to(du, d, be.max_abs(d), g, &stp, &dginit, &dd);
+    int info = 0;
+    // g is overwritten by the line search: its slope at x0 was taken above
+    line_search(be, xk, dginit, xt, g, f, du, stp, 0.0, kGtolLbfgs, trim_threshold, info, nfev);
+    if (info == 0) be.copy(xt, xk);  // nothing evaluated: the new point is the current one
+    rep.nfev += nfev;
+    rep.iterations += 1;
+    rep.f = f;
+    be.add(sk[p], xt);
+    be.add(yk[p], g);
+    { Vec t = xk; xk = xt; xt = t; }
+    const double gg = be.sum_sq(g);
+    if (!std::isfinite(gg) || !std::isfinite(f)) { rep.termination = -8; break; }
+    if (rep.iterations >= opt.maxits && opt.maxits > 0) { rep.termination = 5; break; }
+    if (std::sqrt(gg) <= opt.epsg) { rep.termination = 4; break; }
+    if (fold - f <= opt.epsf * max2(std::fabs(fold), max2(std::fabs(f), 1.0))) { rep.termination = 1; break; }
+    if (std::sqrt(be.sum_sq(sk[p])) <= opt.epsx) { rep.termination = 2; break; }
+    if (info != 1) {
+      // no Wolfe point: skip the update, restart from the antigradient
+      rep.restarts += 1;
+      fold = f;
+      be.neg_copy(d, g);
+      continue;
+    }
+    const double sy = be.dot(yk[p], sk[p]);
+    const double yy = be.dot(yk[p], yk[p]);
+    if (sy == 0.0 || yy == 0.0) { rep.termination = -2; break; }
+    rho[p] = 1 / sy;
+    const double gamma = sy / yy;
+    // two-loop recursion: work = H_{k+1} g
+    be.copy(work, g);
+    for (int i = k; i >= k - q; --i) {
+      const int ic = i % m;
+      const double v = be.dot(sk[ic], work);
+      theta[ic] = v;
+      be.sub_scaled(work, v * rho[ic], yk[ic]);
+    }
+    be.scale(work, gamma);
+    for (int i = k - q; i <= k; ++i) {
+      const int ic = i % m;
+      const double v = be.dot(yk[ic], work);
+      be.add_scaled(work, rho[ic] * (-v + theta[ic]), sk[ic]);
+    }
+    be.neg_copy(d, work);
+    fold = f;
+    k += 1;
+  }
+  if (xk != x_inout) be.copy(x_inout, xk);
+  return rep;
+}
+
 // IRLSMapSolver::RunIRLSLoop (irls_map_solver.cpp:45-157): conjugate-gradient solves of the
 // re-weighted least-squares problem until the cost of two consecutive solves differs by less than
 // the threshold.  The backend's objective must use the weights that be.reweight(x) installs
@@ -342,14 +443,18 @@ struct IrlsReport {
   double f = 0.0;             // cost the last CG solve returned
 };
 
+// lbfgs_corrections = 0: conjugate gradients (CG_SOLVER, the default); m > 0: L-BFGS with m pairs
+// (LBFGS_SOLVER; scratch must then hold lbfgs_scratch_vectors(m) vectors).
 template <class B>
 IrlsReport irls_solve(B& be, typename B::Vec x_inout, typename B::Vec* scratch, const CgOptions& opt,
-                      int max_irls_iterations, double cost_difference_threshold, bool has_regularizer) {
+                      int max_irls_iterations, double cost_difference_threshold, bool has_regularizer,
+                      int lbfgs_corrections = 0) {
   IrlsReport out;
   double previous_cost = INFINITY;
   double cost_difference = cost_difference_threshold + 1.0;
   while (std::fabs(cost_difference) >= cost_difference_threshold) {
-    const CgReport rep = cg_minimize(be, x_inout, scratch, opt);
+    const CgReport rep = lbfgs_corrections > 0 ? lbfgs_minimize(be, x_inout, scratch, lbfgs_corrections, opt)
+                                               : cg_minimize(be, x_inout, scratch, opt);
     out.solver_iterations += rep.iterations;
     out.nfev += rep.nfev;
     out.last_termination = rep.termination;

@@ -7,6 +7,7 @@
 #pragma once
 #include <algorithm>
 #include <string>
+#include <vector>
 
 #include "srb_cg.h"
 #include "srb_common.cuh"
@@ -151,6 +152,18 @@ k_cg_finish(const double* __restrict__ part, int nblk, int nsums, int max_mask, 
   }
 }
 
+// MODE 0: dst += src   1: dst += a * src   2: dst -= a * src   3: dst *= a   (products rounded first)
+template <int MODE>
+__global__ void __launch_bounds__(CG_NT)
+k_cg_update(double* __restrict__ dst, double a, const double* __restrict__ src, long long n) {
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    if (MODE == 0) dst[i] = __dadd_rn(dst[i], src[i]);
+    if (MODE == 1) dst[i] = __dadd_rn(dst[i], __dmul_rn(a, src[i]));
+    if (MODE == 2) dst[i] = __dsub_rn(dst[i], __dmul_rn(a, src[i]));
+    if (MODE == 3) dst[i] = __dmul_rn(dst[i], a);
+  }
+}
+
 __global__ void __launch_bounds__(CG_NT)
 k_cg_neg_copy(double* __restrict__ dst, const double* __restrict__ src, long long n) {
   for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT)
@@ -271,6 +284,11 @@ struct DeviceCgBackend {
     fetch();
     *gg = h_out[0]; *mx = h_out[1];
   }
+  // L-BFGS only (two-loop recursion, pair updates)
+  void add(Vec dst, Vec src) { k_cg_update<0><<<nblk, CG_NT, 0, c->stream>>>(dst, 0.0, src, n); c->timing.kernel_launches += 1; }
+  void add_scaled(Vec dst, double a, Vec src) { k_cg_update<1><<<nblk, CG_NT, 0, c->stream>>>(dst, a, src, n); c->timing.kernel_launches += 1; }
+  void sub_scaled(Vec dst, double a, Vec src) { k_cg_update<2><<<nblk, CG_NT, 0, c->stream>>>(dst, a, src, n); c->timing.kernel_launches += 1; }
+  void scale(Vec v, double a) { k_cg_update<3><<<nblk, CG_NT, 0, c->stream>>>(v, a, nullptr, n); c->timing.kernel_launches += 1; }
   void reweight(Vec x) {  // w = 1 / max(1e-5, reg(x)), irls_map_solver.cpp:128-143 (stream-ordered)
     if (!ok()) return;
     const srb_status st = reweight_dev(c, x);
@@ -282,14 +300,14 @@ struct DeviceCgBackend {
 struct DeviceCgWorkspace {
   double* store = nullptr;
   double* h_out = nullptr;
-  double* scratch[kCgScratchVectors];
+  std::vector<double*> scratch;
   ~DeviceCgWorkspace() {
     if (store) cudaFree(store);
     if (h_out) cudaFreeHost(h_out);
   }
-  srb_status init(srb_ctx* c, DeviceCgBackend* be) {
+  srb_status init(srb_ctx* c, DeviceCgBackend* be, int num_vectors = kCgScratchVectors) {
     const long long n = (long long)c->n_active();
-    const size_t doubles = (size_t)kCgScratchVectors * n + 3 * CG_MAX_BLOCKS + 4;
+    const size_t doubles = (size_t)num_vectors * n + 3 * CG_MAX_BLOCKS + 4;
     if (cudaMalloc((void**)&store, doubles * sizeof(double)) != cudaSuccess) {
       (void)cudaGetLastError();
       store = nullptr;
@@ -302,12 +320,13 @@ struct DeviceCgWorkspace {
     }
     be->c = c;
     be->n = n;
-    be->d_part = store + (size_t)kCgScratchVectors * n;
+    be->d_part = store + (size_t)num_vectors * n;
     be->d_out = be->d_part + 3 * CG_MAX_BLOCKS;
     be->h_out = h_out;
     const long long want = (n + CG_NT - 1) / CG_NT;
     be->nblk = (int)std::max(1LL, std::min<long long>(std::min<long long>(want, (long long)c->num_sms * 8), CG_MAX_BLOCKS));
-    for (int i = 0; i < kCgScratchVectors; ++i) scratch[i] = store + (size_t)i * n;
+    scratch.resize(num_vectors);
+    for (int i = 0; i < num_vectors; ++i) scratch[i] = store + (size_t)i * n;
     return SRB_OK;
   }
   srb_status finish(srb_ctx* c, const DeviceCgBackend& be) {
@@ -325,18 +344,30 @@ inline srb_status cg_minimize_dev(srb_ctx* c, double* d_x, const CgOptions& opt,
   DeviceCgWorkspace ws;
   srb_status st = ws.init(c, &be);
   if (st != SRB_OK) return st;
-  *rep = cg_minimize(be, d_x, ws.scratch, opt);
+  *rep = cg_minimize(be, d_x, ws.scratch.data(), opt);
+  return ws.finish(c, be);
+}
+
+// RunLBFGSSolverAnalyticalDiff (alglib_objective.cpp:111-140) on a device-resident estimate.
+inline srb_status lbfgs_minimize_dev(srb_ctx* c, double* d_x, int m, const CgOptions& opt, CgReport* rep) {
+  DeviceCgBackend be;
+  DeviceCgWorkspace ws;
+  srb_status st = ws.init(c, &be, lbfgs_scratch_vectors(m));
+  if (st != SRB_OK) return st;
+  *rep = lbfgs_minimize(be, d_x, ws.scratch.data(), m, opt);
   return ws.finish(c, be);
 }
 
 // IRLSMapSolver::RunIRLSLoop on a device-resident estimate; the weights must have been reset to 1.
 inline srb_status irls_solve_dev(srb_ctx* c, double* d_x, const CgOptions& opt, int max_irls_iterations,
-                                 double cost_difference_threshold, bool has_regularizer, IrlsReport* rep) {
+                                 double cost_difference_threshold, bool has_regularizer, int lbfgs_corrections,
+                                 IrlsReport* rep) {
   DeviceCgBackend be;
   DeviceCgWorkspace ws;
-  srb_status st = ws.init(c, &be);
+  srb_status st = ws.init(c, &be, lbfgs_corrections > 0 ? lbfgs_scratch_vectors(lbfgs_corrections) : kCgScratchVectors);
   if (st != SRB_OK) return st;
-  *rep = irls_solve(be, d_x, ws.scratch, opt, max_irls_iterations, cost_difference_threshold, has_regularizer);
+  *rep = irls_solve(be, d_x, ws.scratch.data(), opt, max_irls_iterations, cost_difference_threshold,
+                    has_regularizer, lbfgs_corrections);
   return ws.finish(c, be);
 }
 

@@ -37,6 +37,8 @@ SIGNATURES = {
     "srb_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "srb_cg_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srb_cg_minimize_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_lbfgs_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_lbfgs_minimize_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srb_solve_irls": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "srb_set_path": (C.c_int, [_ctx_p, C.c_int]),
     "srb_active_path": (C.c_int, [_ctx_p]),
@@ -93,7 +95,8 @@ class Timing(C.Structure):
 class CgOptions(C.Structure):
     """srb_cg_options: the thresholds of mincgsetcond (alglib_objective.cpp:57-62)."""
     _fields_ = [("gradient_norm_threshold", C.c_double), ("cost_decrease_threshold", C.c_double),
-                ("parameter_variation_threshold", C.c_double), ("max_num_solver_iterations", C.c_int)]
+                ("parameter_variation_threshold", C.c_double), ("max_num_solver_iterations", C.c_int),
+                ("num_lbfgs_hessian_corrections", C.c_int)]
 
 
 class CgReport(C.Structure):
@@ -254,8 +257,8 @@ class Engine:
 
     # -- device-resident solver
     @staticmethod
-    def _cg_options(epsg, epsf, epsx, maxits):
-        return CgOptions(float(epsg), float(epsf), float(epsx), int(maxits))
+    def _cg_options(epsg, epsf, epsx, maxits, lbfgs_corrections=0):
+        return CgOptions(float(epsg), float(epsf), float(epsx), int(maxits), int(lbfgs_corrections))
 
     def cg_minimize(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
         """RunCGSolverAnalyticalDiff with the solver vectors on the device.  Returns (x, report dict)."""
@@ -265,17 +268,25 @@ class Engine:
         self._check(self._lib.srb_cg_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
         return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
 
+    def lbfgs_minimize(self, x0, corrections=5, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        """RunLBFGSSolverAnalyticalDiff with the solver vectors on the device.  Returns (x, report dict)."""
+        x = np.array(_f64(x0).reshape(-1), copy=True)
+        assert x.size == self.num_active
+        opt, rep = self._cg_options(epsg, epsf, epsx, maxits, corrections), CgReport()
+        self._check(self._lib.srb_lbfgs_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
+        return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
+
     def cg_minimize_dev(self, x_dev, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
         opt, rep = self._cg_options(epsg, epsf, epsx, maxits), CgReport()
         self._check(self._lib.srb_cg_minimize_dev(self._ctx, _dev_ptr(x_dev), C.byref(opt), C.byref(rep)))
         return _as_dict(rep)
 
     def solve_irls(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0, max_irls_iterations=0,
-                   irls_cost_difference_threshold=0.0):
+                   irls_cost_difference_threshold=0.0, lbfgs_corrections=0):
         """IRLSMapSolver::RunIRLSLoop on the device.  Returns (x, report dict)."""
         x = np.array(_f64(x0).reshape(-1), copy=True)
         assert x.size == self.num_active
-        opt, rep = self._cg_options(epsg, epsf, epsx, maxits), IrlsReport()
+        opt, rep = self._cg_options(epsg, epsf, epsx, maxits, lbfgs_corrections), IrlsReport()
         self._check(self._lib.srb_solve_irls(self._ctx, _host_ptr(x), C.byref(opt), int(max_irls_iterations),
                                              float(irls_cost_difference_threshold), C.byref(rep)))
         return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)

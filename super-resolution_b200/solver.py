@@ -18,6 +18,8 @@ class IrlsMapSolverOptions:
     cost_decrease_threshold: float = 1.0e-6        # :60
     parameter_variation_threshold: float = 1.0e-6  # :62
     split_channels: bool = False
+    least_squares_solver: str = "cg"               # CG_SOLVER (default) | "lbfgs" (map_solver.h:20-23)
+    num_lbfgs_hessian_corrections: int = 5         # :51
     max_num_irls_iterations: int = 20              # irls_map_solver.h:27
     irls_cost_difference_threshold: float = 1.0e-5  # :35
 
@@ -66,7 +68,9 @@ def solve(engine, initial_estimate, options=None, regularization_parameter_sum=0
                                  epsx=scaled.parameter_variation_threshold,
                                  maxits=scaled.max_num_solver_iterations,
                                  max_irls_iterations=scaled.max_num_irls_iterations,
-                                 irls_cost_difference_threshold=scaled.irls_cost_difference_threshold)
+                                 irls_cost_difference_threshold=scaled.irls_cost_difference_threshold,
+                                 lbfgs_corrections=(scaled.num_lbfgs_hessian_corrections
+                                                    if scaled.least_squares_solver == "lbfgs" else 0))
     try:
         return solve_rounds(device_round, x0, options, regularization_parameter_sum)
     finally:

@@ -103,10 +103,15 @@ def cases():
     ]
 
 
-def run(fn, x0, fg, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
-    """Runs one solver entry point (ref_mincg or srbcg_host_minimize).  Returns (x, report, f trace)."""
+ARGTYPES_LBFGS = [C.c_longlong, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, FG,
+                  C.c_void_p, C.POINTER(C.c_double)]
+
+
+def run(fn, x0, fg, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0, lbfgs_m=0):
+    """Runs one solver entry point (ref_mincg / srbcg_host_minimize, or with lbfgs_m > 0 ref_minlbfgs /
+    srbcg_host_lbfgs).  Returns (x, report, f trace)."""
     fn.restype = C.c_int
-    fn.argtypes = ARGTYPES
+    fn.argtypes = ARGTYPES_LBFGS if lbfgs_m > 0 else ARGTYPES
     if hasattr(fg, "reset"):
         fg.reset()
     x = np.array(x0, dtype=np.float64)
@@ -118,6 +123,6 @@ def run(fn, x0, fg, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
         fp[0] = f
         np.ctypeslib.as_array(gp, (n,))[:] = g
         trace.append(float(f))
-    fn(len(x), x.ctypes.data_as(C.POINTER(C.c_double)), epsg, epsf, epsx, maxits, FG(cb), None,
-       rep.ctypes.data_as(C.POINTER(C.c_double)))
+    head = (len(x), x.ctypes.data_as(C.POINTER(C.c_double))) + ((lbfgs_m,) if lbfgs_m > 0 else ())
+    fn(*head, epsg, epsf, epsx, maxits, FG(cb), None, rep.ctypes.data_as(C.POINTER(C.c_double)))
     return x, rep, np.array(trace)

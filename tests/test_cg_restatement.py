@@ -65,17 +65,39 @@ def test_restatement_reproduces_alglib_live(host_cg, case):
     np.testing.assert_array_equal(xh, xr)
 
 
+# ---- L-BFGS (LBFGS_SOLVER, alglib_objective.cpp:111-140) -----------------------------------------
+LBFGS_CASES = [(c, m) for c in CASES for m in ((5, 3) if c[0].startswith("rosenbrock10") else (5,))]
+
+
+@pytest.mark.parametrize("case,m", LBFGS_CASES, ids=["lbfgs%d_%s" % (m, c[0]) for c, m in LBFGS_CASES])
+def test_lbfgs_restatement_reproduces_alglib(host_cg, golden, case, m):
+    """lbfgs_minimize over host arrays against ALGLIB's minlbfgs: the committed fixture always, ALGLIB
+    live where oracle/_ref is present."""
+    name, fg, x0, kw = case
+    x, rep, trace = cg_cases.run(host_cg.srbcg_host_lbfgs, x0, fg, lbfgs_m=m, **kw)
+    key = "lbfgs%d_%s" % (m, name)
+    np.testing.assert_array_equal(rep[:4], golden[key + "_report"])
+    np.testing.assert_array_equal(trace, golden[key + "_trace"])
+    np.testing.assert_array_equal(x, golden[key + "_x"])
+    from oracle import sr_ref
+    if sr_ref.available():
+        xr, rr, tr = cg_cases.run(sr_ref.lib().ref_minlbfgs, x0, fg, lbfgs_m=m, **kw)
+        np.testing.assert_array_equal(rep[:4], rr[:4])
+        np.testing.assert_array_equal(trace, tr)
+        np.testing.assert_array_equal(x, xr)
+
+
 # ---- the IRLS loop and the round structure of IRLSMapSolver::Solve ------------------------------
 RW = C.CFUNCTYPE(None, C.c_longlong, C.POINTER(C.c_double), C.c_void_p)
 
 
-def _host_irls_round_solver(host_cg, oracle, model, obs_hr, reg_kind, lam):
+def _host_irls_round_solver(host_cg, oracle, model, obs_hr, reg_kind, lam, lbfgs_corrections=0):
     """round_solver for solver.solve_rounds: srb_cg.h's irls_solve over host arrays, the objective
     and the re-weighting being the oracle's (data term + IRLS-weighted regularizer)."""
     fn = host_cg.srbcg_host_irls
     fn.restype = C.c_int
     fn.argtypes = [C.c_longlong, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
-                   C.c_double, C.c_int, cg_cases.FG, RW, C.c_void_p, C.POINTER(C.c_double)]
+                   C.c_double, C.c_int, C.c_int, cg_cases.FG, RW, C.c_void_p, C.POINTER(C.c_double)]
 
     def round_solver(c0, c1, x0_slice, opt):
         Cn, H, W = x0_slice.shape
@@ -97,13 +119,13 @@ def _host_irls_round_solver(host_cg, oracle, model, obs_hr, reg_kind, lam):
         fn(x.size, x.ctypes.data_as(C.POINTER(C.c_double)), opt.gradient_norm_threshold,
            opt.cost_decrease_threshold, opt.parameter_variation_threshold, opt.max_num_solver_iterations,
            opt.max_num_irls_iterations, opt.irls_cost_difference_threshold, 1 if lam > 0 else 0,
-           cg_cases.FG(fg), RW(rw), None, rep.ctypes.data_as(C.POINTER(C.c_double)))
+           lbfgs_corrections, cg_cases.FG(fg), RW(rw), None, rep.ctypes.data_as(C.POINTER(C.c_double)))
         return x.reshape(Cn, H, W), rep
     return round_solver
 
 
-@pytest.mark.parametrize("split_channels", [False, True])
-def test_irls_solve_mirror_reproduces_the_reference_solver(host_cg, oracle, ref, split_channels):
+@pytest.mark.parametrize("split_channels,lbfgs", [(False, False), (True, False), (False, True)])
+def test_irls_solve_mirror_reproduces_the_reference_solver(host_cg, oracle, ref, split_channels, lbfgs):
     """solver.solve_rounds + srb_cg.h's irls_solve + cg_minimize (host backend, oracle objective)
     against the reference's IRLSMapSolver::Solve (oracle/_ref: irls_map_solver.cpp, ALGLIB, the
     reference's TV regularizer; data term = oracle): BASELINE configuration 1's shape and defaults
@@ -120,11 +142,14 @@ def test_irls_solve_mirror_reproduces_the_reference_solver(host_cg, oracle, ref,
     x0 = wl.bilinear_upsample(lr[0], s)
     opt_ref = ref.default_options()
     opt_ref.split_channels = 1 if split_channels else 0
+    opt_ref.solver = 1 if lbfgs else 0                       # LBFGS_SOLVER, 5 correction pairs
     expect, _ = ref.solve(m, lr, x0, reg_kind=oracle.REG_TV, lam=lam, options=opt_ref)
     mine = solver.IrlsMapSolverOptions(split_channels=split_channels)
     obs_hr = oracle.upsample_observations(m, lr)
-    got, reports = solver.solve_rounds(_host_irls_round_solver(host_cg, oracle, m, obs_hr, oracle.REG_TV, lam),
-                                       x0, mine, regularization_parameter_sum=lam)
+    got, reports = solver.solve_rounds(
+        _host_irls_round_solver(host_cg, oracle, m, obs_hr, oracle.REG_TV, lam,
+                                lbfgs_corrections=opt_ref.num_lbfgs_hessian_corrections if lbfgs else 0),
+        x0, mine, regularization_parameter_sum=lam)
     assert len(reports) == (3 if split_channels else 1)
     assert all(r[0] >= 1 for r in reports)
     np.testing.assert_array_equal(got, expect)

@@ -74,6 +74,26 @@ def test_device_cg_follows_alglib_on_the_same_objective(srb, oracle, ref, reg):
     assert abs(rd["final_cost"] - ra[3]) <= 1e-10 * abs(ra[3])
 
 
+def test_device_lbfgs_follows_alglib_on_the_same_objective(srb, oracle, ref):
+    """ALGLIB's minlbfgs (5 pairs) with the device objective behind a host callback against
+    srb_lbfgs_minimize."""
+    psf, shifts, lr, x0 = _problem(oracle)
+    with srb.Engine(lr.shape, 2, psf, shifts) as e:
+        e.set_observations(lr)
+        e.set_regularizer(srb.REG_TV, 0.01)
+        kw = dict(epsg=1e-7, epsf=1e-12, epsx=1e-10, maxits=25)
+
+        def fg(x):
+            f, g = e.eval(x)
+            return f, g.ravel()
+        xa, ra, _ = cg_cases.run(ref.lib().ref_minlbfgs, x0.ravel(), fg, lbfgs_m=5, **kw)
+        xd, rd = e.lbfgs_minimize(x0, corrections=5, **kw)
+    print("device L-BFGS: rel L2 vs ALGLIB %.3e; iterations %d / %d, termination %d / %d"
+          % (rel_l2(xd.ravel(), xa), rd["iterations"], ra[0], rd["termination_type"], ra[2]))
+    assert rel_l2(xd.ravel(), xa) <= CG_REL_L2
+    assert rd["iterations"] == int(ra[0]) and rd["termination_type"] == int(ra[2])
+
+
 def test_device_irls_solve_matches_reference_loop(srb, oracle, ref):
     """IRLSMapSolver::Solve: the reference's loop + ALGLIB with the device objective (ref_solve_fused)
     against the fully device-resident solve, tie-free image, 2 IRLS rounds of 25 CG iterations."""

@@ -21,4 +21,13 @@ for name, fg, x0, kw in cg_cases.cases():
     out[name + "_report"] = rep[:4]      # iterations, nfev, termination type, final f
     out[name + "_trace"] = trace
     print("%-24s iterations %4d nfev %4d termination %2d f %.17g" % (name, rep[0], rep[1], rep[2], rep[3]))
+# the same objectives through ALGLIB's minlbfgs (RunLBFGSSolverAnalyticalDiff: m = 5 by default)
+for name, fg, x0, kw in cg_cases.cases():
+    for m in ((5, 3) if name.startswith("rosenbrock10") else (5,)):
+        x, rep, trace = cg_cases.run(sr_ref.lib().ref_minlbfgs, x0, fg, lbfgs_m=m, **kw)
+        key = "lbfgs%d_%s" % (m, name)
+        out[key + "_x"] = x
+        out[key + "_report"] = rep[:4]
+        out[key + "_trace"] = trace
+        print("%-32s iterations %4d nfev %4d termination %2d f %.17g" % (key, rep[0], rep[1], rep[2], rep[3]))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cg_golden.npz"), **out)
