@@ -66,28 +66,46 @@ class NanAfter:
         return f, g
 
 
-def _sr_objective():
-    """The MAP objective itself (oracle): 32 x 40 HR, 2x, 3x3 PSF, 4 frames, TV."""
-    from oracle import sr_oracle as o
-    rng = np.random.default_rng(7)
-    s, h, w = 2, 16, 20
-    psf = o.gaussian_psf(3, 0.8)
-    shifts = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=np.float64)
-    m = o.Model(s, psf, shifts)
-    truth = rng.random((h * s, w * s))
-    lr = np.stack([o.forward(m, k, truth) for k in range(4)])[:, None] + 0.01 * rng.standard_normal((4, 1, h, w))
-    obs = o.upsample_observations(m, lr)
+class _SrObjective:
+    """The MAP objective itself (oracle): 32 x 40 HR, 2x, 3x3 PSF, 4 frames, TV.  Built on first use so
+    that importing this module never touches the oracle library."""
+    S, H_LR, W_LR = 2, 16, 20
 
-    def fg(x):
-        f, g = o.evaluate(m, x.reshape(1, h * s, w * s), obs, reg_kind=o.REG_TV, lam=0.01)
-        return f, g.ravel()
-    return fg, np.full(h * s * w * s, 0.5)
+    def __init__(self):
+        self._fg = None
+
+    @property
+    def x0(self):
+        return np.full(self.H_LR * self.S * self.W_LR * self.S, 0.5)
+
+    def _build(self):
+        from oracle import sr_oracle as o
+        rng = np.random.default_rng(7)
+        s, h, w = self.S, self.H_LR, self.W_LR
+        psf = o.gaussian_psf(3, 0.8)
+        shifts = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=np.float64)
+        m = o.Model(s, psf, shifts)
+        truth = rng.random((h * s, w * s))
+        lr = np.stack([o.forward(m, k, truth) for k in range(4)])[:, None] + 0.01 * rng.standard_normal((4, 1, h, w))
+        obs = o.upsample_observations(m, lr)
+
+        def fg(x):
+            f, g = o.evaluate(m, x.reshape(1, h * s, w * s), obs, reg_kind=o.REG_TV, lam=0.01)
+            return f, g.ravel()
+        self._keep = (m, obs)
+        return fg
+
+    def __call__(self, x):
+        if self._fg is None:
+            self._fg = self._build()
+        return self._fg(x)
 
 
 def cases():
     rng = np.random.default_rng(1)
     quad = _quadratic()
-    sr, sr_x0 = _sr_objective()
+    sr = _SrObjective()
+    sr_x0 = sr.x0
     return [
         ("rosenbrock10_epsg", rosenbrock, rng.standard_normal(10), dict(epsg=1e-10, maxits=500)),
         ("rosenbrock100_epsf", rosenbrock, -1.2 * np.ones(100), dict(epsf=1e-12, maxits=300)),
