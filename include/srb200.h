@@ -83,6 +83,9 @@ typedef struct {
   int band_lo_r, band_hi_r, band_lo_c, band_hi_c;
   int table_driven;          /* interior tiles use the precomputed residual table: frames per
                                 sub-pixel phase it is specialised for (1, 2 or 4), 0 = generic pass */
+  int zlayout;               /* Z layout (k_tile_z): 1 = qualifies (integer shifts, 3x3 .. 9x9 PSF, one
+                                frame on every sub-pixel phase; the default kernel then), 2 = qualifies with
+                                empty phases (frame shards; opt-in SRB_ZLAYOUT=2), 0 = no */
   char why[160];             /* reason when fused == 0, or the validation error */
 } srb_plan_info;
 srb_status srb_plan(const srb_model_desc* desc, srb_plan_info* out);

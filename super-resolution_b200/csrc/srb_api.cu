@@ -280,6 +280,7 @@ srb_status srb_plan(const srb_model_desc* d, srb_plan_info* out) {
   out->band_lo_r = plan.band.lo_r; out->band_hi_r = plan.band.hi_r;
   out->band_lo_c = plan.band.lo_c; out->band_hi_c = plan.band.hi_c;
   out->table_driven = plan.fast[0].empty() ? 0 : plan.fast_E;
+  out->zlayout = plan.zlayout;
   return SRB_OK;
 }
 

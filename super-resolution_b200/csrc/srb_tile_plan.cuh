@@ -35,6 +35,9 @@ struct TilePlan {
   std::vector<TFast> fast[2];    // table-driven residual pass, tile height 32 / 64 (empty: not applicable)
   std::vector<long long> fast_y[2];  // observation offsets of entries 1 .. fast_E-1, [e-1][items]
   int fast_E = 0;                // entries per sub-pixel phase in the table-driven pass (1, 2 or 4)
+  // Z layout (k_tile_z): 0 the model does not qualify; 1 integer shifts, PSF 3x3 .. 9x9 and exactly one
+  // frame on every sub-pixel phase; 2 the same with some phases empty (a frame shard; HOLES variant)
+  int zlayout = 0;
 };
 
 struct TileState {
@@ -263,6 +266,16 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
     }
   }
 
+  // ---- Z layout: every HR pixel receives at most one regular sample -----------------------------
+  if (!st->frac && hk >= 1 && hk <= 4 && !flat.empty()) {
+    bool at_most_one = true, all_one = true;
+    for (size_t ph = 0; ph < lists.size(); ++ph) {
+      at_most_one = at_most_one && lists[ph].size() <= 1;
+      all_one = all_one && lists[ph].size() == 1;
+    }
+    st->zlayout = (all_one && !st->fast[0].empty()) ? 1 : (at_most_one && !all_one) ? 2 : 0;
+  }
+
   st->supported = true;
 }
 
@@ -325,16 +338,11 @@ inline srb_status fused_setup(srb_ctx* c) {
   {
     const char* e = getenv("SRB_ZLAYOUT");
     const int mode = e == nullptr ? 1 : atoi(e);
-    bool one_per_phase = plan.fast_E == 1 && !plan.fast[0].empty();
-    bool at_most_one = !plan.entries.empty();
-    for (size_t ph = 0; ph + 1 < plan.phase_begin.size(); ++ph)
-      at_most_one = at_most_one && plan.phase_begin[ph + 1] - plan.phase_begin[ph] <= 1;
-    const bool holes = mode >= 2 && !one_per_phase && at_most_one;
-    if (mode != 0 && !plan.frac && (one_per_phase || holes) && plan.KH >= 1 && plan.KH <= 4 && st->tma_ok &&
-        st->tile_h == 32) {
+    const bool take = plan.zlayout == 1 ? mode != 0 : plan.zlayout == 2 ? mode >= 2 : false;
+    if (take && st->tma_ok && st->tile_h == 32) {
       if (cudaMalloc((void**)&st->d_yz, (size_t)G.Ct * G.H * G.W * sizeof(double)) != cudaSuccess)
         return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in Z layout)");
-      st->yz_holes = holes;
+      st->yz_holes = plan.zlayout == 2;
     }
   }
   st->supported = true;

@@ -24,11 +24,12 @@ def test_warp_quantisation_matches_the_oracle(oracle):
 
 
 def test_plans_of_the_baseline_configurations():
-    expect = {1: dict(frac=0, kh=1, per_phase=(1, 1), table=1),
-              2: dict(frac=0, kh=2, per_phase=(0, 1), table=0),     # 9 frames over 16 phases
-              3: dict(frac=0, kh=3, per_phase=(1, 1), table=1),
-              4: dict(frac=0, kh=2, per_phase=(2, 2), table=2),     # 8 frames over 4 phases
-              5: dict(frac=0, kh=4, per_phase=(4, 4), table=4)}     # 64 frames over 16 phases
+    # z: Z layout (k_tile_z) -- 1 one frame on every phase, 2 at most one (opt-in), 0 does not qualify
+    expect = {1: dict(frac=0, kh=1, per_phase=(1, 1), table=1, z=1),
+              2: dict(frac=0, kh=2, per_phase=(0, 1), table=0, z=2),     # 9 frames over 16 phases
+              3: dict(frac=0, kh=3, per_phase=(1, 1), table=1, z=1),
+              4: dict(frac=0, kh=2, per_phase=(2, 2), table=2, z=0),     # 8 frames over 4 phases
+              5: dict(frac=0, kh=4, per_phase=(4, 4), table=4, z=0)}     # 64 frames over 16 phases
     for cfg, ex in expect.items():
         cf = wl.CONFIGS[cfg]
         s = cf["s"]
@@ -39,6 +40,7 @@ def test_plans_of_the_baseline_configurations():
         assert p["fractional"] == ex["frac"] and p["psf_half"] == ex["kh"]
         assert (p["min_entries_per_phase"], p["max_entries_per_phase"]) == ex["per_phase"], (cfg, p)
         assert p["table_driven"] == ex["table"]      # frames per phase of the table-driven residual pass (0: generic)
+        assert p["zlayout"] == ex["z"], (cfg, p)
         assert p["num_entries"] == cf["N"]
         # default shifts are >= 0 and at most s - 1: at most a thin band at the top / left
         assert p["band_hi_r"] >= cf["H"] // s - 2 and p["band_hi_c"] >= cf["W"] // s - 2
@@ -119,3 +121,24 @@ def test_solver_options_mirror_the_reference_defaults_and_scaling():
     assert up.parameter_variation_threshold == 1e-6 * (2352 * 0.01)
     assert up.irls_cost_difference_threshold == 1e-5 * (2352 * 0.01)
     assert (up.max_num_solver_iterations, up.max_num_irls_iterations) == (50, 20)
+
+
+def test_zlayout_qualification_of_frame_shards_and_other_models():
+    """cfg3's model split over 2 / 4 / 8 ranks (sharding.frame_shard): every shard has at most one frame
+    per phase -> Z layout with holes; fractional shifts, no PSF and PSFs wider than 9x9 do not qualify."""
+    from importlib import import_module
+    sharding = import_module("super-resolution_b200.sharding")
+    cf = wl.CONFIGS[3]
+    s = cf["s"]
+    shifts = wl.default_shifts(cf["N"], s)
+    psf = wl.gaussian_psf(cf["K"], cf["sigma"])
+    for world in (2, 4, 8):
+        for rank in range(world):
+            fr = sharding.frame_shard(cf["N"], rank, world)
+            p = srb.plan((len(fr), cf["C"], cf["H"] // s, cf["W"] // s), s, psf, shifts[fr])
+            assert p["fused"] == 1 and p["zlayout"] == 2 and p["table_driven"] == 0, (world, rank, p)
+    frac = shifts.copy()
+    frac[3, 0] += 0.5
+    assert srb.plan((16, 1, 64, 64), s, psf, frac)["zlayout"] == 0
+    assert srb.plan((16, 1, 64, 64), s, None, shifts)["zlayout"] == 0          # no PSF: nothing to gain
+    assert srb.plan((4, 1, 64, 64), 2, wl.gaussian_psf(3, 0.8), wl.default_shifts(4, 2))["zlayout"] == 1
