@@ -229,7 +229,9 @@ def evaluate(model, x, obs_hr, reg_kind=REG_TV, lam=0.0, weights=None, want_grad
     x, obs_hr = _f64(x), _f64(obs_hr)
     Cn, H, W = x.shape
     grad = np.empty_like(x) if want_grad else None
-    w = None if weights is None else _f64(weights)
+    # IRLS weights start at 1 (irls_map_solver.cpp:66-74): a regularizer without explicit weights
+    # means the first IRLS round, not "no regularizer"
+    w = (np.ones_like(x) if lam > 0.0 else None) if weights is None else _f64(weights)
     cost = lib().sro_eval(model.c, _p(x), H, W, Cn, _p(obs_hr), reg_kind, btv_range, btv_decay,
                           lam, _p(w), _p(grad), threads)
     return cost, grad

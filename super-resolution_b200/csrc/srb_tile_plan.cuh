@@ -332,12 +332,11 @@ inline srb_status fused_setup(srb_ctx* c) {
   }
   if (const char* e = getenv("SRB_TILE_H")) st->tile_h = atoi(e) == 64 ? 64 : 32;
   // Z layout (k_tile_z): integer shifts, one frame per sub-pixel phase, PSF of 3x3 .. 9x9, TMA.
-  // SRB_ZLAYOUT=0 keeps k_tile everywhere (A/B).
-  // SRB_ZLAYOUT=2 (opt-in, not yet run on a GPU) also takes models where some phases have no frame at
-  // all -- the frame shards of a multi-GPU run.
+  // Models where some phases have no frame at all -- the frame shards of a multi-GPU run -- take the
+  // HOLES variant (NaN in yz).  SRB_ZLAYOUT=0 keeps k_tile everywhere, 1 only the all-phases form (A/B).
   {
     const char* e = getenv("SRB_ZLAYOUT");
-    const int mode = e == nullptr ? 1 : atoi(e);
+    const int mode = e == nullptr ? 2 : atoi(e);
     const bool take = plan.zlayout == 1 ? mode != 0 : plan.zlayout == 2 ? mode >= 2 : false;
     if (take && st->tma_ok && st->tile_h == 32) {
       if (cudaMalloc((void**)&st->d_yz, (size_t)G.Ct * G.H * G.W * sizeof(double)) != cudaSuccess)

@@ -90,7 +90,8 @@ class _SrObjective:
         obs = o.upsample_observations(m, lr)
 
         def fg(x):
-            f, g = o.evaluate(m, x.reshape(1, h * s, w * s), obs, reg_kind=o.REG_TV, lam=0.01)
+            f, g = o.evaluate(m, x.reshape(1, h * s, w * s), obs, reg_kind=o.REG_TV, lam=0.01,
+                              weights=np.ones((1, h * s, w * s)))
             return f, g.ravel()
         self._keep = (m, obs)
         return fg

@@ -116,8 +116,6 @@ def test_zlayout_declines_models_it_does_not_cover(srb):
         assert not e.zlayout_active
 
 
-@pytest.mark.skipif(os.environ.get("SRB_RUN_PENDING") != "1",
-                    reason="k_tile_z<.., HOLES> (SRB_ZLAYOUT=2) not yet run on a GPU (set SRB_RUN_PENDING=1)")
 @pytest.mark.parametrize("frames", [[0, 1, 2, 3, 4, 5, 6, 7], [8, 9, 10, 11], [3, 12]])
 def test_zlayout_with_empty_phases_matches_oracle(srb, oracle, frames):
     """A frame shard of cfg3's model (some sub-pixel phases carry no frame): SRB_ZLAYOUT=2 keeps the Z
@@ -127,7 +125,7 @@ def test_zlayout_with_empty_phases_matches_oracle(srb, oracle, frames):
     shifts, lr = shifts[frames], np.ascontiguousarray(lr[frames])
     m = oracle.Model(s, psf, shifts)
     obs_hr = oracle.upsample_observations(m, lr)
-    cost_ref, g_ref = oracle.evaluate(m, x, obs_hr, reg_kind=oracle.REG_TV, lam=0.01)
+    cost_ref, g_ref = oracle.evaluate(m, x, obs_hr, reg_kind=oracle.REG_TV, lam=0.01, weights=np.ones_like(x))
     old = os.environ.get("SRB_ZLAYOUT")
     os.environ["SRB_ZLAYOUT"] = "2"
     try:
