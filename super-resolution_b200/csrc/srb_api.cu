@@ -621,7 +621,7 @@ srb_status srb_set_path(srb_ctx* c, int path) {
 int srb_active_path(const srb_ctx* c) { return c ? resolve_path(c) : -1; }
 int srb_zlayout_active(const srb_ctx* c) {
   const TileState* st = c ? tile_state(c) : nullptr;
-  return (st && st->supported && st->d_yz && st->yz_valid) ? 1 : 0;
+  return (st && st->supported && (st->d_yz || st->d_yzt) && st->yz_valid) ? 1 : 0;
 }
 
 srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {

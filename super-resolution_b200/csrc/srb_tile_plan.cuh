@@ -13,6 +13,7 @@
 #include "srb_common.cuh"
 #include "srb_kernels_band.cuh"
 #include "srb_kernels_tile.cuh"
+#include "srb_kernels_tilez.cuh"
 
 namespace srb {
 
@@ -38,6 +39,8 @@ struct TilePlan {
   // Z layout (k_tile_z): 0 the model does not qualify; 1 integer shifts, PSF 3x3 .. 9x9 and exactly one
   // frame on every sub-pixel phase; 2 the same with some phases empty (a frame shard; HOLES variant)
   int zlayout = 0;
+  // transposed Z layout (k_tile_zt): integer shifts, PSF 3x3 .. 9x9, at most one frame per sub-pixel phase
+  bool zt = false;
 };
 
 struct TileState {
@@ -59,6 +62,8 @@ struct TileState {
   double* d_yz = nullptr;  // observations on the HR grid [Ct][H][W] (k_tile_z; SRB_ZLAYOUT=1), else NULL
   bool yz_valid = false;   // d_yz matches the observations currently in d_y
   bool yz_holes = false;   // some sub-pixel phases have no frame (NaN in d_yz; k_tile_z<.., true>)
+  double* d_yzt = nullptr; // observations in the transposed, padded Z layout [Ct][cols_p][rows_p] (k_tile_zt)
+  int yzt_rows = 0, yzt_cols = 0;
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -83,6 +88,7 @@ inline void fused_teardown(srb_ctx* c) {
   for (long long* f : st->d_fast_y)
     if (f) cudaFree(f);
   if (st->d_yz) cudaFree(st->d_yz);
+  if (st->d_yzt) cudaFree(st->d_yzt);
   delete st;
   st = nullptr;
 }
@@ -274,6 +280,7 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
       all_one = all_one && lists[ph].size() == 1;
     }
     st->zlayout = (all_one && !st->fast[0].empty()) ? 1 : (at_most_one && !all_one) ? 2 : 0;
+    st->zt = at_most_one;
   }
 
   st->supported = true;
@@ -338,7 +345,15 @@ inline srb_status fused_setup(srb_ctx* c) {
     const char* e = getenv("SRB_ZLAYOUT");
     const int mode = e == nullptr ? 2 : atoi(e);
     const bool take = plan.zlayout == 1 ? mode != 0 : plan.zlayout == 2 ? mode >= 2 : false;
-    if (take && st->tma_ok && st->tile_h == 32) {
+    // SRB_ZT=0 keeps the round-1 row-major Z layout (k_tile_z) for A/B runs; default: k_tile_zt
+    const char* zt_env = getenv("SRB_ZT");
+    const bool use_zt = plan.zt && mode != 0 && (zt_env == nullptr || atoi(zt_env) != 0) && st->tma_ok && st->tile_h == 32;
+    if (use_zt) {
+      st->yzt_rows = zt_rows_padded(G.H, plan.KH);
+      st->yzt_cols = zt_cols_padded(G.W, plan.KH);
+      if (cudaMalloc((void**)&st->d_yzt, (size_t)G.Ct * st->yzt_rows * st->yzt_cols * sizeof(double)) != cudaSuccess)
+        return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in transposed Z layout)");
+    } else if (take && st->tma_ok && st->tile_h == 32) {
       if (cudaMalloc((void**)&st->d_yz, (size_t)G.Ct * G.H * G.W * sizeof(double)) != cudaSuccess)
         return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in Z layout)");
       st->yz_holes = plan.zlayout == 2;
@@ -351,8 +366,20 @@ inline srb_status fused_setup(srb_ctx* c) {
 // After new observations were stored in c->d_y (stream-ordered): refresh their Z-layout copy.
 inline srb_status fused_observations_changed(srb_ctx* c) {
   TileState* st = tile_state(c);
-  if (!st || !st->supported || !st->d_yz) return SRB_OK;
+  if (!st || !st->supported) return SRB_OK;
   const Geometry& G = c->g;
+  if (st->d_yzt) {
+    const int KH = st->KH;
+    const dim3 grid((unsigned)((st->yzt_rows + 255) / 256), (unsigned)st->yzt_cols, (unsigned)G.Ct);
+    k_build_yzt<<<grid, 256, 0, c->stream>>>(G.h, G.w, G.s, st->yzt_rows, st->yzt_cols, (KH + 1) & ~1, KH,
+                                             st->band.lo_r, st->band.hi_r, st->band.lo_c, st->band.hi_c,
+                                             st->d_entries, st->d_phase_begin, c->d_y, st->d_yzt);
+    c->timing.kernel_launches += 1;
+    SRB_CUDA_CHECK(c, cudaGetLastError());
+    st->yz_valid = true;
+    return SRB_OK;
+  }
+  if (!st->d_yz) return SRB_OK;
   const dim3 grid((unsigned)((G.W + 255) / 256), (unsigned)G.H, (unsigned)G.Ct);
   k_build_yz<<<grid, 256, 0, c->stream>>>(G.H, G.W, G.h, G.w, G.s, st->d_entries, st->d_phase_begin, c->d_y, st->d_yz);
   c->timing.kernel_launches += 1;
@@ -436,6 +463,34 @@ inline srb_status tile_launch_z(srb_ctx* c, TileParams& P, int unit_end) {
   return SRB_OK;
 }
 
+// k_tile_zt launch (transposed Z layout); SRB_ERR_STATE without launching when a tensor map cannot be made.
+template <int KH>
+inline srb_status tile_launch_zt(srb_ctx* c, TileParams& P, int unit_end) {
+  using Z = ZtDims<KH>;
+  using D = typename Z::D;
+  const dim3 grid((P.W + FT_W - 1) / FT_W, unit_end - P.unit_begin, 1);
+  const TileState* st = tile_state(c);
+  CUtensorMap mx, mw, my;
+  memset(&mx, 0, sizeof mx);
+  memset(&mw, 0, sizeof mw);
+  memset(&my, 0, sizeof my);
+  bool ok = make_plane_map(st, &mx, P.x, P.W, P.H, P.Ca, D::XW, D::XH);
+  if (ok && P.reg_fused) ok = make_plane_map(st, &mw, P.wts, P.W, P.H, P.Ca, D::WW, D::WH);
+  // [planes][cols_p][rows_p]: the inner (contiguous) dimension is the HR row
+  if (ok) ok = make_plane_map(st, &my, st->d_yzt, st->yzt_rows, st->yzt_cols, P.Ct, Z::YR, Z::YC);
+  if (!ok) return SRB_ERR_STATE;
+  P.use_tma = 1;
+  static bool attr_set[64] = {};
+  if (c->device >= 64 || !attr_set[c->device]) {
+    SRB_CUDA_CHECK(c, cudaFuncSetAttribute(k_tile_zt<KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Z::SMEM_BYTES));
+    if (c->device < 64) attr_set[c->device] = true;
+  }
+  if (c->profiling) cudaEventRecord(c->ev[4], c->stream);
+  k_tile_zt<KH><<<grid, Z::NT, Z::SMEM_BYTES, c->stream>>>(P, mx, mw, my);
+  if (c->profiling) cudaEventRecord(c->ev[5], c->stream);
+  return SRB_OK;
+}
+
 // Tile height the current model runs with, and the number of (channel, tile row) units.
 inline int tile_height(const srb_ctx* c) {
   const TileState* st = tile_state(c);
@@ -512,7 +567,22 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   // frames per sub-pixel phase the table-driven residual pass is specialised for (1, 2 or 4)
   const int fe = (!st->frac && P.fast != nullptr && (P.fast_E == 2 || P.fast_E == 4)) ? P.fast_E : 1;
   if (P.fast_E != fe) P.fast = nullptr;  // a kernel only ever sees the table it is specialised for
-  if (P.yz != nullptr && TH == 32 && fe == 1 && !st->frac) {  // Z layout (opt-in)
+  if (st->d_yzt != nullptr && st->yz_valid && TH == 32) {  // transposed Z layout: every tile, one code path
+    srb_status zr = SRB_ERR_STATE;
+    switch (st->KH) {
+      case 1: zr = tile_launch_zt<1>(c, P, unit_end); break;
+      case 2: zr = tile_launch_zt<2>(c, P, unit_end); break;
+      case 3: zr = tile_launch_zt<3>(c, P, unit_end); break;
+      case 4: zr = tile_launch_zt<4>(c, P, unit_end); break;
+      default: break;
+    }
+    if (zr == SRB_OK) {
+      c->timing.kernel_launches += 1;
+      return SRB_OK;
+    }
+    if (zr != SRB_ERR_STATE) return zr;
+  }
+  if (P.yz != nullptr && TH == 32 && fe == 1 && !st->frac) {  // row-major Z layout (SRB_ZT=0)
     srb_status zr = SRB_ERR_STATE;
     switch (st->KH * 2 + (st->yz_holes ? 1 : 0)) {
       case 2: zr = tile_launch_z<1, false>(c, P, unit_end); break;
