@@ -377,6 +377,8 @@ void srb_destroy(srb_ctx* c) {
   dev_free(&c->d_y); dev_free(&c->d_decay); dev_free(&c->d_w); dev_free(&c->d_x); dev_free(&c->d_grad);
   dev_free(&c->d_pooled); dev_free(&c->d_vals); dev_free(&c->d_aux); dev_free(&c->d_partial);
   dev_free(&c->d_cost);
+  dev_free(&c->cg_store);
+  if (c->cg_h_out) cudaFreeHost(c->cg_h_out);
   dev_free(&c->peer.d_err);
   for (auto& st : c->peer.s_copy)
     if (st) cudaStreamDestroy(st);

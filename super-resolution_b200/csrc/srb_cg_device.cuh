@@ -36,6 +36,27 @@ __device__ __forceinline__ void cg_block_store3(double a, double b, double c, do
   }
 }
 
+// <g, d> of the trial point and the three beta sums of the direction update in one pass over g (trial
+// gradient), g0 (gradient at the start of the line search) and dk (the un-normalised direction; the unit
+// direction is d = (dk * s1) * s2, rounded as linminnormalized rounds it): with y = g - g0
+//   part[0] <g, d>   part[1] <y, dk>   part[2] <g, g>   part[3] <g, y>
+__global__ void __launch_bounds__(CG_NT)
+k_cg_trial_sums(const double* __restrict__ g, const double* __restrict__ g0, const double* __restrict__ dk,
+                double s1, double s2, long long n, double* __restrict__ part) {
+  double s0 = 0.0, sy = 0.0, sg = 0.0, sgy = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    const double gi = g[i], di = dk[i];
+    const double y = gi - g0[i];
+    s0 = fma(gi, __dmul_rn(__dmul_rn(di, s1), s2), s0);
+    sy = fma(y, di, sy);
+    sg = fma(gi, gi, sg);
+    sgy = fma(gi, y, sgy);
+  }
+  cg_block_store3(s0, sy, sg, part, gridDim.x);
+  __syncthreads();
+  cg_block_store3(sgy, 0.0, 0.0, part + 3 * gridDim.x, gridDim.x);
+}
+
 // MODE 0: <a, b>   1: sum a^2   2: sum (a - b)^2   3: y = a - b: <y, c>, <a, a>, <a, y>
 template <int MODE>
 __global__ void __launch_bounds__(CG_NT)
@@ -70,18 +91,25 @@ __device__ __forceinline__ void cg_block_store_max(double m, double* slot) {
   }
 }
 
-// dk = -g + beta * dk (rounded like ALGLIB's two statements: product, then sum); sum g^2; max |dk|
+// dk = -g + beta * dk (rounded like ALGLIB's two statements: product, then sum); sum g^2; max |dk|; and
+// for the normalisation that follows (linminnormalized) without another pass: sum dk^2 and <g, dk>
+//   part[0] sum g^2   part[1] max |dk|   part[2] sum dk^2   part[3] <g, dk>
 __global__ void __launch_bounds__(CG_NT)
 k_cg_direction(double* dk, const double* __restrict__ g, double beta, long long n, double* __restrict__ part) {
-  double s0 = 0.0, m = 0.0;
+  double s0 = 0.0, m = 0.0, sd = 0.0, sgd = 0.0;
   for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
     const double gi = g[i];
     const double v = __dadd_rn(-gi, __dmul_rn(beta, dk[i]));
     dk[i] = v;
     s0 = fma(gi, gi, s0);
     m = fmax(m, fabs(v));
+    sd = fma(v, v, sd);
+    sgd = fma(gi, v, sgd);
   }
-  cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
+  cg_block_store3(s0, 0.0, sd, part, gridDim.x);
+  __syncthreads();
+  cg_block_store3(sgd, 0.0, 0.0, part + 3 * gridDim.x, gridDim.x);
+  __syncthreads();
   cg_block_store_max(m, part + gridDim.x);  // slot 1 <- max (overwrites the zero sum written above)
 }
 
@@ -133,6 +161,31 @@ k_cg_step(double* __restrict__ x, const double* __restrict__ x0, double stp, con
   cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
 }
 
+// trial point with the unit direction formed on the fly: x = x0 + stp * ((dk * s1) * s2)
+__global__ void __launch_bounds__(CG_NT)
+k_cg_step_scaled(double* __restrict__ x, const double* __restrict__ x0, double stp, const double* __restrict__ dk,
+                 double s1, double s2, long long n, double* __restrict__ part) {
+  double s0 = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT) {
+    const double b = x0[i];
+    const double v = __dadd_rn(b, __dmul_rn(stp, __dmul_rn(__dmul_rn(dk[i], s1), s2)));
+    x[i] = v;
+    const double t = b - v;
+    s0 = fma(t, t, s0);
+  }
+  cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
+}
+
+// <a, (dk * s1) * s2>
+__global__ void __launch_bounds__(CG_NT)
+k_cg_dot_scaled(const double* __restrict__ a, const double* __restrict__ dk, double s1, double s2, long long n,
+                double* __restrict__ part) {
+  double s0 = 0.0;
+  for (long long i = (long long)blockIdx.x * CG_NT + threadIdx.x; i < n; i += (long long)gridDim.x * CG_NT)
+    s0 = fma(a[i], __dmul_rn(__dmul_rn(dk[i], s1), s2), s0);
+  cg_block_store3(s0, 0.0, 0.0, part, gridDim.x);
+}
+
 // out[k] = sum (or max, where bit k of max_mask is set) of part[k * nblk + 0 .. nblk), fixed order
 __global__ void __launch_bounds__(CG_NT)
 k_cg_finish(const double* __restrict__ part, int nblk, int nsums, int max_mask, double* __restrict__ out) {
@@ -177,12 +230,24 @@ struct DeviceCgBackend {
   using Vec = double*;
   srb_ctx* c;
   long long n;
-  double* d_part;   // [3 * CG_MAX_BLOCKS]
-  double* d_out;    // [4]: three reduction results + the objective value
+  double* d_part;   // [6 * CG_MAX_BLOCKS]
+  double* d_out;    // [8]: 0..3 reduction results, 4 = |x - x0|^2 of the trial step, 5 = objective value
   double* h_out;    // pinned mirror
   int nblk;
   srb_status status = SRB_OK;
   long long evals = 0;
+
+  // The unit search direction d = (dk * s1) * s2 of linminnormalized is never stored: normalize_to()
+  // records (d, dk, s1, s2) and trial() / dot() form it on the fly from dk -- same rounding, one vector
+  // write and one read less per line-search step.
+  Vec unit_d = nullptr, unit_src = nullptr, unit_g0 = nullptr;
+  double unit_s1 = 1.0, unit_s2 = 1.0;
+  // sums that direction() produced for the normalisation that follows it
+  Vec dir_dk = nullptr, dir_g = nullptr;
+  double dir_sumsq = 0.0, dir_gdk = 0.0;
+  // beta sums that the last trial() produced (valid for trial_g against unit_g0 / unit_src)
+  Vec trial_g = nullptr;
+  double trial_dy = 0.0, trial_gg = 0.0, trial_gy = 0.0;
 
   long long size() const { return n; }
   bool ok() const { return status == SRB_OK; }
@@ -192,35 +257,54 @@ struct DeviceCgBackend {
   }
   // results of the reductions queued so far -> host (one copy, one synchronisation)
   void fetch() {
-    check(cudaMemcpyAsync(h_out, d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream), "cg fetch");
+    check(cudaMemcpyAsync(h_out, d_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream), "cg fetch");
     check(cudaStreamSynchronize(c->stream), "cg synchronize");
-    if (!ok()) h_out[0] = h_out[1] = h_out[2] = h_out[3] = NAN;
+    if (!ok())
+      for (int i = 0; i < 8; ++i) h_out[i] = NAN;
   }
   // partial sums of the kernel just launched -> d_out[offset .. offset + nsums)
   void finish(int nsums, int max_mask = 0, int offset = 0) {
     k_cg_finish<<<1, CG_NT, 0, c->stream>>>(d_part, nblk, nsums, max_mask, d_out + offset);
     c->timing.kernel_launches += 2;
   }
+  void forget(Vec v) {  // v is about to be overwritten: drop what was cached about it
+    if (v == unit_d || v == unit_src) unit_d = unit_src = nullptr;
+    if (v == dir_dk || v == dir_g) dir_dk = dir_g = nullptr;
+    if (v == trial_g) trial_g = nullptr;
+    if (v == unit_g0) trial_g = unit_g0 = nullptr;
+  }
 
   void eval(Vec x, Vec g, double* f) {
+    forget(g);
     if (ok()) {
-      const srb_status st = eval_core(c, x, g, d_out + 3, true, true, false);
+      const srb_status st = eval_core(c, x, g, d_out + 5, true, true, false);
       if (st != SRB_OK) status = st;
     }
     ++evals;
     fetch();
-    *f = h_out[3];
+    *f = h_out[5];
   }
   void copy(Vec dst, Vec src) {
+    forget(dst);
     check(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream), "cg copy");
   }
   void neg_copy(Vec dst, Vec src) {
+    forget(dst);
     k_cg_neg_copy<<<nblk, CG_NT, 0, c->stream>>>(dst, src, n);
     c->timing.kernel_launches += 1;
   }
-  void zero(Vec v) { check(cudaMemsetAsync(v, 0, (size_t)n * sizeof(double), c->stream), "cg zero"); }
+  void zero(Vec v) {
+    forget(v);
+    check(cudaMemsetAsync(v, 0, (size_t)n * sizeof(double), c->stream), "cg zero");
+  }
   double dot(Vec a, Vec b) {
-    k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(a, b, nullptr, n, d_part);
+    if (b == unit_d && unit_src) {
+      k_cg_dot_scaled<<<nblk, CG_NT, 0, c->stream>>>(a, unit_src, unit_s1, unit_s2, n, d_part);
+    } else if (a == unit_d && unit_src) {
+      k_cg_dot_scaled<<<nblk, CG_NT, 0, c->stream>>>(b, unit_src, unit_s1, unit_s2, n, d_part);
+    } else {
+      k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(a, b, nullptr, n, d_part);
+    }
     finish(1);
     fetch();
     return h_out[0];
@@ -238,6 +322,7 @@ struct DeviceCgBackend {
     return h_out[0];
   }
   void normalize_to(Vec d, Vec dk, double mx, Vec g0, double* stp, double* slope, double* dd) {
+    forget(d);
     if (mx == 0.0) {  // zero direction: d = dk, slope and length are zero
       copy(d, dk);
       *slope = 0.0;
@@ -245,50 +330,87 @@ struct DeviceCgBackend {
       return;
     }
     const double s1 = 1 / mx;
-    k_cg_scaled_sumsq<<<nblk, CG_NT, 0, c->stream>>>(dk, s1, n, d_part);
-    finish(1);
-    fetch();
-    const double s2 = 1 / std::sqrt(h_out[0]);
-    k_cg_normalize<<<nblk, CG_NT, 0, c->stream>>>(d, dk, s1, s2, g0, n, d_part);
-    finish(2);
-    fetch();
+    double sumsq_scaled, gdk;
+    bool have = dir_dk == dk && dir_g == g0;
+    if (have) {
+      // sums of the un-normalised direction from the pass that built it; scaling them instead of the
+      // elements changes the result by rounding only.  Not when the scaling matters for the range.
+      sumsq_scaled = dir_sumsq * s1 * s1;
+      gdk = dir_gdk;
+      have = std::isfinite(dir_sumsq) && dir_sumsq > 1e-280 && std::isfinite(sumsq_scaled) && sumsq_scaled > 0.0;
+    }
+    if (!have) {
+      k_cg_scaled_sumsq<<<nblk, CG_NT, 0, c->stream>>>(dk, s1, n, d_part);
+      finish(1);
+      k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(g0, dk, nullptr, n, d_part);
+      finish(1, 0, 1);
+      fetch();
+      sumsq_scaled = h_out[0];
+      gdk = h_out[1];
+    }
+    const double s2 = 1 / std::sqrt(sumsq_scaled);
+    unit_d = d; unit_src = dk; unit_g0 = g0; unit_s1 = s1; unit_s2 = s2;
+    trial_g = nullptr;
     *stp = *stp / s1;
     *stp = *stp / s2;
-    *slope = h_out[0];
-    *dd = h_out[1];
+    *slope = gdk * s1 * s2;
+    *dd = sumsq_scaled * s2 * s2;
   }
   void trial(Vec x, Vec x0, double stp, Vec d, Vec g, double* f, double* dg, double* moved) {
-    k_cg_step<<<nblk, CG_NT, 0, c->stream>>>(x, x0, stp, d, n, d_part);
-    finish(1, 0, 2);  // moved -> d_out[2]
+    forget(x);
+    const bool unit = d == unit_d && unit_src != nullptr;
+    if (unit) k_cg_step_scaled<<<nblk, CG_NT, 0, c->stream>>>(x, x0, stp, unit_src, unit_s1, unit_s2, n, d_part);
+    else k_cg_step<<<nblk, CG_NT, 0, c->stream>>>(x, x0, stp, d, n, d_part);
+    finish(1, 0, 4);  // moved -> d_out[4]
+    if (g == trial_g) trial_g = nullptr;
     if (ok()) {
-      const srb_status st = eval_core(c, x, g, d_out + 3, true, true, false);
+      const srb_status st = eval_core(c, x, g, d_out + 5, true, true, false);
       if (st != SRB_OK) status = st;
     }
     ++evals;
-    k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(g, d, nullptr, n, d_part);
-    finish(1);        // <g, d> -> d_out[0]
+    const bool sums = unit && unit_g0 != nullptr && g != unit_g0;  // (L-BFGS searches overwrite g0 itself)
+    if (sums) {
+      k_cg_trial_sums<<<nblk, CG_NT, 0, c->stream>>>(g, unit_g0, unit_src, unit_s1, unit_s2, n, d_part);
+      finish(4);      // <g, d>, <y, dk>, <g, g>, <g, y> -> d_out[0..3]
+    } else if (unit) {
+      k_cg_dot_scaled<<<nblk, CG_NT, 0, c->stream>>>(g, unit_src, unit_s1, unit_s2, n, d_part);
+      finish(1);
+    } else {
+      k_cg_reduce<0><<<nblk, CG_NT, 0, c->stream>>>(g, d, nullptr, n, d_part);
+      finish(1);      // <g, d> -> d_out[0]
+    }
     fetch();
-    *f = h_out[3];
+    *f = h_out[5];
     *dg = h_out[0];
-    *moved = h_out[2];
+    *moved = h_out[4];
+    if (sums) {
+      trial_g = g;
+      trial_dy = h_out[1]; trial_gg = h_out[2]; trial_gy = h_out[3];
+    }
   }
   void beta_terms(Vec gn, Vec go, Vec dk, double* dy, double* gg, double* gy) {
+    if (gn == trial_g && go == unit_g0 && dk == unit_src) {  // the accepted trial already summed them
+      *dy = trial_dy; *gg = trial_gg; *gy = trial_gy;
+      return;
+    }
     k_cg_reduce<3><<<nblk, CG_NT, 0, c->stream>>>(gn, go, dk, n, d_part);
     finish(3);
     fetch();
     *dy = h_out[0]; *gg = h_out[1]; *gy = h_out[2];
   }
   void direction(Vec dk, Vec g, double beta, double* gg, double* mx) {
+    forget(dk);
     k_cg_direction<<<nblk, CG_NT, 0, c->stream>>>(dk, g, beta, n, d_part);
-    finish(2, 2);     // slot 0: sum g^2, slot 1: max |dk|
+    finish(4, 2);     // slot 0: sum g^2, slot 1: max |dk|, slot 2: sum dk^2, slot 3: <g, dk>
     fetch();
     *gg = h_out[0]; *mx = h_out[1];
+    dir_dk = dk; dir_g = g; dir_sumsq = h_out[2]; dir_gdk = h_out[3];
   }
   // L-BFGS only (two-loop recursion, pair updates)
-  void add(Vec dst, Vec src) { k_cg_update<0><<<nblk, CG_NT, 0, c->stream>>>(dst, 0.0, src, n); c->timing.kernel_launches += 1; }
-  void add_scaled(Vec dst, double a, Vec src) { k_cg_update<1><<<nblk, CG_NT, 0, c->stream>>>(dst, a, src, n); c->timing.kernel_launches += 1; }
-  void sub_scaled(Vec dst, double a, Vec src) { k_cg_update<2><<<nblk, CG_NT, 0, c->stream>>>(dst, a, src, n); c->timing.kernel_launches += 1; }
-  void scale(Vec v, double a) { k_cg_update<3><<<nblk, CG_NT, 0, c->stream>>>(v, a, nullptr, n); c->timing.kernel_launches += 1; }
+  void add(Vec dst, Vec src) { forget(dst); k_cg_update<0><<<nblk, CG_NT, 0, c->stream>>>(dst, 0.0, src, n); c->timing.kernel_launches += 1; }
+  void add_scaled(Vec dst, double a, Vec src) { forget(dst); k_cg_update<1><<<nblk, CG_NT, 0, c->stream>>>(dst, a, src, n); c->timing.kernel_launches += 1; }
+  void sub_scaled(Vec dst, double a, Vec src) { forget(dst); k_cg_update<2><<<nblk, CG_NT, 0, c->stream>>>(dst, a, src, n); c->timing.kernel_launches += 1; }
+  void scale(Vec v, double a) { forget(v); k_cg_update<3><<<nblk, CG_NT, 0, c->stream>>>(v, a, nullptr, n); c->timing.kernel_launches += 1; }
   void reweight(Vec x) {  // w = 1 / max(1e-5, reg(x)), irls_map_solver.cpp:128-143 (stream-ordered)
     if (!ok()) return;
     const srb_status st = reweight_dev(c, x);
@@ -296,33 +418,36 @@ struct DeviceCgBackend {
   }
 };
 
-// Scratch vectors, reduction slots and the pinned scalar mirror of one solve.
+// Scratch vectors, reduction slots and the pinned scalar mirror of a solve.  The storage belongs to the
+// context and is kept between solves (cudaMalloc / cudaFree of five 100 MB vectors cost more than twenty
+// CG iterations at cfg3); srb_destroy releases it.
 struct DeviceCgWorkspace {
-  double* store = nullptr;
-  double* h_out = nullptr;
   std::vector<double*> scratch;
-  ~DeviceCgWorkspace() {
-    if (store) cudaFree(store);
-    if (h_out) cudaFreeHost(h_out);
-  }
   srb_status init(srb_ctx* c, DeviceCgBackend* be, int num_vectors = kCgScratchVectors) {
     const long long n = (long long)c->n_active();
-    const size_t doubles = (size_t)num_vectors * n + 3 * CG_MAX_BLOCKS + 4;
-    if (cudaMalloc((void**)&store, doubles * sizeof(double)) != cudaSuccess) {
-      (void)cudaGetLastError();
-      store = nullptr;
-      return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (CG vectors)");
+    const size_t doubles = (size_t)num_vectors * n + 6 * CG_MAX_BLOCKS + 8;
+    if (doubles > c->cg_store_doubles) {
+      if (c->cg_store) cudaFree(c->cg_store);
+      c->cg_store = nullptr;
+      c->cg_store_doubles = 0;
+      if (cudaMalloc((void**)&c->cg_store, doubles * sizeof(double)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->cg_store = nullptr;
+        return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (CG vectors)");
+      }
+      c->cg_store_doubles = doubles;
     }
-    if (cudaMallocHost((void**)&h_out, 4 * sizeof(double)) != cudaSuccess) {
+    if (!c->cg_h_out && cudaMallocHost((void**)&c->cg_h_out, 8 * sizeof(double)) != cudaSuccess) {
       (void)cudaGetLastError();
-      h_out = nullptr;
+      c->cg_h_out = nullptr;
       return c->fail(SRB_ERR_NOMEM, "cudaMallocHost failed (CG scalars)");
     }
+    double* store = c->cg_store;
     be->c = c;
     be->n = n;
     be->d_part = store + (size_t)num_vectors * n;
-    be->d_out = be->d_part + 3 * CG_MAX_BLOCKS;
-    be->h_out = h_out;
+    be->d_out = be->d_part + 6 * CG_MAX_BLOCKS;
+    be->h_out = c->cg_h_out;
     const long long want = (n + CG_NT - 1) / CG_NT;
     be->nblk = (int)std::max(1LL, std::min<long long>(std::min<long long>(want, (long long)c->num_sms * 8), CG_MAX_BLOCKS));
     scratch.resize(num_vectors);

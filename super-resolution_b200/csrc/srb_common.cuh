@@ -90,6 +90,9 @@ struct srb_ctx {
   double* d_aux = nullptr;    // [Ct*P] second scratch plane (constants / partials)
   double* d_partial = nullptr;  // per-block cost partial sums
   size_t partial_capacity = 0;
+  double* cg_store = nullptr;   // solver vectors + reduction slots of the device-resident solver, kept between solves
+  size_t cg_store_doubles = 0;
+  double* cg_h_out = nullptr;   // pinned scalar mirror of the solver
   double* d_cost = nullptr;   // [4] data cost, reg cost, total, spare
   double* h_cost = nullptr;   // pinned mirror of d_cost
 
