@@ -100,6 +100,9 @@ int srb_sample_is_special(int q, int hr_size, int psf_half, int scale, double sh
  * MapSolver::MapSolver (map_solver.cpp:52-86).  Fails with SRB_ERR_GEOMETRY when cv::resize
  * (INTER_NEAREST) would not map LR<->HR block-regularly for this size/scale. */
 srb_status srb_create(const srb_model_desc* desc, int device, srb_ctx** out);
+/* Same for one rank's frame shard of a multi-GPU run: num_frames may be 0 (more devices than frames); such a
+ * context contributes only its row band of the regularization term (srb_set_regularizer_rows). */
+srb_status srb_create_shard(const srb_model_desc* desc, int device, srb_ctx** out);
 void srb_destroy(srb_ctx* ctx);
 const char* srb_last_error(const srb_ctx* ctx);
 
@@ -259,6 +262,33 @@ srb_status srb_peer_scatter_dev(srb_ctx* ctx, const double* x_dev);
 srb_status srb_peer_gather_dev(srb_ctx* ctx);
 srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, unsigned long long bytes);
 
+/* ---- single-process multi-GPU form ------------------------------------------------------------------
+ * The reference's solver is one process and one thread (IRLSMapSolver::Solve, irls_map_solver.cpp:192-265;
+ * AlglibObjectiveFunction, alglib_objective.cpp:142-152): srb_multi_* lets that thread drive up to 8 GPUs
+ * through the same call shape as srb_eval.  desc describes the WHOLE model (all frames); the frames are
+ * sharded in contiguous blocks over the devices (objective_data_term.cpp:104-114 is the loop being split),
+ * x and the IRLS weights are replicated, the regularization term is split by HR row bands.  Per evaluation
+ * device r copies only its 1/G band of x from the host over its own PCIe link, the bands are all-gathered
+ * over NVLink peer memory, every device evaluates its frames band by band while copy engines push finished
+ * bands to their owners (the reduce-scatter), and device r returns its summed band of the gradient to the
+ * host: host traffic per PCIe link is 1/G of srb_eval's.  devices = NULL means devices 0 .. n_gpus-1.  Pin
+ * the host buffers with srb_pin_host.  Results equal srb_eval's up to fp64 re-association of the
+ * cross-device sum (fixed device order: deterministic). */
+typedef struct srb_multi srb_multi;
+srb_status srb_multi_create(const srb_model_desc* desc, int n_gpus, const int* devices, srb_multi** out);
+void srb_multi_destroy(srb_multi* m);
+const char* srb_multi_last_error(const srb_multi* m);
+int srb_multi_num_gpus(const srb_multi* m);
+srb_ctx* srb_multi_rank_ctx(srb_multi* m, int rank);            /* the per-device context (diagnostics) */
+srb_status srb_multi_set_observations(srb_multi* m, const double* lr_host);  /* [num_frames][C][h][w] */
+srb_status srb_multi_set_channel_range(srb_multi* m, int c0, int c1);
+srb_status srb_multi_set_regularizer(srb_multi* m, int kind, double lambda, int btv_range, double btv_decay);
+srb_status srb_multi_set_irls_weights(srb_multi* m, const double* weights_host);
+srb_status srb_multi_reweight(srb_multi* m, const double* x_host, double* weights_out_host);
+srb_status srb_multi_set_path(srb_multi* m, int path);
+/* ObjectiveFunction::ComputeAllTerms (objective_function.cpp:5-20) on all devices; gradient_host may be NULL. */
+srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* gradient_host, double* cost);
+
 /* ObjectiveDataTerm::Compute (objective_data_term.cpp:98-116): returns the data cost and ADDS the
  * data gradient into gradient_host (may be NULL). */
 srb_status srb_data_term(srb_ctx* ctx, const double* x_host, double* gradient_host_accum,
@@ -316,6 +346,9 @@ typedef struct {
   double last_main_kernel_ms;   /* device time of the last fused tile kernel launch (profiling on) */
 } srb_timing;
 srb_status srb_get_timing(srb_ctx* ctx, srb_timing* out);
+/* Summed over the devices of a multi-GPU context; last_eval_kernel_ms = device time of the last srb_multi_eval
+ * (first H2D to last D2H on device 0's clock). */
+srb_status srb_multi_get_timing(srb_multi* m, srb_timing* out);
 
 #ifdef __cplusplus
 }

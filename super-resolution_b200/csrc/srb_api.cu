@@ -166,11 +166,14 @@ void update_timing(srb_ctx* c) {
 // Host part of srb_create, shared with srb_plan: validates the description the way the reference
 // CHECK-fails (map_solver.cpp:52-76, blur_module.cpp:13-18, downsampling_module.cpp:13-17,
 // objective_data_term.cpp:91-95), fills the geometry and quantises the warps.  No CUDA calls.
-srb_status build_host_model(srb_ctx* c, const srb_model_desc* d) {
+srb_status build_host_model(srb_ctx* c, const srb_model_desc* d, bool allow_empty_shard = false) {
   if (!d) return c->fail(SRB_ERR_INVALID, "null model description");
   if (d->lr_height <= 0 || d->lr_width <= 0 || d->num_channels <= 0)
     return c->fail(SRB_ERR_INVALID, "observation size and channel count must be positive");
-  if (d->num_frames <= 0) return c->fail(SRB_ERR_INVALID, "cannot solve with 0 observations");
+  // map_solver.cpp:56-57 refuses an empty observation list; a frame shard of a multi-GPU run may be empty
+  // (more devices than frames): it then contributes only its band of the regularization term
+  if (d->num_frames < 0 || (d->num_frames == 0 && !allow_empty_shard))
+    return c->fail(SRB_ERR_INVALID, "cannot solve with 0 observations");
   if (d->scale < 1) return c->fail(SRB_ERR_INVALID, "downsampling scale must be >= 1");
   if (d->psf_size < 0 || (d->psf_size > 0 && (d->psf_size % 2 == 0 || !d->psf)))
     return c->fail(SRB_ERR_INVALID, "blur kernel size must be odd and the kernel non-null");
@@ -293,14 +296,18 @@ int srb_sample_is_special(int q, int hr_size, int psf_half, int scale, double sh
 
 const char* srb_last_error(const srb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) {
+static srb_status create_ctx(const srb_model_desc* d, int device, bool allow_empty_shard, srb_ctx** out);
+srb_status srb_create(const srb_model_desc* d, int device, srb_ctx** out) { return create_ctx(d, device, false, out); }
+srb_status srb_create_shard(const srb_model_desc* d, int device, srb_ctx** out) { return create_ctx(d, device, true, out); }
+
+static srb_status create_ctx(const srb_model_desc* d, int device, bool allow_empty_shard, srb_ctx** out) {
   if (!out) return SRB_ERR_INVALID;
   *out = nullptr;
   srb_ctx* c = new (std::nothrow) srb_ctx();
   if (!c) return SRB_ERR_NOMEM;
   *out = c;  // returned even on failure so the caller can read srb_last_error, then srb_destroy
   {
-    srb_status hst = build_host_model(c, d);
+    srb_status hst = build_host_model(c, d, allow_empty_shard);
     if (hst != SRB_OK) return hst;
   }
   Geometry& G = c->g;
@@ -405,8 +412,9 @@ srb_status srb_set_observations(srb_ctx* c, const double* lr_host) {
   if (!c) return SRB_ERR_INVALID;
   if (!lr_host) return c->fail(SRB_ERR_INVALID, "null observations");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
-  SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_y, lr_host, (size_t)c->g.N * c->g.Ct * c->p * sizeof(double),
-                                    cudaMemcpyHostToDevice, c->stream));
+  if (c->g.N > 0)
+    SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_y, lr_host, (size_t)c->g.N * c->g.Ct * c->p * sizeof(double),
+                                      cudaMemcpyHostToDevice, c->stream));
   srb_status zst = fused_observations_changed(c);
   if (zst != SRB_OK) return zst;
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -1195,7 +1203,7 @@ srb_status srb_transpose(srb_ctx* c, int frame, const double* lr_host, int h, in
 // ---- plumbing -----------------------------------------------------------------------------------
 srb_status srb_pin_host(void* ptr, unsigned long long bytes) {
   if (!ptr || !bytes) return SRB_ERR_INVALID;
-  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);  // pinned for every device (srb_multi_*)
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     return SRB_ERR_CUDA;
@@ -1236,3 +1244,5 @@ srb_status srb_get_timing(srb_ctx* c, srb_timing* out) {
 }
 
 }  // extern "C"
+
+#include "srb_multi.cuh"  // single-process multi-GPU form (needs everything above)

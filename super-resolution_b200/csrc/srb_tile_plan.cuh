@@ -273,13 +273,13 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
   }
 
   // ---- Z layout: every HR pixel receives at most one regular sample -----------------------------
-  if (!st->frac && hk >= 1 && hk <= 4 && !flat.empty()) {
+  if (!st->frac && hk >= 1 && hk <= 4) {  // (an empty frame shard qualifies too: every position is a hole)
     bool at_most_one = true, all_one = true;
     for (size_t ph = 0; ph < lists.size(); ++ph) {
       at_most_one = at_most_one && lists[ph].size() <= 1;
       all_one = all_one && lists[ph].size() == 1;
     }
-    st->zlayout = (all_one && !st->fast[0].empty()) ? 1 : (at_most_one && !all_one) ? 2 : 0;
+    st->zlayout = flat.empty() ? 0 : (all_one && !st->fast[0].empty()) ? 1 : (at_most_one && !all_one) ? 2 : 0;
     st->zt = at_most_one;
   }
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "srb_quantize_shift": (C.c_int, [C.c_double]),
     "srb_sample_is_special": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "srb_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_ctx_p)]),
+    "srb_create_shard": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(_ctx_p)]),
     "srb_destroy": (None, [_ctx_p]),
     "srb_last_error": (C.c_char_p, [_ctx_p]),
     "srb_set_observations": (C.c_int, [_ctx_p, C.c_void_p]),
@@ -76,6 +77,20 @@ SIGNATURES = {
     "srb_dev_gradient": (C.c_void_p, [_ctx_p]),
     "srb_synchronize": (C.c_int, [_ctx_p]),
     "srb_get_timing": (C.c_int, [_ctx_p, C.c_void_p]),
+    # single-process multi-GPU form
+    "srb_multi_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_ctx_p)]),
+    "srb_multi_destroy": (None, [_ctx_p]),
+    "srb_multi_last_error": (C.c_char_p, [_ctx_p]),
+    "srb_multi_num_gpus": (C.c_int, [_ctx_p]),
+    "srb_multi_rank_ctx": (_ctx_p, [_ctx_p, C.c_int]),
+    "srb_multi_set_observations": (C.c_int, [_ctx_p, C.c_void_p]),
+    "srb_multi_set_channel_range": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
+    "srb_multi_set_regularizer": (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_double]),
+    "srb_multi_set_irls_weights": (C.c_int, [_ctx_p, C.c_void_p]),
+    "srb_multi_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_multi_set_path": (C.c_int, [_ctx_p, C.c_int]),
+    "srb_multi_eval": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
+    "srb_multi_get_timing": (C.c_int, [_ctx_p, C.c_void_p]),
 }
 
 
@@ -438,6 +453,103 @@ class Engine:
     def timing(self):
         t = Timing()
         self._check(self._lib.srb_get_timing(self._ctx, C.byref(t)))
+        return {name: getattr(t, name) for name, _ in Timing._fields_}
+
+
+class MultiEngine:
+    """One srb_multi: the whole model sharded over `n_gpus` devices of this process (frames in contiguous
+    blocks, x and IRLS weights replicated, regularizer split by row bands) behind the call shape of
+    `Engine.eval` -- what the reference's single-threaded solver would hold."""
+
+    def __init__(self, lr_shape, scale, psf=None, shifts=None, n_gpus=1, devices=None, shard_frames=None):
+        self._lib = load_library()
+        self._ctx = _ctx_p()
+        N, Cn, h, w = (int(v) for v in lr_shape)
+        self.N, self.C, self.h, self.w, self.scale = N, Cn, h, w, int(scale)
+        self.H, self.W = h * self.scale, w * self.scale
+        self.c0, self.c1 = 0, Cn
+        self.n_gpus = int(n_gpus)
+        self._psf = None if psf is None else _f64(psf)
+        self._shifts = None if shifts is None else _f64(shifts).reshape(-1, 2)
+        desc = ModelDesc(h, w, Cn, N, self.scale, 0 if self._psf is None else self._psf.shape[0],
+                         None if self._psf is None else self._psf.ctypes.data_as(_dp),
+                         None if self._shifts is None else self._shifts.ctypes.data_as(_dp))
+        dev = None if devices is None else (C.c_int * self.n_gpus)(*[int(d) for d in devices])
+        st = self._lib.srb_multi_create(C.byref(desc), self.n_gpus, dev, C.byref(self._ctx))
+        if st != 0:
+            msg = self._lib.srb_multi_last_error(self._ctx).decode() if self._ctx else "allocation failed"
+            if self._ctx:
+                self._lib.srb_multi_destroy(self._ctx)
+            self._ctx = None
+            raise SrbError(st, msg)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.srb_multi_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st):
+        if st != 0:
+            raise SrbError(st, self._lib.srb_multi_last_error(self._ctx).decode())
+
+    @property
+    def num_active(self):
+        return (self.c1 - self.c0) * self.H * self.W
+
+    def set_observations(self, lr):
+        lr = _f64(lr)
+        assert lr.shape == (self.N, self.C, self.h, self.w), lr.shape
+        self._check(self._lib.srb_multi_set_observations(self._ctx, _host_ptr(lr)))
+
+    def set_channel_range(self, c0, c1):
+        self._check(self._lib.srb_multi_set_channel_range(self._ctx, int(c0), int(c1)))
+        self.c0, self.c1 = int(c0), int(c1)
+
+    def set_regularizer(self, kind, lam, btv_range=3, btv_decay=0.5):
+        self._check(self._lib.srb_multi_set_regularizer(self._ctx, int(kind), float(lam), int(btv_range),
+                                                        float(btv_decay)))
+
+    def set_irls_weights(self, weights):
+        w = None if weights is None else _f64(weights).reshape(-1)
+        if w is not None:
+            assert w.size == self.num_active
+        self._check(self._lib.srb_multi_set_irls_weights(self._ctx, _host_ptr(w)))
+
+    def reweight(self, x, want_weights=True):
+        xa = _f64(x).reshape(-1)
+        out = np.empty(self.num_active) if want_weights else None
+        self._check(self._lib.srb_multi_reweight(self._ctx, _host_ptr(xa), _host_ptr(out)))
+        return None if out is None else out.reshape(self.c1 - self.c0, self.H, self.W)
+
+    def set_path(self, path):
+        self._check(self._lib.srb_multi_set_path(self._ctx, int(path)))
+
+    def eval(self, x, want_grad=True, out=None):
+        """ObjectiveFunction::ComputeAllTerms over all devices, host buffers.  Returns (cost, gradient|None)."""
+        xa = _f64(x).reshape(-1)
+        assert xa.size == self.num_active
+        g = None
+        if want_grad:
+            g = out if out is not None else np.empty(self.num_active)
+        cost = C.c_double()
+        self._check(self._lib.srb_multi_eval(self._ctx, _host_ptr(xa), _host_ptr(g), C.byref(cost)))
+        return cost.value, (None if g is None else g.reshape(self.c1 - self.c0, self.H, self.W))
+
+    def timing(self):
+        t = Timing()
+        self._check(self._lib.srb_multi_get_timing(self._ctx, C.byref(t)))
         return {name: getattr(t, name) for name, _ in Timing._fields_}
 
 

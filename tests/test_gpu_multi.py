@@ -1,0 +1,110 @@
+"""GPU tests of the single-process multi-GPU form (srb_multi_*, include/srb200.h): one host thread drives
+G devices; frames sharded in contiguous blocks (objective_data_term.cpp:104-114 is the loop being split),
+regularizer by row bands, gradient reduce-scattered over NVLink peer memory.  The G-device result must
+equal the oracle's full objective and the single-device evaluation up to fp64 re-association (SURVEY 8e:
+<= 1e-13 relative).  Cases that need more devices than the box has are skipped; G = 1 always runs."""
+from importlib import import_module
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+wl = import_module("super-resolution_b200.workloads")
+REL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def srb():
+    import srb200
+    assert srb200.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return srb200
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def _case(N, s, K, sigma, C, h, w, seed, frac=False):
+    rng = np.random.default_rng(seed)
+    psf = wl.gaussian_psf(K, sigma)
+    shifts = wl.default_shifts(N, s)
+    if frac:
+        shifts = shifts + rng.uniform(-0.4, 0.4, size=shifts.shape)
+    lr = rng.random((N, C, h, w))
+    x = rng.random((C, h * s, w * s))
+    wts = rng.uniform(0.5, 2.0, size=x.shape)
+    return psf, shifts, lr, x, wts
+
+
+CASES = [
+    # N, s, K, sigma, C, h, w, reg, frac
+    (16, 4, 7, 1.5, 2, 48, 80, "tv", False),    # cfg3's model: Z layout with holes on every shard
+    (5, 4, 7, 1.5, 1, 48, 80, "tv", False),     # fewer frames than devices at G = 8: empty shards
+    (9, 4, 5, 1.2, 1, 40, 64, "btv", False),    # cfg2's model: BTV is not fused -> unpipelined exchange
+    (8, 2, 5, 1.0, 3, 40, 64, "tv3d", False),   # cfg4's model: two frames per phase, 3-D TV
+    (6, 2, 3, 0.8, 1, 64, 96, "none", True),    # fractional shifts, no regularizer
+]
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("N,s,K,sigma,C,h,w,reg,frac", CASES)
+def test_multi_eval_matches_oracle_and_single_device(srb, oracle, G, N, s, K, sigma, C, h, w, reg, frac):
+    if srb.device_count() < G:
+        pytest.skip("needs %d GPUs" % G)
+    psf, shifts, lr, x, wts = _case(N, s, K, sigma, C, h, w, seed=100 + N + K, frac=frac)
+    kind = {"tv": srb.REG_TV, "tv3d": srb.REG_TV3D, "btv": srb.REG_BTV, "none": srb.REG_NONE}[reg]
+    okind = {"tv": oracle.REG_TV, "tv3d": oracle.REG_TV3D, "btv": oracle.REG_BTV, "none": oracle.REG_TV}[reg]
+    lam = 0.0 if reg == "none" else 0.01
+    m = oracle.Model(s, psf, shifts)
+    obs = oracle.upsample_observations(m, lr)
+    cost_ref, g_ref = oracle.evaluate(m, x, obs, okind, lam, wts if lam > 0 else None)
+    with srb.MultiEngine(lr.shape, s, psf, shifts, n_gpus=G) as me, srb.Engine(lr.shape, s, psf, shifts) as e1:
+        for e in (me, e1):
+            e.set_observations(lr)
+            e.set_regularizer(kind, lam)
+            if lam > 0:
+                e.set_irls_weights(wts)
+        c1, g1 = e1.eval(x)
+        for rep in range(2):   # the second evaluation re-uses the slots of the first
+            cm, gm = me.eval(x)
+            assert abs(cm - cost_ref) <= REL * abs(cost_ref)
+            assert rel_l2(gm, g_ref) <= REL
+            assert abs(cm - c1) <= 1e-13 * abs(c1)
+            assert rel_l2(gm, g1) <= 1e-13
+        c_only, none = me.eval(x, want_grad=False)
+        assert none is None and abs(c_only - cost_ref) <= REL * abs(cost_ref)
+        # a channel sub-range (IRLSMapSolver's split_channels)
+        if C > 1 and reg != "tv3d":
+            me.set_channel_range(1, C)
+            e1.set_channel_range(1, C)
+            if lam > 0:
+                me.set_irls_weights(wts[1:])
+                e1.set_irls_weights(wts[1:])
+            cm, gm = me.eval(x[1:])
+            c1, g1 = e1.eval(x[1:])
+            assert abs(cm - c1) <= 1e-13 * abs(c1) and rel_l2(gm, g1) <= 1e-13
+
+
+def test_multi_reweight_replicates_weights(srb, oracle):
+    G = min(srb.device_count(), 2)
+    psf, shifts, lr, x, wts = _case(4, 2, 3, 0.8, 2, 32, 64, seed=9)
+    with srb.MultiEngine(lr.shape, 2, psf, shifts, n_gpus=G) as me:
+        me.set_observations(lr)
+        me.set_regularizer(srb.REG_TV, 0.01)
+        w = me.reweight(x)
+        assert np.array_equal(w, oracle.reweight(oracle.REG_TV, x))
+        m = oracle.Model(2, psf, shifts)
+        obs = oracle.upsample_observations(m, lr)
+        cost_ref, g_ref = oracle.evaluate(m, x, obs, oracle.REG_TV, 0.01, w)
+        cm, gm = me.eval(x)
+        assert abs(cm - cost_ref) <= REL * abs(cost_ref) and rel_l2(gm, g_ref) <= REL
+
+
+def test_multi_rejects_bad_arguments(srb):
+    psf = wl.gaussian_psf(3, 0.8)
+    with pytest.raises(srb.SrbError):
+        srb.MultiEngine((4, 1, 16, 16), 2, psf, wl.default_shifts(4, 2), n_gpus=9)
+    with pytest.raises(srb.SrbError):
+        srb.MultiEngine((4, 1, 16, 16), 2, psf, wl.default_shifts(4, 2), n_gpus=2, devices=[0, 0])
+    with pytest.raises(srb.SrbError):
+        srb.MultiEngine((0, 1, 16, 16), 2, psf, None, n_gpus=1)

@@ -5,7 +5,7 @@ The report must have been taken from the same source revision.
     python tools/phase_breakdown.py gpurun_out/prof.ncu-rep [pixels_per_launch]"""
 import csv, re, subprocess, sys
 csv.field_size_limit(10 ** 9)
-SRC = "super-resolution_b200/csrc/srb_kernels_tile.cuh"
+SRC = sys.argv[3] if len(sys.argv) > 3 else "super-resolution_b200/csrc/srb_kernels_tile.cuh"
 rep = sys.argv[1]
 npx = float(sys.argv[2]) if len(sys.argv) > 2 else 2048 * 2048 * 3
 marks = []
