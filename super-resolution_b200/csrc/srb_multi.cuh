@@ -26,16 +26,18 @@ struct srb_multi {
   srb_model_desc desc{};                 // the whole model (pointers into the vectors below)
   std::vector<double> psf, shifts;
   size_t lr_plane = 0;                   // h * w
-  // ownership of the active gradient: device o owns elements [band_elem[o], band_elem[o + 1])
+  // The active range is cut into `ngroups` groups of whole channels (no dependency crosses a channel
+  // boundary for the data term or 2-D TV), each group into G contiguous bands of gradient units: device o
+  // owns elements [band_elem[g][o], band_elem[g][o + 1]) of group g.  Groups flow through the stages
+  // H2D -> all-gather -> evaluate -> sum -> D2H as a pipeline.
+  static constexpr int kMaxGroups = 4;
   bool bands_valid = false;
   bool pipelined = false;                // every rank can evaluate unit ranges (fused path, no border band)
-  int band_unit[SRB_MAX_PEERS + 1] = {};
-  long long band_elem[SRB_MAX_PEERS + 1] = {};
-  long long band_cap = 0;
-  std::vector<double*> slots;            // per device: [G][band_cap] incoming partial bands
-  long long slots_cap = 0;
-  std::vector<cudaStream_t> s_gather, s_push[2];
-  std::vector<cudaEvent_t> ev_h2d, ev_x, ev_band[SRB_MAX_PEERS], ev_pushed, ev_sum, ev_t0, ev_t1;
+  int ngroups = 1;
+  int band_unit[kMaxGroups][SRB_MAX_PEERS + 1] = {};
+  long long band_elem[kMaxGroups][SRB_MAX_PEERS + 1] = {};
+  std::vector<cudaStream_t> s_gather;
+  std::vector<cudaEvent_t> ev_h2d[kMaxGroups], ev_x[kMaxGroups], ev_part[kMaxGroups], ev_t0, ev_t1;
   std::vector<double*> h_cost;           // pinned, [4] per device
   std::string err;
   srb_timing timing{};
@@ -60,15 +62,53 @@ namespace srb {
     }                                                                                            \
   } while (0)
 
-// own += slots[s] for s != rank, in rank order: out = sum_s contribution_s (fixed order: deterministic)
+struct MultiPtrs {
+  double* p[SRB_MAX_PEERS];
+  long long begin[SRB_MAX_PEERS + 1];
+};
+
+// All-gather, pull form: this device copies band s of x from device s's replica (NVLink peer loads) into its
+// own replica, for every s != rank.  16-byte accesses; bands start on even elements.
 __global__ void __launch_bounds__(256)
-k_multi_sum_band(double* __restrict__ own, const double* __restrict__ slots, long long cap, long long len,
-                 int world, int rank) {
+k_multi_pull_x(MultiPtrs X, int world, int rank) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-    double acc = 0.0;
-    for (int s = 0; s < world; ++s) acc += s == rank ? own[i] : slots[(long long)s * cap + i];
-    own[i] = acc;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int s = 0; s < world; ++s) {
+    if (s == rank) continue;
+    const long long b = X.begin[s], e = X.begin[s + 1];
+    if (((b | e) & 1) == 0) {
+      const double2* __restrict__ src = reinterpret_cast<const double2*>(X.p[s] + b);
+      double2* __restrict__ dst = reinterpret_cast<double2*>(X.p[rank] + b);
+      for (long long i = i0; i < ((e - b) >> 1); i += stride) dst[i] = src[i];
+    } else {
+      for (long long i = i0; i < e - b; i += stride) X.p[rank][b + i] = X.p[s][b + i];
+    }
+  }
+}
+
+// Reduce-scatter, pull form: out[i] = sum over devices s = 0 .. world-1 (fixed order: deterministic) of
+// device s's partial gradient, for this device's band [begin, end); the partials of the other devices are
+// read over NVLink, the sum replaces this device's own partial.
+__global__ void __launch_bounds__(256)
+k_multi_sum_pull(MultiPtrs Gp, int world, int rank, long long begin, long long end) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((begin | end) & 1) == 0) {
+    for (long long i = i0; i < ((end - begin) >> 1); i += stride) {
+      double2 acc = make_double2(0.0, 0.0);
+      for (int s = 0; s < world; ++s) {
+        const double2 v = reinterpret_cast<const double2*>(Gp.p[s] + begin)[i];
+        acc.x += v.x;
+        acc.y += v.y;
+      }
+      reinterpret_cast<double2*>(Gp.p[rank] + begin)[i] = acc;
+    }
+  } else {
+    for (long long i = i0; i < end - begin; i += stride) {
+      double acc = 0.0;
+      for (int s = 0; s < world; ++s) acc += Gp.p[s][begin + i];
+      Gp.p[rank][begin + i] = acc;
+    }
   }
 }
 
@@ -77,8 +117,9 @@ inline srb_status multi_status(srb_multi* m, int r, srb_status st) {
   return st;
 }
 
-// Band ownership for the current channel range / regularizer: unit-aligned when every rank can evaluate
-// unit ranges (then finished bands leave while the next ones are computed), even element split otherwise.
+// Groups and band ownership for the current channel range / regularizer: whole-channel groups cut into
+// unit-aligned bands when every rank can evaluate unit ranges; one group with an even element split
+// otherwise (the evaluation is then one eval_core per device).
 inline srb_status multi_plan_bands(srb_multi* m) {
   const int G = m->G;
   srb_ctx* c0 = m->rank[0];
@@ -86,26 +127,32 @@ inline srb_status multi_plan_bands(srb_multi* m) {
   for (int r = 0; r < G; ++r) m->pipelined = m->pipelined && units_pipelined(m->rank[r]);
   const long long n = (long long)c0->n_active();
   if (m->pipelined) {
-    peer_bands(c0, G, m->band_unit, m->band_elem, &m->band_cap);
-  } else {
-    m->band_cap = 0;
-    for (int o = 0; o <= G; ++o) {
-      m->band_unit[o] = 0;
-      m->band_elem[o] = o == G ? n : ((n * o / G) & ~1LL);
-      if (o > 0) m->band_cap = std::max(m->band_cap, m->band_elem[o] - m->band_elem[o - 1]);
-    }
-  }
-  if (m->band_cap > m->slots_cap) {
-    for (int r = 0; r < G; ++r) {
-      SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-      if (m->slots[r]) cudaFree(m->slots[r]);
-      m->slots[r] = nullptr;
-      if (cudaMalloc((void**)&m->slots[r], (size_t)G * (size_t)m->band_cap * sizeof(double)) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return m->fail(SRB_ERR_NOMEM, "cudaMalloc failed (multi-GPU band slots)");
+    const int Ca = c0->Ca();
+    const int tr = tile_rows_per_channel(c0), TH = tile_height(c0);
+    static const int env_groups = getenv("SRB_MULTI_GROUPS") ? atoi(getenv("SRB_MULTI_GROUPS")) : 0;
+    int ng = env_groups > 0 ? env_groups : 3;
+    ng = std::max(1, std::min(std::min(ng, Ca), (int)srb_multi::kMaxGroups));
+    m->ngroups = ng;
+    auto first_elem = [&](int u) -> long long {
+      if (u >= tr * Ca) return n;
+      const int ch = u / tr, t = u - ch * tr;
+      const int row = t * TH < c0->g.H ? t * TH : c0->g.H;
+      return (long long)ch * (long long)c0->P + (long long)row * c0->g.W;
+    };
+    for (int g = 0; g < ng; ++g) {
+      const int u0 = (int)((long long)Ca * g / ng) * tr, u1 = (int)((long long)Ca * (g + 1) / ng) * tr;
+      for (int o = 0; o <= G; ++o) {
+        const int u = u0 + (int)((long long)(u1 - u0) * o / G);
+        m->band_unit[g][o] = u;
+        m->band_elem[g][o] = first_elem(u);
       }
     }
-    m->slots_cap = m->band_cap;
+  } else {
+    m->ngroups = 1;
+    for (int o = 0; o <= G; ++o) {
+      m->band_unit[0][o] = 0;
+      m->band_elem[0][o] = o == G ? n : ((n * o / G) & ~1LL);
+    }
   }
   m->bands_valid = true;
   return SRB_OK;
@@ -125,12 +172,9 @@ void srb_multi_destroy(srb_multi* m) {
     cudaSetDevice(m->dev[r]);
     if (m->rank[r] && m->rank[r]->stream) cudaStreamSynchronize(m->rank[r]->stream);
     if (r < (int)m->s_gather.size() && m->s_gather[r]) { cudaStreamSynchronize(m->s_gather[r]); cudaStreamDestroy(m->s_gather[r]); }
-    for (auto& sp : m->s_push)
-      if (r < (int)sp.size() && sp[r]) { cudaStreamSynchronize(sp[r]); cudaStreamDestroy(sp[r]); }
     auto kill = [&](std::vector<cudaEvent_t>& v) { if (r < (int)v.size() && v[r]) cudaEventDestroy(v[r]); };
-    kill(m->ev_h2d); kill(m->ev_x); kill(m->ev_pushed); kill(m->ev_sum); kill(m->ev_t0); kill(m->ev_t1);
-    for (auto& v : m->ev_band) kill(v);
-    if (r < (int)m->slots.size() && m->slots[r]) cudaFree(m->slots[r]);
+    kill(m->ev_t0); kill(m->ev_t1);
+    for (int g = 0; g < srb_multi::kMaxGroups; ++g) { kill(m->ev_h2d[g]); kill(m->ev_x[g]); kill(m->ev_part[g]); }
     if (r < (int)m->h_cost.size() && m->h_cost[r]) cudaFreeHost(m->h_cost[r]);
   }
   for (srb_ctx* c : m->rank) srb_destroy(c);
@@ -179,12 +223,15 @@ srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devi
     m->frame_begin[n_gpus] = f;
   }
   m->rank.assign(n_gpus, nullptr);
-  m->slots.assign(n_gpus, nullptr);
   m->h_cost.assign(n_gpus, nullptr);
   m->s_gather.assign(n_gpus, nullptr);
-  for (auto& sp : m->s_push) sp.assign(n_gpus, nullptr);
-  for (auto* v : {&m->ev_h2d, &m->ev_x, &m->ev_pushed, &m->ev_sum, &m->ev_t0, &m->ev_t1}) v->assign(n_gpus, nullptr);
-  for (auto& v : m->ev_band) v.assign(n_gpus, nullptr);
+  m->ev_t0.assign(n_gpus, nullptr);
+  m->ev_t1.assign(n_gpus, nullptr);
+  for (int g = 0; g < srb_multi::kMaxGroups; ++g) {
+    m->ev_h2d[g].assign(n_gpus, nullptr);
+    m->ev_x[g].assign(n_gpus, nullptr);
+    m->ev_part[g].assign(n_gpus, nullptr);
+  }
   for (int r = 0; r < n_gpus; ++r) {
     srb_model_desc dr = m->desc;
     dr.num_frames = m->frame_begin[r + 1] - m->frame_begin[r];
@@ -210,12 +257,13 @@ srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devi
     int lo = 0, hi = 0;
     SRB_MULTI_CHECK(m, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     SRB_MULTI_CHECK(m, cudaStreamCreateWithPriority(&m->s_gather[r], cudaStreamNonBlocking, hi));
-    for (auto& sp : m->s_push) SRB_MULTI_CHECK(m, cudaStreamCreateWithPriority(&sp[r], cudaStreamNonBlocking, hi));
-    for (auto* v : {&m->ev_h2d, &m->ev_x, &m->ev_pushed, &m->ev_sum})
-      SRB_MULTI_CHECK(m, cudaEventCreateWithFlags(&(*v)[r], cudaEventDisableTiming));
+    for (int g = 0; g < srb_multi::kMaxGroups; ++g) {
+      SRB_MULTI_CHECK(m, cudaEventCreateWithFlags(&m->ev_h2d[g][r], cudaEventDisableTiming));
+      SRB_MULTI_CHECK(m, cudaEventCreateWithFlags(&m->ev_x[g][r], cudaEventDisableTiming));
+      SRB_MULTI_CHECK(m, cudaEventCreateWithFlags(&m->ev_part[g][r], cudaEventDisableTiming));
+    }
     SRB_MULTI_CHECK(m, cudaEventCreate(&m->ev_t0[r]));
     SRB_MULTI_CHECK(m, cudaEventCreate(&m->ev_t1[r]));
-    for (auto& v : m->ev_band) SRB_MULTI_CHECK(m, cudaEventCreateWithFlags(&v[r], cudaEventDisableTiming));
     SRB_MULTI_CHECK(m, cudaMallocHost((void**)&m->h_cost[r], 4 * sizeof(double)));
   }
   return SRB_OK;
@@ -311,97 +359,97 @@ srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* g_host, do
     srb_status st = multi_plan_bands(m);
     if (st != SRB_OK) return st;
   }
-  const long long* be = m->band_elem;
-  // ---- 1. every device fetches its own band of x over its own PCIe link --------------------------------
+  const int NG = m->ngroups;
+  MultiPtrs X, Gp;
   for (int r = 0; r < G; ++r) {
-    srb_ctx* c = m->rank[r];
-    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t0[r], c->s_in));
-    if (be[r + 1] > be[r])
-      SRB_MULTI_CHECK(m, cudaMemcpyAsync(c->d_x + be[r], x_host + be[r], (size_t)(be[r + 1] - be[r]) * sizeof(double),
-                                         cudaMemcpyHostToDevice, c->s_in));
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_h2d[r], c->s_in));
+    X.p[r] = m->rank[r]->d_x;
+    Gp.p[r] = m->rank[r]->d_grad;
   }
-  // ---- 2. all-gather of the bands over NVLink: device r pushes its band into every replica ---------------
+  // Streams per device: s_in (H2D of its bands), s_gather (pulls the other bands of x over NVLink), stream
+  // (the tile kernel), s_out (sums its band over the devices' partials, then D2H).  Groups are issued one
+  // after the other on every stream, so group g + 1 is copied in while group g is evaluated and group g - 1
+  // returns to the host.
   for (int r = 0; r < G; ++r) {
     SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-    SRB_MULTI_CHECK(m, cudaStreamWaitEvent(m->s_gather[r], m->ev_h2d[r], 0));
-    if (be[r + 1] > be[r])
-      for (int i = 1; i < G; ++i) {
-        const int q = (r + i) % G;   // staggered destinations: every link carries one band at a time
-        SRB_MULTI_CHECK(m, cudaMemcpyPeerAsync(m->rank[q]->d_x + be[r], m->dev[q], m->rank[r]->d_x + be[r], m->dev[r],
-                                               (size_t)(be[r + 1] - be[r]) * sizeof(double), m->s_gather[r]));
-      }
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_x[r], m->s_gather[r]));
+    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t0[r], m->rank[r]->s_in));
   }
-  // ---- 3. partial objective of every device's frames, band by band (other owners first); a finished
-  //         band goes to its owner's slot by copy engine while the SMs compute the next one ---------------
-  for (int r = 0; r < G; ++r) {
-    srb_ctx* c = m->rank[r];
-    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-    for (int q = 0; q < G; ++q) SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->stream, m->ev_x[q], 0));
-    // the slots of this device may still be read by the previous evaluation's sum (same stream: ordered)
-    const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
-    double* d_g = c->d_grad;
-    if (m->pipelined) {
-      for (int i = 0; i < G; ++i) {
-        const int o = (r + 1 + i) % G;  // i == G - 1  <=>  o == r: the own band last, it stays local
-        if (m->band_unit[o + 1] > m->band_unit[o]) {
-          bool reg_done = false;
-          srb_status st = fused_eval_units(c, c->d_x, d_g, do_reg, m->band_unit[o], m->band_unit[o + 1], &reg_done);
-          if (st != SRB_OK) return multi_status(m, r, st);
-        }
-        if (o == r) break;
-        SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_band[i][r], c->stream));
-        if (be[o + 1] > be[o]) {
-          cudaStream_t sp = m->s_push[i & 1][r];
-          SRB_MULTI_CHECK(m, cudaStreamWaitEvent(sp, m->ev_band[i][r], 0));
-          SRB_MULTI_CHECK(m, cudaMemcpyPeerAsync(m->slots[o] + (long long)r * m->band_cap, m->dev[o], d_g + be[o], m->dev[r],
-                                                 (size_t)(be[o + 1] - be[o]) * sizeof(double), sp));
-        }
-      }
-      srb_status st = fused_eval_finish(c, c->d_x, d_g, nullptr);
-      if (st != SRB_OK) return multi_status(m, r, st);
-      c->timing.num_evals += 1;
-    } else {
-      srb_status st = eval_core(c, c->d_x, d_g, nullptr, true, true, false);
-      if (st != SRB_OK) return multi_status(m, r, st);
-      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_band[0][r], c->stream));
-      for (int i = 0; i + 1 < G; ++i) {
-        const int o = (r + 1 + i) % G;
-        if (be[o + 1] <= be[o]) continue;
-        cudaStream_t sp = m->s_push[i & 1][r];
-        SRB_MULTI_CHECK(m, cudaStreamWaitEvent(sp, m->ev_band[0][r], 0));
-        SRB_MULTI_CHECK(m, cudaMemcpyPeerAsync(m->slots[o] + (long long)r * m->band_cap, m->dev[o], d_g + be[o], m->dev[r],
-                                               (size_t)(be[o + 1] - be[o]) * sizeof(double), sp));
-      }
+  for (int g = 0; g < NG; ++g) {
+    const long long* be = m->band_elem[g];
+    for (int o = 0; o <= G; ++o) X.begin[o] = be[o];
+    // ---- 1. every device fetches its own band of x over its own PCIe link ------------------------------
+    for (int r = 0; r < G; ++r) {
+      srb_ctx* c = m->rank[r];
+      SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+      if (be[r + 1] > be[r])
+        SRB_MULTI_CHECK(m, cudaMemcpyAsync(c->d_x + be[r], x_host + be[r], (size_t)(be[r + 1] - be[r]) * sizeof(double),
+                                           cudaMemcpyHostToDevice, c->s_in));
+      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_h2d[g][r], c->s_in));
     }
-    SRB_MULTI_CHECK(m, cudaMemcpyAsync(m->h_cost[r], c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    // "all pushes of device r delivered": one event per push stream, joined on the first
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_sum[r], m->s_push[1][r]));
-    SRB_MULTI_CHECK(m, cudaStreamWaitEvent(m->s_push[0][r], m->ev_sum[r], 0));
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_pushed[r], m->s_push[0][r]));
-  }
-  // ---- 4. every owner sums its band in fixed device order and returns it over its own PCIe link -------
-  for (int o = 0; o < G; ++o) {
-    srb_ctx* c = m->rank[o];
-    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[o]));
-    if (g_host && be[o + 1] > be[o]) {
-      for (int q = 0; q < G; ++q)
-        if (q != o) SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->stream, m->ev_pushed[q], 0));
-      const long long len = be[o + 1] - be[o];
-      const int blocks = (int)std::min<long long>((len + 255) / 256, (long long)c->num_sms * 8);
-      k_multi_sum_band<<<blocks, 256, 0, c->stream>>>(c->d_grad + be[o], m->slots[o], m->band_cap, len, G, o);
+    // ---- 2. all-gather over NVLink: every device pulls the other devices' bands into its replica ----------
+    for (int r = 0; r < G; ++r) {
+      srb_ctx* c = m->rank[r];
+      SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+      for (int q = 0; q < G; ++q) SRB_MULTI_CHECK(m, cudaStreamWaitEvent(m->s_gather[r], m->ev_h2d[g][q], 0));
+      const long long len = be[G] - be[0];
+      const int blocks = (int)std::max<long long>(1, std::min<long long>((len / 2 + 255) / 256, (long long)c->num_sms * 4));
+      k_multi_pull_x<<<blocks, 256, 0, m->s_gather[r]>>>(X, G, r);
       c->timing.kernel_launches += 1;
       SRB_MULTI_CHECK(m, cudaGetLastError());
-      SRB_MULTI_CHECK(m, cudaMemcpyAsync(g_host + be[o], c->d_grad + be[o], (size_t)len * sizeof(double),
-                                         cudaMemcpyDeviceToHost, c->stream));
-    } else {
-      // nothing to sum here, but the next evaluation must not overwrite slots that are still being filled
-      for (int q = 0; q < G; ++q)
-        if (q != o) SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->stream, m->ev_pushed[q], 0));
+      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_x[g][r], m->s_gather[r]));
     }
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t1[o], c->stream));
+    // ---- 3. partial objective of every device's frames over the group ------------------------------------
+    for (int r = 0; r < G; ++r) {
+      srb_ctx* c = m->rank[r];
+      SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+      SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->stream, m->ev_x[g][r], 0));
+      if (m->pipelined) {
+        const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
+        bool reg_done = false;
+        if (m->band_unit[g][G] > m->band_unit[g][0]) {
+          srb_status st = fused_eval_units(c, c->d_x, c->d_grad, do_reg, m->band_unit[g][0], m->band_unit[g][G], &reg_done);
+          if (st != SRB_OK) return multi_status(m, r, st);
+        }
+        if (g == NG - 1) {
+          srb_status st = fused_eval_finish(c, c->d_x, c->d_grad, nullptr);
+          if (st != SRB_OK) return multi_status(m, r, st);
+          c->timing.num_evals += 1;
+        }
+      } else {
+        srb_status st = eval_core(c, c->d_x, c->d_grad, nullptr, true, true, false);
+        if (st != SRB_OK) return multi_status(m, r, st);
+      }
+      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_part[g][r], c->stream));
+      if (g == NG - 1)
+        SRB_MULTI_CHECK(m, cudaMemcpyAsync(m->h_cost[r], c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    // ---- 4. every owner sums its band over the devices' partials (NVLink peer loads, fixed order) and
+    //         returns it over its own PCIe link -----------------------------------------------------------
+    if (g_host) {
+      for (int o = 0; o < G; ++o) {
+        srb_ctx* c = m->rank[o];
+        if (be[o + 1] <= be[o]) continue;
+        SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[o]));
+        for (int q = 0; q < G; ++q) SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->s_out, m->ev_part[g][q], 0));
+        const long long len = be[o + 1] - be[o];
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((len / 2 + 255) / 256, (long long)c->num_sms * 4));
+        k_multi_sum_pull<<<blocks, 256, 0, c->s_out>>>(Gp, G, o, be[o], be[o + 1]);
+        c->timing.kernel_launches += 1;
+        SRB_MULTI_CHECK(m, cudaGetLastError());
+        SRB_MULTI_CHECK(m, cudaMemcpyAsync(g_host + be[o], c->d_grad + be[o], (size_t)len * sizeof(double),
+                                           cudaMemcpyDeviceToHost, c->s_out));
+      }
+    }
+  }
+  for (int r = 0; r < G; ++r) {
+    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t1[r], m->rank[r]->s_out));
+  }
+  // every stream of every device drains before the buffers are touched again: a device's partial gradient
+  // and its replica of x are read by its peers
+  for (int r = 0; r < G; ++r) {
+    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+    SRB_MULTI_CHECK(m, cudaStreamSynchronize(m->rank[r]->s_out));
+    SRB_MULTI_CHECK(m, cudaStreamSynchronize(m->s_gather[r]));
   }
   double total = 0.0;
   for (int r = 0; r < G; ++r) {
