@@ -190,6 +190,13 @@ srb_status srb_solve_irls(srb_ctx* ctx, double* x_host_inout, const srb_cg_optio
  * the current configuration resolves to. */
 srb_status srb_set_path(srb_ctx* ctx, int path);
 int srb_active_path(const srb_ctx* ctx);
+/* Parity device for the reference-order kernels (SRB_PATH_REFERENCE_ORDER, srb_data_term, srb_irls_term): sum
+ * the data cost and the regularization cost sequentially in the reference's own order
+ * (objective_data_term.cpp:36-50 and :104-114, objective_irls_regularization_term.cpp:44-55) instead of by a
+ * parallel tree, so that the cost -- like the gradient -- is BIT-IDENTICAL to the CPU reference's and a whole
+ * ALGLIB solve on top of it reproduces the CPU solve bit for bit.  One thread per frame: for small problems
+ * (cfg1, cfg2); off by default. */
+srb_status srb_set_strict_cost(srb_ctx* ctx, int on);
 /* 1 when the fused path evaluates interior tiles from the observations re-laid out on the HR grid
  * ("Z layout", opt-in with SRB_ZLAYOUT=1 in the environment of srb_create; integer shifts with one
  * frame per sub-pixel phase only), else 0.  No reference counterpart. */

@@ -28,43 +28,11 @@
 #include "optimization/objective_irls_regularization_term.h"
 #include "optimization/tv_regularizer.h"
 #include "sr_oracle.h"
-#include "srb200_adapters.hpp"  // include/: the adapters INTEGRATION.md tells a maintainer to add
 #include "optimization/alglib_objective.h"
 
 #include "glog/logging.h"
 
-extern "C" {
-typedef double (*ref_data_term_cb)(const double* x, double* grad_accum_or_null, int channel_start,
-                                   int channel_end, void* user);
-typedef void (*ref_reg_apply_cb)(const double* x, int num_channels, double* values, void* user);
-typedef void (*ref_reg_apply_diff_cb)(const double* x, const double* constants, int num_channels,
-                                      double* values, double* partials, void* user);
-typedef struct {
-  ref_data_term_cb data_term;          // NULL => oracle restatement
-  ref_reg_apply_cb reg_apply;          // NULL => reference regularizer classes
-  ref_reg_apply_diff_cb reg_apply_diff;
-  void* user;
-} ref_callbacks;
-
-typedef struct {
-  int solver;  // 0 = CG_SOLVER, 1 = LBFGS_SOLVER (map_solver.h:20-23)
-  int max_num_solver_iterations;
-  int max_num_irls_iterations;
-  double gradient_norm_threshold, cost_decrease_threshold, parameter_variation_threshold;
-  double irls_cost_difference_threshold;
-  int split_channels;
-  int num_lbfgs_hessian_corrections;
-  int use_numerical_differentiation;
-  double numerical_differentiation_step;
-  int num_threads;  // oracle data term threads
-} ref_options;
-
-typedef struct {
-  long num_data_term_evals;
-  double seconds_in_data_term;
-  double seconds_total;
-} ref_stats;
-}
+#include "ref_shim.h"
 
 namespace {
 struct SolveContext {
@@ -227,6 +195,18 @@ void ref_default_options(ref_options* o) {
 int ref_solve(const sro_model* m, const double* lr, int N, int C, int h, int w, const double* x0,
               int reg_kind, int R, double decay, double lambda, const ref_options* opt,
               const ref_callbacks* cbs, double* out, ref_stats* stats) {
+  return ref_solve_with_regularizer(m, lr, N, C, h, w, x0, reg_kind, R, decay, lambda, opt, cbs, nullptr, out, stats);
+}
+
+}  // extern "C"
+
+// The same with a caller-built Regularizer object handed to IRLSMapSolver::AddRegularizer
+// (map_solver.h:85-93) -- how oracle/ref_fused.cpp passes the product's CudaRegularizer adapter to the
+// reference's unmodified solver.  C++ linkage: both sides are built by the same compiler.
+int ref_solve_with_regularizer(const sro_model* m, const double* lr, int N, int C, int h, int w, const double* x0,
+                               int reg_kind, int R, double decay, double lambda, const ref_options* opt,
+                               const ref_callbacks* cbs, std::shared_ptr<super_resolution::Regularizer> reg_override,
+                               double* out, ref_stats* stats) {
   const auto t0 = std::chrono::steady_clock::now();
   const int s = m->scale;
   const int H = h * s, W = w * s;
@@ -271,7 +251,9 @@ int ref_solve(const sro_model* m, const double* lr, int N, int C, int h, int w, 
   IRLSMapSolver solver(options, image_model, low_res_images, /*print_solver_output=*/false);
   if (reg_kind >= 0 && lambda > 0) {
     std::shared_ptr<Regularizer> reg;
-    if (cbs && cbs->reg_apply && cbs->reg_apply_diff)
+    if (reg_override)
+      reg = reg_override;
+    else if (cbs && cbs->reg_apply && cbs->reg_apply_diff)
       reg = std::make_shared<CallbackRegularizer>(cv::Size(W, H), cbs);
     else
       reg = MakeRegularizer(reg_kind, R, decay, H, W);
@@ -287,69 +269,7 @@ int ref_solve(const sro_model* m, const double* lr, int N, int C, int h, int w, 
   return 0;
 }
 
-// IRLSMapSolver::Solve with the B200 engine behind the reference's seams, the way INTEGRATION.md
-// wires it: ONE CudaObjectiveTerm (srb_eval = data term + IRLS regularization term, fused) replaces
-// the ObjectiveDataTerm built at irls_map_solver.cpp:243-246 and the ObjectiveIRLSRegularizationTerm
-// added per outer iteration at :83-93; the weight vector the reference keeps on the host
-// (:66-74, :128-143) lives on the device (srb_set_irls_weights / srb_reweight).  The loop below
-// restates irls_map_solver.cpp:45-157 and :192-265 around those three substitutions; the inner solve
-// is the reference's own RunCGSolverAnalyticalDiff / RunLBFGSSolverAnalyticalDiff + ALGLIB,
-// unmodified.  `ctx` already holds the model, the observations and the regularizer
-// (srb_create / srb_set_observations / srb_set_regularizer).
-int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has_regularizer,
-                    double lambda_sum, const ref_options* opt, double* out, ref_stats* stats) {
-  const auto t0 = std::chrono::steady_clock::now();
-  const size_t P = (size_t)H * W;
-  IRLSMapSolverOptions options;
-  options.least_squares_solver = opt->solver == 1 ? LBFGS_SOLVER : CG_SOLVER;
-  options.max_num_solver_iterations = opt->max_num_solver_iterations;
-  options.max_num_irls_iterations = opt->max_num_irls_iterations;
-  options.gradient_norm_threshold = opt->gradient_norm_threshold;
-  options.cost_decrease_threshold = opt->cost_decrease_threshold;
-  options.parameter_variation_threshold = opt->parameter_variation_threshold;
-  options.irls_cost_difference_threshold = opt->irls_cost_difference_threshold;
-  options.split_channels = opt->split_channels != 0;
-  options.num_lbfgs_hessian_corrections = opt->num_lbfgs_hessian_corrections;
-  options.use_numerical_differentiation = false;
-
-  // irls_map_solver.cpp:200-216
-  const int per_split = options.split_channels ? 1 : C;
-  const int rounds = C / per_split;
-  const int num_data_points = per_split * (int)P;
-  options.AdjustThresholdsAdaptively(num_data_points, has_regularizer ? lambda_sum : 0.0);
-  ref_stats st{};
-  for (int i = 0; i < rounds; ++i) {
-    const int c0 = i * per_split, c1 = c0 + per_split;
-    CHECK(srb_set_channel_range(ctx, c0, c1) == SRB_OK) << srb_last_error(ctx);  // resets weights to 1 (:66-74)
-    alglib::real_1d_array solver_data;  // :232-239
-    solver_data.setlength(num_data_points);
-    std::memcpy(solver_data.getcontent(), x0 + (size_t)c0 * P, (size_t)num_data_points * sizeof(double));
-    // :45-157
-    double previous_cost = std::numeric_limits<double>::infinity();
-    double cost_difference = options.irls_cost_difference_threshold + 1.0;
-    int num_iterations_ran = 0;
-    while (std::abs(cost_difference) >= options.irls_cost_difference_threshold) {
-      ObjectiveFunction objective_function(num_data_points);
-      objective_function.AddTerm(std::make_shared<CudaObjectiveTerm>(ctx));
-      const double final_cost = options.least_squares_solver == CG_SOLVER
-                                    ? RunCGSolverAnalyticalDiff(options, objective_function, &solver_data)
-                                    : RunLBFGSSolverAnalyticalDiff(options, objective_function, &solver_data);
-      if (!has_regularizer) break;  // :118-121
-      // :128-143, on the device: w = 1 / max(1e-5, reg(x))
-      CHECK(srb_reweight(ctx, solver_data.getcontent(), nullptr) == SRB_OK) << srb_last_error(ctx);
-      cost_difference = previous_cost - final_cost;
-      previous_cost = final_cost;
-      num_iterations_ran++;
-      if (options.max_num_irls_iterations > 0 && num_iterations_ran >= options.max_num_irls_iterations) break;
-    }
-    std::memcpy(out + (size_t)c0 * P, solver_data.getcontent(), (size_t)num_data_points * sizeof(double));
-  }
-  srb_timing tm;
-  if (srb_get_timing(ctx, &tm) == SRB_OK) st.num_data_term_evals = (long)tm.num_evals;
-  st.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  if (stats) *stats = st;
-  return 0;
-}
+extern "C" {
 
 // ---- ALGLIB's mincg on an arbitrary objective (C callback), configured exactly as
 // RunCGSolverAnalyticalDiff does (alglib_objective.cpp:47-75).  The checker of the device-resident

@@ -221,10 +221,11 @@ void sro_transpose(const sro_model* m, int k, const double* lr, int h, int w, do
 
 /* ------------------------------------------------------------------------------------------
  * ComputeTermForObservation (objective_data_term.cpp:15-75) for one frame and one channel:
- * returns the channel's residual sum, adds 2 * A^T(...) into grad_c (may be NULL).
+ * continues the frame's running residual sum `sum` through this channel's pixels (:36-50 keeps ONE
+ * accumulator over all channels of a frame) and returns it; adds 2 * A^T(...) into grad_c (may be NULL).
  * ---------------------------------------------------------------------------------------- */
 static double sro_data_term_frame_channel(const sro_model* m, int k, const double* x_c, int H,
-                                          int W, const double* obs_c, double* grad_c) {
+                                          int W, const double* obs_c, double* grad_c, double sum) {
   const size_t P = (size_t)H * W;
   int h, w;
   sro_lr_size(m->scale, H, W, &h, &w);
@@ -234,7 +235,6 @@ static double sro_data_term_frame_channel(const sro_model* m, int k, const doubl
   sro_forward(m, k, x_c, H, W, lr);
   sro_resize_nearest(lr, h, w, up, H, W);
   /* :36-50  residuals and their squared sum, pixel order */
-  double sum = 0.0;
   for (size_t p = 0; p < P; ++p) {
     const double r = up[p] - obs_c[p];
     up[p] = r;
@@ -258,9 +258,10 @@ static double sro_data_term_frame_channel(const sro_model* m, int k, const doubl
 }
 
 /* ObjectiveDataTerm::Compute (objective_data_term.cpp:98-116): frames in order, channels in
- * order.  With num_threads > 1 frames x channels run in parallel into private gradient buffers
- * that are then summed in frame order (so the result equals the serial one up to the order in
- * which per-frame costs are added, which is kept: frame-major, channel-minor). */
+ * order; serially the cost is summed exactly as the reference does (one running sum per frame over
+ * its channels and pixels, frame sums added in frame order).  With num_threads > 1 frames x
+ * channels run in parallel into private gradient buffers that are then summed in frame order, and
+ * the cost is the sum of per-(frame, channel) sums: equal to the serial one up to re-association. */
 double sro_data_term(const sro_model* m, const double* x, int H, int W, int C,
                      const double* obs_hr, int C_total, int channel_start, double* gradient,
                      int num_threads) {
@@ -270,12 +271,17 @@ double sro_data_term(const sro_model* m, const double* x, int H, int W, int C,
   double* costs = sro_alloc((size_t)jobs);
   if (num_threads <= 1) {
     /* the reference's order: frame-major, channels inside, gradient accumulated in place */
-    for (int j = 0; j < jobs; ++j) {
-      const int k = j / C, c = j % C;
-      costs[j] = sro_data_term_frame_channel(
-          m, k, x + c * P, H, W, obs_hr + ((size_t)k * C_total + channel_start + c) * P,
-          gradient ? gradient + c * P : NULL);
+    double total = 0.0;
+    for (int k = 0; k < N; ++k) {
+      double frame = 0.0;
+      for (int c = 0; c < C; ++c)
+        frame = sro_data_term_frame_channel(
+            m, k, x + c * P, H, W, obs_hr + ((size_t)k * C_total + channel_start + c) * P,
+            gradient ? gradient + c * P : NULL, frame);
+      total += frame;
     }
+    free(costs);
+    return total;
   } else {
     /* threaded: per-job private gradient buffers, reduced afterwards in frame order */
     double* priv = NULL;
@@ -290,7 +296,7 @@ double sro_data_term(const sro_model* m, const double* x, int H, int W, int C,
       const int k = j / C, c = j % C;
       costs[j] = sro_data_term_frame_channel(
           m, k, x + c * P, H, W, obs_hr + ((size_t)k * C_total + channel_start + c) * P,
-          priv ? priv + (size_t)j * P : NULL);
+          priv ? priv + (size_t)j * P : NULL, 0.0);
     }
     if (gradient) {
       for (int j = 0; j < jobs; ++j) {

@@ -15,6 +15,7 @@ from . import sr_oracle as _o  # noqa: F401  (also makes sure libsr_oracle.so is
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libsr_ref.so")
+_FUSED_LIB_PATH = os.path.join(_HERE, "_ref", "libsr_ref_fused.so")
 _dp = C.POINTER(C.c_double)
 
 DATA_TERM_CB = C.CFUNCTYPE(C.c_double, _dp, _dp, C.c_int, C.c_int, C.c_void_p)
@@ -71,11 +72,28 @@ def lib():
                                 C.c_int, C.c_double, C.c_double, C.POINTER(Options),
                                 C.POINTER(Callbacks), _dp, C.POINTER(Stats)]
         L.ref_solve.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+_fused = None
+
+
+def fused_lib():
+    """oracle/_ref/libsr_ref_fused.so: the reference's solver with the product's C++ adapters plugged in.
+    The only oracle library that links libsrb200.so; the CPU reference arm never loads it."""
+    global _fused
+    if _fused is None:
+        lib()
+        L = C.CDLL(_FUSED_LIB_PATH)
         L.ref_solve_fused.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_double,
                                       C.POINTER(Options), _dp, C.POINTER(Stats)]
         L.ref_solve_fused.restype = C.c_int
-        _lib = L
-    return _lib
+        L.ref_solve_adapters.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
+                                         C.c_int, C.c_double, C.POINTER(Options), _dp, C.POINTER(Stats)]
+        L.ref_solve_adapters.restype = C.c_int
+        _fused = L
+    return _fused
 
 
 def _p(a):
@@ -152,7 +170,22 @@ def solve_fused(engine, x0, has_regularizer, lambda_sum, options=None):
     out = np.empty_like(x0)
     st = Stats()
     opt = options if options is not None else default_options()
-    rc = lib().ref_solve_fused(engine._ctx, Cn, H, W, _p(x0), 1 if has_regularizer else 0,
+    rc = fused_lib().ref_solve_fused(engine._ctx, Cn, H, W, _p(x0), 1 if has_regularizer else 0,
                                float(lambda_sum), C.byref(opt), _p(out), C.byref(st))
+    assert rc == 0
+    return out, st
+
+
+def solve_adapters(engine, model, lr, x0, has_regularizer, lam, options=None):
+    """The reference's UNMODIFIED IRLSMapSolver::Solve with CudaObjectiveDataTerm and CudaRegularizer
+    (include/srb200_adapters.hpp) instantiated in C++ (ref_fused.cpp: ref_solve_adapters).  `engine` holds the
+    model, the observations and the regularizer kind.  Returns (result, Stats)."""
+    lr, x0 = _f64(lr), _f64(x0)
+    N, Cn, h, w = lr.shape
+    out = np.empty_like(x0)
+    st = Stats()
+    opt = options if options is not None else default_options()
+    rc = fused_lib().ref_solve_adapters(engine._ctx, C.cast(model.c, C.c_void_p), _p(lr), N, Cn, h, w, _p(x0),
+                                        1 if has_regularizer else 0, float(lam), C.byref(opt), _p(out), C.byref(st))
     assert rc == 0
     return out, st

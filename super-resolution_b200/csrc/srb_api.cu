@@ -113,9 +113,19 @@ srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, b
     const dim3 grid = grid2d(G.w, G.h, G.N * Ca);
     const size_t nblocks = (size_t)grid.x * grid.y * grid.z;
     if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
+    if (c->strict_cost && (st = dev_alloc(c, &c->d_resid, (size_t)G.N * G.Ct * c->p)) != SRB_OK) return st;
+    if (c->strict_cost && (st = ensure_partials(c, nblocks + (size_t)G.N)) != SRB_OK) return st;
     k_forward_generic<1><<<grid, dim3(32, 8), 0, c->stream>>>(make_params(c, false), d_x, c->d_y,
-                                                             c->d_pooled, c->d_partial);
-    k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 0);
+                                                             c->d_pooled, c->d_partial, c->strict_cost ? c->d_resid : nullptr);
+    if (c->strict_cost) {
+      // the reference's summation order (objective_data_term.cpp:36-50, 104-114): bit-identical cost
+      k_strict_data_cost<<<(G.N + 31) / 32, 32, 0, c->stream>>>(c->d_resid, G.N, Ca, G.H, G.W, G.h, G.w, G.s,
+                                                               c->d_partial + nblocks, nullptr);
+      k_strict_sum_frames<<<1, 1, 0, c->stream>>>(c->d_partial + nblocks, G.N, c->d_cost);
+      c->timing.kernel_launches += 1;
+    } else {
+      k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 0);
+    }
     c->timing.kernel_launches += 2;
     if (d_g) {
       k_adjoint_generic<<<grid2d(G.W, G.H, Ca), dim3(32, 8), 0, c->stream>>>(
@@ -138,7 +148,10 @@ srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, b
     if ((st = ensure_partials(c, nblocks)) != SRB_OK) return st;
     k_reg_partials<1><<<grid, dim3(32, 8), 0, c->stream>>>(R, d_x, c->d_vals, c->d_w, c->lambda,
                                                           c->reg_row0, c->reg_row1, d_g, c->d_partial);
-    k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 1);
+    if (c->strict_cost && c->reg_row0 == 0 && c->reg_row1 == G.H)
+      k_strict_reg_cost<<<1, 1, 0, c->stream>>>(c->d_vals, c->d_w, c->lambda, c->n_active(), c->d_cost + 1);
+    else
+      k_reduce_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nblocks, c->d_cost, 1);
     c->timing.kernel_launches += 3;
   }
   k_finish_cost<<<1, 1, 0, c->stream>>>(c->d_cost, tail);
@@ -382,7 +395,7 @@ void srb_destroy(srb_ctx* c) {
   dev_free(&c->d_psf); dev_free(&c->d_src_r); dev_free(&c->d_src_c);
   dev_free(&c->d_rowY_fwd); dev_free(&c->d_rowY_tr); dev_free(&c->d_nX_fwd); dev_free(&c->d_nX_tr);
   dev_free(&c->d_y); dev_free(&c->d_decay); dev_free(&c->d_w); dev_free(&c->d_x); dev_free(&c->d_grad);
-  dev_free(&c->d_pooled); dev_free(&c->d_vals); dev_free(&c->d_aux); dev_free(&c->d_partial);
+  dev_free(&c->d_resid); dev_free(&c->d_pooled); dev_free(&c->d_vals); dev_free(&c->d_aux); dev_free(&c->d_partial);
   dev_free(&c->d_cost);
   dev_free(&c->cg_store);
   if (c->cg_h_out) cudaFreeHost(c->cg_h_out);
@@ -629,6 +642,11 @@ srb_status srb_set_path(srb_ctx* c, int path) {
   return SRB_OK;
 }
 int srb_active_path(const srb_ctx* c) { return c ? resolve_path(c) : -1; }
+srb_status srb_set_strict_cost(srb_ctx* c, int on) {
+  if (!c) return SRB_ERR_INVALID;
+  c->strict_cost = on != 0;
+  return SRB_OK;
+}
 int srb_zlayout_active(const srb_ctx* c) {
   const TileState* st = c ? tile_state(c) : nullptr;
   return (st && st->supported && (st->d_yz || st->d_yzt) && st->yz_valid) ? 1 : 0;

@@ -80,6 +80,8 @@ struct srb_ctx {
   double* d_w = nullptr;      // IRLS weights [Ct][H][W]
   int reg_row0 = 0, reg_row1 = 0;
   int path = SRB_PATH_AUTO;
+  bool strict_cost = false;   // reference-order kernels sum their costs sequentially in the reference's order
+  double* d_resid = nullptr;  // [N][Ct][h][w] raw residuals (strict cost only)
   void* fused = nullptr;  // srb::FusedState (srb_kernels_fused.cuh)
 
   // work buffers

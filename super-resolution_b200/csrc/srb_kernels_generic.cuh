@@ -69,7 +69,7 @@ __device__ __forceinline__ double forward_pixel(const GenericParams& P, const do
 template <int kMode>
 __global__ void __launch_bounds__(256)
 k_forward_generic(GenericParams P, const double* __restrict__ x, const double* __restrict__ y,
-                  double* __restrict__ out, double* __restrict__ cost_partial) {
+                  double* __restrict__ out, double* __restrict__ cost_partial, double* __restrict__ resid = nullptr) {
   const int qc = blockIdx.x * 32 + threadIdx.x;
   const int qr = blockIdx.y * 8 + threadIdx.y;
   const int kc = blockIdx.z;
@@ -90,6 +90,7 @@ k_forward_generic(GenericParams P, const double* __restrict__ x, const double* _
       const int reps = P.s * P.s;
       for (int t = 0; t < reps; ++t) pooled = __dadd_rn(pooled, r);
       out[o] = pooled;
+      if (resid) resid[o] = r;   // strict-order cost (k_strict_data_cost)
       cost = (double)reps * (r * r);
     }
   }
@@ -98,6 +99,34 @@ k_forward_generic(GenericParams P, const double* __restrict__ x, const double* _
     if (threadIdx.x == 0 && threadIdx.y == 0)
       cost_partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = bs;
   }
+}
+
+// The data cost summed in the REFERENCE'S order (objective_data_term.cpp:36-50, 104-114): per frame one
+// running sum over channels and HR pixels of residual * residual -- the residual image is the nearest-
+// upsampled LR residual, so every LR residual enters s*s times, in raster order -- and the frame sums added
+// in frame order.  One thread per frame; a parity device (srb_set_strict_cost), not a fast path.
+__global__ void k_strict_data_cost(const double* __restrict__ resid, int N, int Ca, int H, int W, int h, int w, int s,
+                                   double* __restrict__ frame_sums, double* __restrict__ cost_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < N) {
+    double sum = 0.0;
+    for (int c = 0; c < Ca; ++c) {
+      const double* __restrict__ rc = resid + ((size_t)k * Ca + c) * ((size_t)h * w);
+      for (int pr = 0; pr < H; ++pr) {
+        const double* __restrict__ rr = rc + (size_t)(pr / s) * w;
+        for (int pc = 0; pc < W; ++pc) {
+          const double r = rr[pc / s];
+          sum = __dadd_rn(sum, __dmul_rn(r, r));
+        }
+      }
+    }
+    frame_sums[k] = sum;
+  }
+}
+__global__ void k_strict_sum_frames(const double* __restrict__ frame_sums, int N, double* __restrict__ cost_out) {
+  double total = 0.0;
+  for (int k = 0; k < N; ++k) total = __dadd_rn(total, frame_sums[k]);
+  *cost_out = total;
 }
 
 // B^T D^T of one frame at HR pixel (pr, pc): filter2D with blur_kernel_.t() (blur_module.cpp:

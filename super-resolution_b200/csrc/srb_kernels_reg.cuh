@@ -181,6 +181,18 @@ k_reg_partials(RegParams P, const double* __restrict__ x, const double* __restri
   }
 }
 
+// The IRLS regularization cost summed in the reference's order (objective_irls_regularization_term.cpp:
+// 44-55): residual_sum += lambda * w_i * r_i * r_i, i ascending.  One thread (srb_set_strict_cost).
+__global__ void k_strict_reg_cost(const double* __restrict__ vals, const double* __restrict__ w, double lambda, size_t n,
+                                  double* __restrict__ cost_out) {
+  double sum = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    const double v = vals[i];
+    sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(__dmul_rn(lambda, w[i]), v), v));
+  }
+  *cost_out = sum;
+}
+
 __global__ void k_fill(double* __restrict__ p, size_t n, double v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     p[i] = v;

@@ -43,6 +43,7 @@ SIGNATURES = {
     "srb_solve_irls": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "srb_set_path": (C.c_int, [_ctx_p, C.c_int]),
     "srb_active_path": (C.c_int, [_ctx_p]),
+    "srb_set_strict_cost": (C.c_int, [_ctx_p, C.c_int]),
     "srb_zlayout_active": (C.c_int, [_ctx_p]),
     "srb_set_regularizer_rows": (C.c_int, [_ctx_p, C.c_int, C.c_int]),
     "srb_eval": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
@@ -291,6 +292,14 @@ class Engine:
         self._check(self._lib.srb_lbfgs_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
         return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
 
+    def cg_minimize_inplace(self, x, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        """srb_cg_minimize on the caller's own buffer (float64, contiguous, num_active elements; pin it with
+        pin_host for full PCIe rate): the initial estimate on entry, the solution on return.  Returns the report."""
+        assert isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.size == self.num_active
+        opt, rep = self._cg_options(epsg, epsf, epsx, maxits), CgReport()
+        self._check(self._lib.srb_cg_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
+        return _as_dict(rep)
+
     def cg_minimize_dev(self, x_dev, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
         opt, rep = self._cg_options(epsg, epsf, epsx, maxits), CgReport()
         self._check(self._lib.srb_cg_minimize_dev(self._ctx, _dev_ptr(x_dev), C.byref(opt), C.byref(rep)))
@@ -308,6 +317,10 @@ class Engine:
 
     def set_path(self, path):
         self._check(self._lib.srb_set_path(self._ctx, int(path)))
+
+    def set_strict_cost(self, on=True):
+        """Reference-order kernels sum their costs in the reference's own sequential order (bit-identical cost)."""
+        self._check(self._lib.srb_set_strict_cost(self._ctx, 1 if on else 0))
 
     @property
     def active_path(self):

@@ -202,7 +202,7 @@ def test_forward_transpose_data_term_vs_opencv(oracle, cv2_fixtures, name):
     cost_only, none = oracle.data_term(m, x, obs, want_grad=False)
     assert none is None and cost_only == cost
     cost_t, grad_t = oracle.data_term(m, x, obs, threads=4)
-    assert cost_t == cost
+    assert abs(cost_t - cost) <= 1e-14 * abs(cost)   # per-(frame, channel) sums re-associated
     np.testing.assert_array_equal(grad_t, grad)
 
 
