@@ -83,9 +83,10 @@ typedef struct {
   int band_lo_r, band_hi_r, band_lo_c, band_hi_c;
   int table_driven;          /* interior tiles use the precomputed residual table: frames per
                                 sub-pixel phase it is specialised for (1, 2 or 4), 0 = generic pass */
-  int zlayout;               /* Z layout (k_tile_z): 1 = qualifies (integer shifts, 3x3 .. 9x9 PSF, one
-                                frame on every sub-pixel phase; the default kernel then), 2 = qualifies with
-                                empty phases (frame shards; opt-in SRB_ZLAYOUT=2), 0 = no */
+  int zlayout;               /* Z layout (k_tile_zt): 1 = qualifies (integer shifts, 3x3 .. 9x9 PSF, one
+                                frame on every sub-pixel phase), 2 = qualifies with empty phases (at most one
+                                frame per phase: frame shards, cfg2), 0 = no.  Both are the DEFAULT kernel for
+                                such models; SRB_ZLAYOUT=0 in the environment of srb_create disables it */
   char why[160];             /* reason when fused == 0, or the validation error */
 } srb_plan_info;
 srb_status srb_plan(const srb_model_desc* desc, srb_plan_info* out);
@@ -131,8 +132,14 @@ srb_status srb_set_regularizer(srb_ctx* ctx, int kind, double lambda, int btv_ra
  * (irls_map_solver.cpp:83-93). */
 srb_status srb_set_irls_weights(srb_ctx* ctx, const double* weights_host);
 /* IRLS re-weighting on device (irls_map_solver.cpp:128-143): w = 1 / max(1e-5, reg(x)).
- * x_host = NULL re-uses the estimate of the last evaluation; weights_out_host may be NULL. */
+ * x_host = NULL re-uses the estimate the last HOST-buffer evaluation or solve on the current channel range
+ * left in the context (srb_eval, srb_data_term, srb_irls_term, srb_cg_minimize, srb_lbfgs_minimize,
+ * srb_solve_irls); after anything else -- the *_dev and srb_peer_* forms work on the caller's own device
+ * buffer -- it fails with SRB_ERR_STATE.  weights_out_host may be NULL. */
 srb_status srb_reweight(srb_ctx* ctx, const double* x_host, double* weights_out_host);
+/* Same for a device-resident estimate ((c1-c0)*H*W doubles on the context's device), stream-ordered, no
+ * host synchronisation: what follows srb_cg_minimize_dev in a device-resident IRLS loop. */
+srb_status srb_reweight_dev(srb_ctx* ctx, const double* x_dev);
 
 /* ---- device-resident solver ------------------------------------
  * The reference minimises with ALGLIB's mincg on host arrays (RunCGSolverAnalyticalDiff,
@@ -197,9 +204,11 @@ int srb_active_path(const srb_ctx* ctx);
  * ALGLIB solve on top of it reproduces the CPU solve bit for bit.  One thread per frame: for small problems
  * (cfg1, cfg2); off by default. */
 srb_status srb_set_strict_cost(srb_ctx* ctx, int on);
-/* 1 when the fused path evaluates interior tiles from the observations re-laid out on the HR grid
- * ("Z layout", opt-in with SRB_ZLAYOUT=1 in the environment of srb_create; integer shifts with one
- * frame per sub-pixel phase only), else 0.  No reference counterpart. */
+/* 1 when the fused path evaluates its tiles from the observations re-laid out on the HR grid ("Z layout":
+ * default for models with integer shifts and at most one frame per sub-pixel phase; SRB_ZLAYOUT=0 in the
+ * environment of srb_create disables it), else 0.  The layout is a second, padded copy of the observations
+ * ([Ct][W+2*KH rounded to tiles][H+halo] doubles: the size of x for N = s^2) built on the device by
+ * srb_set_observations.  No reference counterpart. */
 int srb_zlayout_active(const srb_ctx* ctx);
 /* Multi-GPU frame sharding: this context holds the frames of one rank.  The data
  * term covers the context's frames; the regularizer term is computed only for HR rows
@@ -267,6 +276,11 @@ srb_status srb_peer_scatter_dev(srb_ctx* ctx, const double* x_dev);
 /* Phase 2: wait for all ranks' flags, sum this rank's band over the slots and store it, with the
  * total cost, into every rank's gradient buffer; wait until all bands have arrived here. */
 srb_status srb_peer_gather_dev(srb_ctx* ctx);
+/* The flag barriers spin a bounded number of times.  When a rank never arrives they record the failure on the
+ * device, skip the sum and the stores (nothing partial is published; the other ranks time out in turn) and
+ * return.  srb_peer_status, srb_synchronize and srb_memcpy_d2h read that record: SRB_ERR_STATE means the
+ * gradient and cost of the evaluation are not valid (the record is cleared by the call). */
+srb_status srb_peer_status(srb_ctx* ctx);
 srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, unsigned long long bytes);
 
 /* ---- single-process multi-GPU form ------------------------------------------------------------------

@@ -463,6 +463,7 @@ srb_status srb_set_channel_range(srb_ctx* c, int c0, int c1) {
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   c->c0 = c0;
   c->c1 = c1;
+  c->x_resident = false;
   return reset_weights(c);
 }
 
@@ -509,14 +510,29 @@ srb_status srb_reweight(srb_ctx* c, const double* x_host, double* w_out) {
   if (!c) return SRB_ERR_INVALID;
   if (!reg_active(c)) return c->fail(SRB_ERR_STATE, "no regularizer configured");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
-  if (x_host)
+  if (x_host) {
     SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, c->n_active() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->x_resident = true;
+  } else if (!c->x_resident) {
+    // only the host-buffer entry points (srb_eval, srb_cg_minimize, ...) leave the estimate in the context;
+    // the *_dev forms work on the caller's device buffer, which this context does not keep
+    return c->fail(SRB_ERR_STATE, "srb_reweight(x = NULL) needs a preceding evaluation or solve with a HOST estimate "
+                                  "on the current channel range; use srb_reweight_dev for device-resident estimates");
+  }
   srb_status rst = reweight_dev(c, c->d_x);
   if (rst != SRB_OK) return rst;
   if (w_out)
     SRB_CUDA_CHECK(c, cudaMemcpyAsync(w_out, c->d_w, c->n_active() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   return SRB_OK;
+}
+
+srb_status srb_reweight_dev(srb_ctx* c, const double* x_dev) {
+  if (!c) return SRB_ERR_INVALID;
+  if (!x_dev) return c->fail(SRB_ERR_INVALID, "null estimate");
+  if (!reg_active(c)) return c->fail(SRB_ERR_STATE, "no regularizer configured");
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  return reweight_dev(c, x_dev);
 }
 
 // ---- device-resident solver --------------------------------------------------------
@@ -582,6 +598,7 @@ srb_status srb_lbfgs_minimize(srb_ctx* c, double* x_host, const srb_cg_options* 
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   const size_t bytes = c->n_active() * sizeof(double);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = true;
   srb_status st = srb_lbfgs_minimize_dev(c, c->d_x, options, report);
   if (st != SRB_OK) return st;
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(x_host, c->d_x, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -595,6 +612,7 @@ srb_status srb_cg_minimize(srb_ctx* c, double* x_host, const srb_cg_options* opt
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   const size_t bytes = c->n_active() * sizeof(double);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = true;
   srb_status st = srb_cg_minimize_dev(c, c->d_x, options, report);
   if (st != SRB_OK) return st;
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(x_host, c->d_x, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -608,10 +626,16 @@ srb_status srb_solve_irls(srb_ctx* c, double* x_host, const srb_cg_options* opti
   if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
   if (!cg_options_valid(options) || max_num_irls_iterations < 0 || !(irls_cost_difference_threshold >= 0))
     return c->fail(SRB_ERR_INVALID, "invalid solver options");
+  // the outer loop runs while |cost difference| >= threshold (irls_map_solver.cpp:76-78,145-152): with a zero
+  // threshold and no iteration limit it cannot end once a regularizer is configured
+  if (max_num_irls_iterations == 0 && irls_cost_difference_threshold == 0.0 && reg_active(c))
+    return c->fail(SRB_ERR_INVALID, "unlimited IRLS iterations with a zero cost-difference threshold never terminate "
+                                    "(the reference's defaults are 20 and 1e-5, irls_map_solver.h:27,35)");
   if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   const size_t bytes = c->n_active() * sizeof(double);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = true;
   srb_status st = reset_weights(c);  // irls_map_solver.cpp:66-74: all weights 1
   if (st != SRB_OK) return st;
   IrlsReport rep;
@@ -668,6 +692,7 @@ static bool units_pipelined(const srb_ctx* c);
 // every finished gradient slice returns on a copy-out stream -- H2D, compute and D2H overlap, so the
 // call costs about one PCIe direction instead of two (both directions of the link work at once).
 static srb_status eval_host_pipelined(srb_ctx* c, const double* x_host, double* g_host, double* cost) {
+  c->x_resident = true;
   const int nu = tile_rows_per_channel(c) * c->Ca();
   const int nch = std::max(1, std::min(c->pipe_chunks, nu));
   unsigned long long b[srb_ctx::kMaxPipe + 1];
@@ -728,6 +753,7 @@ srb_status srb_eval(srb_ctx* c, const double* x_host, double* g_host, double* co
   const size_t bytes = c->n_active() * sizeof(double);
   cudaEventRecord(c->ev[0], c->stream);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = true;
   cudaEventRecord(c->ev[1], c->stream);
   srb_status st = eval_core(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr, true, true, false);
   if (st != SRB_OK) return st;
@@ -1055,12 +1081,34 @@ srb_status srb_peer_gather_dev(srb_ctx* c) {
   return SRB_OK;
 }
 
+// The flag barriers of the peer path spin a bounded number of times; a rank that never arrives makes them
+// record the failure on the device instead of hanging the GPU (and nothing partial is published).  Every
+// synchronising entry point reads that record back here: the evaluation is then reported as failed and the
+// record (and the last-block counter of k_sum_gather) is cleared so that the next evaluation starts clean.
+static srb_status peer_status(srb_ctx* c) {
+  srb_ctx::Peer& p = c->peer;
+  if (!p.active || !p.d_err) return SRB_OK;
+  int e[2] = {0, 0};
+  SRB_CUDA_CHECK(c, cudaMemcpyAsync(e, p.d_err, sizeof e, cudaMemcpyDeviceToHost, c->stream));
+  SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (e[0] == 0) return SRB_OK;
+  SRB_CUDA_CHECK(c, cudaMemsetAsync(p.d_err, 0, sizeof e, c->stream));
+  return c->fail(SRB_ERR_STATE, "peer barrier timed out: a rank did not deliver its gradient bands; "
+                                "the gradient and cost of this evaluation are not valid");
+}
+
+srb_status srb_peer_status(srb_ctx* c) {
+  if (!c) return SRB_ERR_INVALID;
+  SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
+  return peer_status(c);
+}
+
 srb_status srb_memcpy_d2h(srb_ctx* c, void* dst_host, const void* src_dev, unsigned long long bytes) {
   if (!c || !dst_host || !src_dev) return SRB_ERR_INVALID;
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-  return SRB_OK;
+  return peer_status(c);
 }
 
 srb_status srb_set_profiling(srb_ctx* c, int on) {
@@ -1075,6 +1123,7 @@ static srb_status term_host(srb_ctx* c, const double* x_host, double* g_accum, d
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   const size_t bytes = c->n_active() * sizeof(double);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = true;
   if (g_accum) SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_grad, g_accum, bytes, cudaMemcpyHostToDevice, c->stream));
   // single terms always run the reference-order kernels (they ADD into the caller's gradient in
   // the reference's operation order)
@@ -1104,6 +1153,7 @@ srb_status srb_reg_apply(srb_ctx* c, const double* x_host, int C, double* values
   if (st != SRB_OK) return st;
   const size_t bytes = (size_t)C * c->P * sizeof(double);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = false;
   k_reg_values<0><<<grid2d(c->g.W, c->g.H, C), dim3(32, 8), 0, c->stream>>>(make_reg_params(c, C), c->d_x, c->d_vals);
   c->timing.kernel_launches += 1;
   SRB_CUDA_CHECK(c, cudaGetLastError());
@@ -1124,6 +1174,7 @@ srb_status srb_reg_apply_diff(srb_ctx* c, const double* x_host, const double* cs
   if ((st = dev_alloc(c, &c->d_aux, (size_t)c->g.Ct * c->P)) != SRB_OK) return st;
   const size_t bytes = (size_t)C * c->P * sizeof(double);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = false;
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_aux, cst_host, bytes, cudaMemcpyHostToDevice, c->stream));
   const RegParams R = make_reg_params(c, C);
   k_reg_values<0><<<grid2d(c->g.W, c->g.H, C), dim3(32, 8), 0, c->stream>>>(R, c->d_x, c->d_vals);
@@ -1181,6 +1232,7 @@ srb_status srb_forward_all(srb_ctx* c, const double* hr_host, double* lr_out_hos
   srb_status st = dev_alloc(c, &c->d_pooled, n_lr);  // scratch of the reference-order path, same shape
   if (st != SRB_OK) return st;
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, hr_host, n_hr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->x_resident = false;
   GenericParams P = make_params(c, false);
   P.Ca = G.Ct;  // every channel, whatever the active channel range is
   P.c0 = 0;
@@ -1243,7 +1295,7 @@ double* srb_dev_gradient(srb_ctx* c) { return c ? c->d_grad : nullptr; }
 srb_status srb_synchronize(srb_ctx* c) {
   if (!c) return SRB_ERR_INVALID;
   SRB_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-  return SRB_OK;
+  return peer_status(c);
 }
 srb_status srb_get_timing(srb_ctx* c, srb_timing* out) {
   if (!c || !out) return SRB_ERR_INVALID;

@@ -71,6 +71,7 @@ struct srb_ctx {
   // observations and state
   double* d_y = nullptr;
   bool have_obs = false;
+  bool x_resident = false;  // d_x holds the caller's whole estimate of the active channel range (srb_reweight(NULL))
   int c0 = 0, c1 = 0;
   int reg_kind = SRB_REG_NONE;
   double lambda = 0.0;

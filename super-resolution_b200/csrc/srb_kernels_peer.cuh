@@ -23,10 +23,16 @@ struct GatherParams {
 // rank order (deterministic), stored into the gradient buffer of EVERY rank (peer stores over
 // NVLink).  Every block first waits (bounded spin on the local phase-0 flags) until all ranks'
 // contributions have arrived; the last block to finish publishes the total cost locally and raises
-// this rank's phase-1 flag on every rank after a system fence.
+// this rank's phase-1 flag on every rank after a system fence.  A block whose wait times out records the
+// failure in *err and neither sums nor stores nor raises the flag: nothing partial is ever published, the
+// other ranks time out in turn, and the host reports SRB_ERR_STATE at the next synchronisation point
+// (peer_status in srb_api.cu).
 __global__ void __launch_bounds__(256)
 k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long long epoch, unsigned int* done_counter,
              int* err) {
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
   if (threadIdx.x < G.world) {
     const volatile unsigned long long* f =
         reinterpret_cast<const volatile unsigned long long*>(G.out[G.rank] + flag_base) + threadIdx.x;
@@ -34,11 +40,13 @@ k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long lon
     while (*f < epoch)
       if (++spins > (1ull << 24)) {  // seconds: a rank is missing -- give up instead of hanging the GPU
         *err = 1;
+        timed_out = 1;
         break;
       }
     __threadfence_system();
   }
   __syncthreads();
+  if (timed_out || *reinterpret_cast<volatile int*>(err) != 0) return;  // block-uniform
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (((G.band_len | G.band_begin | G.band_cap) & 1) == 0) {
@@ -75,6 +83,7 @@ k_sum_gather(GatherParams G, long long n, long long flag_base, unsigned long lon
       G.out[G.rank][n] = acc;
       *done_counter = 0;
     }
+    __syncthreads();  // the cost slots are read before any peer may start overwriting them for the next epoch
     if (threadIdx.x < G.world) {
       __threadfence_system();
       volatile unsigned long long* f =

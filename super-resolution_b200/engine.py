@@ -36,6 +36,7 @@ SIGNATURES = {
     "srb_set_regularizer": (C.c_int, [_ctx_p, C.c_int, C.c_double, C.c_int, C.c_double]),
     "srb_set_irls_weights": (C.c_int, [_ctx_p, C.c_void_p]),
     "srb_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_reweight_dev": (C.c_int, [_ctx_p, C.c_void_p]),
     "srb_cg_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srb_cg_minimize_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srb_lbfgs_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "srb_peer_setup": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "srb_peer_scatter_dev": (C.c_int, [_ctx_p, C.c_void_p]),
     "srb_peer_gather_dev": (C.c_int, [_ctx_p]),
+    "srb_peer_status": (C.c_int, [_ctx_p]),
     "srb_memcpy_d2h": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_ulonglong]),
     "srb_data_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
     "srb_irls_term": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
@@ -271,6 +273,9 @@ class Engine:
         self._check(self._lib.srb_reweight(self._ctx, _host_ptr(xa), _host_ptr(out)))
         return None if out is None else out.reshape(self.c1 - self.c0, self.H, self.W)
 
+    def reweight_dev(self, x_dev):
+        self._check(self._lib.srb_reweight_dev(self._ctx, _dev_ptr(x_dev)))
+
     # -- device-resident solver
     @staticmethod
     def _cg_options(epsg, epsf, epsx, maxits, lbfgs_corrections=0):
@@ -305,9 +310,11 @@ class Engine:
         self._check(self._lib.srb_cg_minimize_dev(self._ctx, _dev_ptr(x_dev), C.byref(opt), C.byref(rep)))
         return _as_dict(rep)
 
-    def solve_irls(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0, max_irls_iterations=0,
-                   irls_cost_difference_threshold=0.0, lbfgs_corrections=0):
-        """IRLSMapSolver::RunIRLSLoop on the device.  Returns (x, report dict)."""
+    def solve_irls(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0, max_irls_iterations=20,
+                   irls_cost_difference_threshold=1.0e-5, lbfgs_corrections=0):
+        """IRLSMapSolver::RunIRLSLoop on the device.  Returns (x, report dict).  The outer-loop defaults are
+        the reference's (irls_map_solver.h:27,35: 20 iterations, cost difference 1e-5); unlimited iterations
+        together with a zero threshold would never terminate and is refused by srb_solve_irls."""
         x = np.array(_f64(x0).reshape(-1), copy=True)
         assert x.size == self.num_active
         opt, rep = self._cg_options(epsg, epsf, epsx, maxits, lbfgs_corrections), IrlsReport()
@@ -391,6 +398,10 @@ class Engine:
 
     def peer_gather_dev(self):
         self._check(self._lib.srb_peer_gather_dev(self._ctx))
+
+    def peer_status(self):
+        """Raises SrbError(SRB_ERR_STATE) if a flag barrier of the peer path timed out since the last check."""
+        self._check(self._lib.srb_peer_status(self._ctx))
 
     def memcpy_d2h(self, dst, src_ptr, nbytes):
         self._check(self._lib.srb_memcpy_d2h(self._ctx, dst.ctypes.data_as(C.c_void_p), C.c_void_p(src_ptr), int(nbytes)))
