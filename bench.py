@@ -338,7 +338,7 @@ def main():
         return ms, launches, part, step, stream, peer, objective
 
     def reduce_max(*vals):
-        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t.cpu()]
@@ -351,8 +351,8 @@ def main():
     x0 = np.ascontiguousarray(work["x0"]).reshape(-1)
     stream0 = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
     with torch.cuda.stream(stream0):
-        x_dev = torch.from_numpy(x0).to("cuda", non_blocking=False)
-        gc_dev = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+        x_dev = torch.from_numpy(x0).to(dev, non_blocking=False)
+        gc_dev = torch.zeros(n + 1, dtype=torch.float64, device=dev)
     if world > 1:
         dist.broadcast(x_dev, src=0)        # replicas of the same estimate
     h_x = torch.from_numpy(x0.copy()).pin_memory()
@@ -405,6 +405,7 @@ def main():
                     cost, _ = me.eval(h_x.numpy(), out=h_g.numpy()[:n])
                 e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
             del full
+        torch.cuda.set_device(local_rank)   # rank 0 drove every GPU from this thread
         dist.barrier(group=cpu_group)
     ms_step, e2e_ms, kernel_ms = reduce_max(ms_step, e2e_ms, kernel_ms)
 
@@ -484,6 +485,15 @@ def main():
                 line["roofline"]["traffic"] = json.load(open(prof)).get("cfg%d_%s" % (args.config, path_name))
             except Exception:
                 pass
+        plan = srb.plan((len(frames), C, H // s, W // s), s, psf, work["shifts"])
+        if path_name == "fused_zlayout" and plan["zt_frames"] > 1:
+            # frames with equal shifts are averaged once at upload (srb_kernels_tilez.cuh): the kernel then reads one
+            # observation per HR pixel instead of N / s^2.  `achieved` stays SURVEY 8d's algorithmic bytes (what the
+            # reference's algorithm has to touch); the bytes the kernel really moves are stated beside it.
+            moved = wl.algorithmic_bytes(H, W, C, len(frames) // plan["zt_frames"], s, has_reg=True)
+            line["roofline"].update(merged_frames_per_phase=plan["zt_frames"], bytes_moved_model=moved,
+                                    achieved_moved=moved / (kernel_ms * 1e-3) / 1e9,
+                                    frac_moved=moved / (kernel_ms * 1e-3) / 1e9 / peak)
         if solve is not None:
             line["solve"] = solve
         if weak is not None:

@@ -87,6 +87,10 @@ typedef struct {
                                 frame on every sub-pixel phase), 2 = qualifies with empty phases (at most one
                                 frame per phase: frame shards, cfg2), 0 = no.  Both are the DEFAULT kernel for
                                 such models; SRB_ZLAYOUT=0 in the environment of srb_create disables it */
+  int zt_frames;             /* transposed Z layout (k_tile_zt): frames per non-empty sub-pixel phase, all with
+                                the same shift and averaged at upload (1: cfg1-3 and frame shards, 2: cfg4,
+                                4: cfg5); 0 = the model does not qualify (fractional shifts, PSF outside
+                                3x3 .. 9x9, different shifts on one phase, unequal frame counts) */
   char why[160];             /* reason when fused == 0, or the validation error */
 } srb_plan_info;
 srb_status srb_plan(const srb_model_desc* desc, srb_plan_info* out);

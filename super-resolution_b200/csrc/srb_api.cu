@@ -297,6 +297,7 @@ srb_status srb_plan(const srb_model_desc* d, srb_plan_info* out) {
   out->band_lo_c = plan.band.lo_c; out->band_hi_c = plan.band.hi_c;
   out->table_driven = plan.fast[0].empty() ? 0 : plan.fast_E;
   out->zlayout = plan.zlayout;
+  out->zt_frames = plan.zt ? plan.zt_n : 0;
   return SRB_OK;
 }
 

@@ -92,6 +92,9 @@ struct TileParams {
   int fast_items;      // items in the table (pass A + ring)
   // k_tile_z only (kept last for the same reason): the observations re-laid out on the HR grid
   const double* yz;    // [Ct][H][W]: yz(c, p) = the one regular LR sample that lands on HR pixel p
+  // k_tile_zt with merged frames (several frames with the SAME shift on a sub-pixel phase, averaged at upload):
+  // [Ct] per-channel constant s^2 * sum_p sum_e (y_e(p) - mean(p))^2 of the data cost; NULL when nothing is merged
+  const double* yvar;
 };
 
 template <int KH, bool FRAC, int TH>

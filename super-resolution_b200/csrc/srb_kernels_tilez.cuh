@@ -1,9 +1,16 @@
 // srb_kernels_tilez.cuh -- k_tile_zt: the fused tile kernel for models with integer shifts and at most
-// one frame per sub-pixel phase (cfg1, cfg2, cfg3 and every frame shard of them), observations in the
+// one DISTINCT shift per sub-pixel phase (cfg1 .. cfg5 and every frame shard of them), observations in the
 // TRANSPOSED Z layout.  Same mathematics as k_tile (srb_kernels_tile.cuh):
 //     r_k = D M_k (B x) - y_k,     g = 2 s^2 B^T ( sum_k M_k^T D^T r_k ) + TV part,
 // (objective_data_term.cpp:15-75, tv_regularizer.cpp:134-227), rearranged around what bounds the tile
 // on a B200 -- the shared-memory pipe, not HBM and not the fp64 pipe (profiles/r02_k_tile_z_full.txt):
+//
+//  * Frames with the SAME shift (cfg4: 2 per phase, cfg5: 4 per phase) have the same operator A, so
+//        sum_e ||A x - y_e||^2 = n ||A x - m||^2 + sum_e ||y_e - m||^2,      m = mean_e y_e,
+//    exactly, with no cancellation (both terms are sums of squares).  The observations are constant during
+//    a solve: m and the constant second term are formed ONCE, when the observations are uploaded
+//    (k_build_yzt), and the kernel below runs on m with the factor n folded into its two scale factors.
+//    The n frames then cost one observation load per HR pixel instead of n.
 //
 //  * The observations are gathered once, at upload, onto the HR grid ("Z layout": yzt(c, p) = the one
 //    regular LR sample that lands on HR pixel p), stored COLUMN-MAJOR per channel, padded by the PSF half
@@ -221,32 +228,66 @@ k_tile_zt(const TileParams P, const __grid_constant__ CUtensorMap map_x, const _
   const size_t cta = (size_t)unit * gridDim.x + blockIdx.x;
   block_sum2<NT>(cost_data, cost_reg);
   if (tid == 0) {
-    P.part_data[cta] = P.s2 * cost_data;
+    // P.s2 = n s^2 with n frames merged per phase; the constant part of the merged data cost is added once per
+    // channel, by the channel's first tile
+    const double merged_const = (P.yvar != nullptr && blockIdx.x == 0 && ty0 == 0) ? P.yvar[P.c0 + ch] : 0.0;
+    P.part_data[cta] = P.s2 * cost_data + merged_const;
     P.part_reg[cta] = cost_reg;
   }
 }
 
 // Builds the transposed, padded Z layout from the LR observations (once per srb_set_observations):
-//   yzt[(c * cols_p + pc + KH) * rows_p + pr + HYR] = y_k(q) for the one regular sample (k, q) that lands on
-//   HR position (pr, pc) -- positions up to the PSF half width outside the image included -- else NaN.
+//   yzt[(c * cols_p + pc + KH) * rows_p + pr + HYR] = mean over the n frames (k, q) of the sub-pixel phase whose
+//   regular sample lands on HR position (pr, pc) -- positions up to the PSF half width outside the image
+//   included -- else NaN.  All frames of a phase have the same shift (planner: zt), hence the same q; n = 1 is
+//   the plain copy.  var_part[c][block] = sum over the block of sum_e (y_e - mean)^2 (0 for n = 1).
 // grid: (ceil(rows_p / 256), cols_p, Ct)
 __global__ void __launch_bounds__(256)
 k_build_yzt(int h, int w, int s, int rows_p, int cols_p, int pad_r, int pad_c, int lo_r, int hi_r, int lo_c,
             int hi_c, const TEntry* __restrict__ entries, const int* __restrict__ phase_begin,
-            const double* __restrict__ y, double* __restrict__ yzt) {
+            const double* __restrict__ y, double* __restrict__ yzt, double* __restrict__ var_part) {
   const int rp = blockIdx.x * 256 + threadIdx.x, cp = blockIdx.y, c = blockIdx.z;
-  if (rp >= rows_p) return;
-  const int pr = rp - pad_r, pc = cp - pad_c;
-  const int mr = floordiv(pr, s), mc = floordiv(pc, s);
-  const int ph = (pr - mr * s) * s + (pc - mc * s);
-  double v = __longlong_as_double(0x7ff8000000000000LL);
-  if (phase_begin[ph + 1] > phase_begin[ph]) {
-    const TEntry e = entries[phase_begin[ph]];
-    const int qr = mr + (int)(short)(e.qoff & 0xffff), qc = mc + (e.qoff >> 16);
-    if (qr >= lo_r && qr < hi_r && qc >= lo_c && qc < hi_c)
-      v = y[(size_t)c * ((size_t)h * w) + e.yoff + (long long)mr * w + mc];
+  double var = 0.0;
+  if (rp < rows_p) {
+    const int pr = rp - pad_r, pc = cp - pad_c;
+    const int mr = floordiv(pr, s), mc = floordiv(pc, s);
+    const int ph = (pr - mr * s) * s + (pc - mc * s);
+    double v = __longlong_as_double(0x7ff8000000000000LL);
+    const int e0 = phase_begin[ph], cnt = phase_begin[ph + 1] - e0;
+    if (cnt > 0) {
+      const TEntry e = entries[e0];
+      const int qr = mr + (int)(short)(e.qoff & 0xffff), qc = mc + (e.qoff >> 16);
+      if (qr >= lo_r && qr < hi_r && qc >= lo_c && qc < hi_c) {
+        const double* __restrict__ yc = y + (size_t)c * ((size_t)h * w) + ((long long)mr * w + mc);
+        if (cnt == 1) {
+          v = yc[e.yoff];
+        } else {
+          double sum = 0.0;
+          for (int i = 0; i < cnt; ++i) sum += yc[entries[e0 + i].yoff];
+          v = sum / (double)cnt;
+          for (int i = 0; i < cnt; ++i) {
+            const double d = yc[entries[e0 + i].yoff] - v;
+            var = fma(d, d, var);
+          }
+        }
+      }
+    }
+    yzt[((size_t)c * cols_p + cp) * rows_p + rp] = v;
   }
-  yzt[((size_t)c * cols_p + cp) * rows_p + rp] = v;
+  if (var_part != nullptr) {
+    var = block_sum(var);
+    if (threadIdx.x == 0) var_part[((size_t)c * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = var;
+  }
+}
+
+// yvar[c] = scale * sum(var_part[c][0 .. per_channel)), fixed order (deterministic).  grid: Ct
+__global__ void __launch_bounds__(1024)
+k_reduce_yvar(const double* __restrict__ var_part, size_t per_channel, double scale, double* __restrict__ yvar) {
+  const double* __restrict__ p = var_part + (size_t)blockIdx.x * per_channel;
+  double acc = 0.0;
+  for (size_t i = threadIdx.x; i < per_channel; i += blockDim.x) acc += p[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) yvar[blockIdx.x] = scale * acc;
 }
 
 }  // namespace srb

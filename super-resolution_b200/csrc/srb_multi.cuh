@@ -62,6 +62,21 @@ namespace srb {
     }                                                                                            \
   } while (0)
 
+// srb_multi_* walk over the devices with cudaSetDevice; the caller's current device is restored on return
+// (the host solver that owns the thread may be using CUDA itself).
+struct DeviceRestore {
+  int dev = -1;
+  DeviceRestore() {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      dev = -1;
+      (void)cudaGetLastError();
+    }
+  }
+  ~DeviceRestore() {
+    if (dev >= 0) cudaSetDevice(dev);
+  }
+};
+
 struct MultiPtrs {
   double* p[SRB_MAX_PEERS];
   long long begin[SRB_MAX_PEERS + 1];
@@ -168,6 +183,7 @@ srb_ctx* srb_multi_rank_ctx(srb_multi* m, int r) { return (m && r >= 0 && r < m-
 
 void srb_multi_destroy(srb_multi* m) {
   if (!m) return;
+  srb::DeviceRestore restore_device;
   for (int r = 0; r < (int)m->rank.size(); ++r) {
     cudaSetDevice(m->dev[r]);
     if (m->rank[r] && m->rank[r]->stream) cudaStreamSynchronize(m->rank[r]->stream);
@@ -183,6 +199,7 @@ void srb_multi_destroy(srb_multi* m) {
 
 srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devices, srb_multi** out) {
   if (!out) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   *out = nullptr;
   srb_multi* m = new (std::nothrow) srb_multi();
   if (!m) return SRB_ERR_NOMEM;
@@ -271,6 +288,7 @@ srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devi
 
 srb_status srb_multi_set_observations(srb_multi* m, const double* lr_host) {
   if (!m) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   if (!lr_host) return m->fail(SRB_ERR_INVALID, "null observations");
   const size_t per_frame = (size_t)m->desc.num_channels * m->lr_plane;
   for (int r = 0; r < m->G; ++r) {
@@ -283,6 +301,7 @@ srb_status srb_multi_set_observations(srb_multi* m, const double* lr_host) {
 
 srb_status srb_multi_set_channel_range(srb_multi* m, int c0, int c1) {
   if (!m) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   for (int r = 0; r < m->G; ++r) {
     srb_status st = srb_set_channel_range(m->rank[r], c0, c1);
     if (st != SRB_OK) return srb::multi_status(m, r, st);
@@ -293,6 +312,7 @@ srb_status srb_multi_set_channel_range(srb_multi* m, int c0, int c1) {
 
 srb_status srb_multi_set_regularizer(srb_multi* m, int kind, double lambda, int btv_range, double btv_decay) {
   if (!m) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   for (int r = 0; r < m->G; ++r) {
     srb_status st = srb_set_regularizer(m->rank[r], kind, lambda, btv_range, btv_decay);
     if (st != SRB_OK) return srb::multi_status(m, r, st);
@@ -303,6 +323,7 @@ srb_status srb_multi_set_regularizer(srb_multi* m, int kind, double lambda, int 
 
 srb_status srb_multi_set_irls_weights(srb_multi* m, const double* w) {
   if (!m) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   // replicated: every device reads the same host buffer over its own PCIe link, all copies in flight at once
   for (int r = 0; r < m->G; ++r) {
     srb_ctx* c = m->rank[r];
@@ -335,6 +356,7 @@ srb_status srb_multi_set_path(srb_multi* m, int path) {
 // it from its replica of x (the regularizer values are local, one streaming pass), no exchange.
 srb_status srb_multi_reweight(srb_multi* m, const double* x_host, double* w_out) {
   if (!m) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   if (!x_host) return m->fail(SRB_ERR_INVALID, "null estimate");
   for (int r = 0; r < m->G; ++r) {
     srb_status st = srb_reweight(m->rank[r], x_host, r == 0 ? w_out : nullptr);
@@ -347,6 +369,7 @@ srb_status srb_multi_reweight(srb_multi* m, const double* x_host, double* w_out)
 srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* g_host, double* cost) {
   using namespace srb;
   if (!m) return SRB_ERR_INVALID;
+  srb::DeviceRestore restore_device;
   if (!x_host) return m->fail(SRB_ERR_INVALID, "null estimate");
   const int G = m->G;
   for (int r = 0; r < G; ++r)

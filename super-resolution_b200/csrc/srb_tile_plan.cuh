@@ -39,8 +39,11 @@ struct TilePlan {
   // Z layout (k_tile_z): 0 the model does not qualify; 1 integer shifts, PSF 3x3 .. 9x9 and exactly one
   // frame on every sub-pixel phase; 2 the same with some phases empty (a frame shard; HOLES variant)
   int zlayout = 0;
-  // transposed Z layout (k_tile_zt): integer shifts, PSF 3x3 .. 9x9, at most one frame per sub-pixel phase
+  // transposed Z layout (k_tile_zt): integer shifts, PSF 3x3 .. 9x9, at most one DISTINCT shift per sub-pixel
+  // phase and the same number zt_n of frames on every non-empty phase (frames with the same shift are averaged
+  // at upload: cfg4 has 2 per phase, cfg5 4)
   bool zt = false;
+  int zt_n = 0;
 };
 
 struct TileState {
@@ -64,6 +67,8 @@ struct TileState {
   bool yz_holes = false;   // some sub-pixel phases have no frame (NaN in d_yz; k_tile_z<.., true>)
   double* d_yzt = nullptr; // observations in the transposed, padded Z layout [Ct][cols_p][rows_p] (k_tile_zt)
   int yzt_rows = 0, yzt_cols = 0;
+  double* d_yvar = nullptr;      // [Ct] constant part of the merged data cost (zt_n > 1), else NULL
+  double* d_yvar_part = nullptr; // per-block partial sums of k_build_yzt
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -89,6 +94,8 @@ inline void fused_teardown(srb_ctx* c) {
     if (f) cudaFree(f);
   if (st->d_yz) cudaFree(st->d_yz);
   if (st->d_yzt) cudaFree(st->d_yzt);
+  if (st->d_yvar) cudaFree(st->d_yvar);
+  if (st->d_yvar_part) cudaFree(st->d_yvar_part);
   delete st;
   st = nullptr;
 }
@@ -280,7 +287,18 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
       all_one = all_one && lists[ph].size() == 1;
     }
     st->zlayout = flat.empty() ? 0 : (all_one && !st->fast[0].empty()) ? 1 : (at_most_one && !all_one) ? 2 : 0;
-    st->zt = at_most_one;
+    // k_tile_zt: one distinct shift per phase, the same number of frames on every non-empty phase
+    bool mergeable = true;
+    int n = 0;
+    for (size_t ph = 0; ph < lists.size(); ++ph) {
+      if (lists[ph].empty()) continue;
+      if (n == 0) n = (int)lists[ph].size();
+      mergeable = mergeable && (int)lists[ph].size() == n;
+      for (const TEntry& e : lists[ph])
+        mergeable = mergeable && e.qoff == lists[ph][0].qoff && e.bxoff == lists[ph][0].bxoff;
+    }
+    st->zt = mergeable;
+    st->zt_n = mergeable ? std::max(n, 1) : 0;
   }
 
   st->supported = true;
@@ -353,6 +371,12 @@ inline srb_status fused_setup(srb_ctx* c) {
       st->yzt_cols = zt_cols_padded(G.W, plan.KH);
       if (cudaMalloc((void**)&st->d_yzt, (size_t)G.Ct * st->yzt_rows * st->yzt_cols * sizeof(double)) != cudaSuccess)
         return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in transposed Z layout)");
+      if (plan.zt_n > 1) {
+        const size_t per_channel = (size_t)((st->yzt_rows + 255) / 256) * st->yzt_cols;
+        if (cudaMalloc((void**)&st->d_yvar, (size_t)G.Ct * sizeof(double)) != cudaSuccess ||
+            cudaMalloc((void**)&st->d_yvar_part, (size_t)G.Ct * per_channel * sizeof(double)) != cudaSuccess)
+          return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (merged-frame cost constants)");
+      }
     } else if (take && st->tma_ok && st->tile_h == 32) {
       if (cudaMalloc((void**)&st->d_yz, (size_t)G.Ct * G.H * G.W * sizeof(double)) != cudaSuccess)
         return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in Z layout)");
@@ -373,8 +397,12 @@ inline srb_status fused_observations_changed(srb_ctx* c) {
     const dim3 grid((unsigned)((st->yzt_rows + 255) / 256), (unsigned)st->yzt_cols, (unsigned)G.Ct);
     k_build_yzt<<<grid, 256, 0, c->stream>>>(G.h, G.w, G.s, st->yzt_rows, st->yzt_cols, (KH + 1) & ~1, KH,
                                              st->band.lo_r, st->band.hi_r, st->band.lo_c, st->band.hi_c,
-                                             st->d_entries, st->d_phase_begin, c->d_y, st->d_yzt);
+                                             st->d_entries, st->d_phase_begin, c->d_y, st->d_yzt, st->d_yvar_part);
     c->timing.kernel_launches += 1;
+    if (st->d_yvar) {
+      k_reduce_yvar<<<G.Ct, 1024, 0, c->stream>>>(st->d_yvar_part, (size_t)grid.x * grid.y, (double)G.s * G.s, st->d_yvar);
+      c->timing.kernel_launches += 1;
+    }
     SRB_CUDA_CHECK(c, cudaGetLastError());
     st->yz_valid = true;
     return SRB_OK;
@@ -567,13 +595,20 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   // frames per sub-pixel phase the table-driven residual pass is specialised for (1, 2 or 4)
   const int fe = (!st->frac && P.fast != nullptr && (P.fast_E == 2 || P.fast_E == 4)) ? P.fast_E : 1;
   if (P.fast_E != fe) P.fast = nullptr;  // a kernel only ever sees the table it is specialised for
+  P.yvar = nullptr;
   if (st->d_yzt != nullptr && st->yz_valid && TH == 32) {  // transposed Z layout: every tile, one code path
     srb_status zr = SRB_ERR_STATE;
+    TileParams PZ = P;
+    if (st->plan.zt_n > 1) {  // n frames of the same shift merged per phase: n ||A x - mean||^2 + constant
+      PZ.s2 = P.s2 * st->plan.zt_n;
+      PZ.two_s2 = P.two_s2 * st->plan.zt_n;
+      PZ.yvar = st->d_yvar;
+    }
     switch (st->KH) {
-      case 1: zr = tile_launch_zt<1>(c, P, unit_end); break;
-      case 2: zr = tile_launch_zt<2>(c, P, unit_end); break;
-      case 3: zr = tile_launch_zt<3>(c, P, unit_end); break;
-      case 4: zr = tile_launch_zt<4>(c, P, unit_end); break;
+      case 1: zr = tile_launch_zt<1>(c, PZ, unit_end); break;
+      case 2: zr = tile_launch_zt<2>(c, PZ, unit_end); break;
+      case 3: zr = tile_launch_zt<3>(c, PZ, unit_end); break;
+      case 4: zr = tile_launch_zt<4>(c, PZ, unit_end); break;
       default: break;
     }
     if (zr == SRB_OK) {

@@ -137,7 +137,7 @@ class PlanInfo(C.Structure):
                 ("psf_half", C.c_int), ("num_entries", C.c_int), ("min_entries_per_phase", C.c_int),
                 ("max_entries_per_phase", C.c_int), ("band_lo_r", C.c_int), ("band_hi_r", C.c_int),
                 ("band_lo_c", C.c_int), ("band_hi_c", C.c_int), ("table_driven", C.c_int), ("zlayout", C.c_int),
-                ("why", C.c_char * 160)]
+                ("zt_frames", C.c_int), ("why", C.c_char * 160)]
 
 
 class SrbError(RuntimeError):

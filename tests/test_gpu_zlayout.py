@@ -103,12 +103,18 @@ def test_zlayout_channel_range_and_new_observations(srb, oracle):
 
 
 def test_zlayout_declines_models_it_does_not_cover(srb):
-    """Fractional shifts or several frames per phase: the knob is ignored, the default kernels run."""
+    """Fractional shifts, two DIFFERENT shifts on one sub-pixel phase, unequal frame counts per phase: the
+    default kernels run."""
     wl = import_module("super-resolution_b200.workloads")
     rng = np.random.default_rng(3)
     psf = wl.gaussian_psf(5, 1.0)
     lr = rng.random((8, 1, 40, 64))
-    with _engine(srb, True, lr, 2, psf, wl.default_shifts(8, 2)) as e:      # two frames per phase
+    sh = wl.default_shifts(8, 2)
+    sh[4:, 0] += 2.0                                                         # same phases, one LR pixel further
+    with _engine(srb, True, lr, 2, psf, sh) as e:
+        assert not e.zlayout_active
+    lr = rng.random((5, 1, 40, 64))
+    with _engine(srb, True, lr, 2, psf, wl.default_shifts(5, 2)) as e:      # phase (0, 0) twice, the others once
         assert not e.zlayout_active
     lr = rng.random((4, 1, 40, 64))
     sh = np.array([[0.0, 0.0], [1.0, 0.0], [0.5, 1.0], [1.0, 1.0]])
@@ -142,3 +148,82 @@ def test_zlayout_with_empty_phases_matches_oracle(srb, oracle, frames):
         c, g = e.eval(x)
     assert abs(c - cost_ref) <= REL_L2 * abs(cost_ref)
     assert rel_l2(g, g_ref) <= REL_L2
+
+
+@pytest.mark.parametrize("K,s,sigma,C,h,w,N", [
+    (5, 2, 1.5, 3, 80, 96, 8),      # cfg4's model: 2 frames on every sub-pixel phase
+    (9, 4, 2.5, 2, 40, 48, 64),     # cfg5's model: 4 frames on every phase
+    (7, 4, 2.0, 1, 48, 80, 24),     # 3 frames on 8 of the 16 phases, none on the others
+    (3, 2, 0.8, 1, 45, 70, 12),     # 3 per phase, HR size not a multiple of the tile
+])
+def test_frames_with_equal_shifts_are_merged_at_upload(srb, oracle, K, s, sigma, C, h, w, N):
+    """Several frames with the same shift: k_tile_zt runs on their mean, n ||A x - m||^2 + the constant
+    sum_e ||y_e - m||^2 (srb_kernels_tilez.cuh).  Cost and gradient against the oracle, which evaluates every
+    frame separately (objective_data_term.cpp:104-114), and against k_tile (SRB_ZLAYOUT=0), which does too."""
+    wl = import_module("super-resolution_b200.workloads")
+    rng = np.random.default_rng(K * 1000 + N)
+    psf = wl.gaussian_psf(K, sigma)
+    if N == 24:
+        base = wl.default_shifts(16, s)[:8]
+        shifts = np.concatenate([base, base, base])
+    else:
+        shifts = wl.default_shifts(N, s)
+    x = rng.random((C, h * s, w * s))
+    # observations the way a solve sees them: a common signal plus noise (the merged form must not lose digits
+    # when the residual is small against the signal)
+    common = rng.random((1, C, h, w))
+    lr = common + 0.01 * rng.standard_normal((N, C, h, w))
+    wts = rng.uniform(0.5, 2.0, size=x.shape)
+    m = oracle.Model(s, psf, shifts)
+    obs_hr = oracle.upsample_observations(m, lr)
+    p = srb.plan(lr.shape, s, psf, shifts)
+    assert p["zt_frames"] == (3 if N in (24, 12) else N // (s * s)), p
+    cost_ref, g_ref = oracle.evaluate(m, x, obs_hr, reg_kind=oracle.REG_TV, lam=0.01, weights=wts)
+    with _engine(srb, True, lr, s, psf, shifts) as ez, _engine(srb, False, lr, s, psf, shifts) as ed:
+        assert ez.zlayout_active and not ed.zlayout_active
+        for e in (ez, ed):
+            e.set_regularizer(srb.REG_TV, 0.01)
+            e.set_irls_weights(wts)
+        cz, gz = ez.eval(x)
+        cd, gd = ed.eval(x)
+        assert abs(cz - cost_ref) <= REL_L2 * abs(cost_ref)
+        assert rel_l2(gz, g_ref) <= REL_L2
+        assert abs(cz - cd) <= REL_L2 * abs(cd) and rel_l2(gz, gd) <= REL_L2
+        cz2, _ = ez.eval(x, want_grad=False)
+        assert abs(cz2 - cost_ref) <= REL_L2 * abs(cost_ref)
+        ez.set_regularizer(srb.REG_NONE, 0.0)
+        if C > 1:   # the constant term is per channel
+            ez.set_channel_range(1, C)
+            cost_c, g_c = oracle.data_term(m, x[1:], obs_hr, channel_start=1)
+            c1, g1 = ez.eval(x[1:])
+            assert abs(c1 - cost_c) <= REL_L2 * abs(cost_c)
+            assert rel_l2(g1, g_c) <= REL_L2
+        # new observations: the mean and the constant follow
+        ez.set_channel_range(0, C)
+        lr2 = common + 0.02 * rng.standard_normal((N, C, h, w))
+        ez.set_observations(lr2)
+        cost2, g2 = oracle.data_term(m, x, oracle.upsample_observations(m, lr2))
+        c2, gg2 = ez.eval(x)
+        assert abs(c2 - cost2) <= REL_L2 * abs(cost2)
+        assert rel_l2(gg2, g2) <= REL_L2
+
+
+def test_merged_frames_near_the_solution_keep_the_cost_digits(srb, oracle):
+    """Noise-free observations evaluated at the truth: the residual is ~0, the cost is dominated by rounding.
+    The merged form n (b - m)^2 + sum (y_e - m)^2 is a sum of squares and must stay as small as the oracle's."""
+    wl = import_module("super-resolution_b200.workloads")
+    K, s, sigma, C, h, w, N = 5, 2, 1.5, 1, 64, 64, 8
+    rng = np.random.default_rng(77)
+    psf = wl.gaussian_psf(K, sigma)
+    shifts = wl.default_shifts(N, s)
+    x = wl.box_smooth(rng.random((C, h * s, w * s)))
+    m = oracle.Model(s, psf, shifts)
+    lr = np.stack([np.stack([oracle.forward(m, k, x[c]) for c in range(C)]) for k in range(N)])
+    obs_hr = oracle.upsample_observations(m, lr)
+    cost_ref, g_ref = oracle.data_term(m, x, obs_hr)
+    with _engine(srb, True, lr, s, psf, shifts) as e:
+        assert e.zlayout_active
+        c, g = e.eval(x)
+    scale = float(np.sum(obs_hr ** 2))
+    assert cost_ref <= 1e-25 * scale and c <= 1e-25 * scale, (cost_ref, c, scale)
+    assert np.abs(g).max() <= 1e-12 and np.abs(g_ref).max() <= 1e-12

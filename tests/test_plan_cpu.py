@@ -41,6 +41,8 @@ def test_plans_of_the_baseline_configurations():
         assert (p["min_entries_per_phase"], p["max_entries_per_phase"]) == ex["per_phase"], (cfg, p)
         assert p["table_driven"] == ex["table"]      # frames per phase of the table-driven residual pass (0: generic)
         assert p["zlayout"] == ex["z"], (cfg, p)
+        # k_tile_zt: frames per non-empty phase, all with the same shift, averaged at upload
+        assert p["zt_frames"] == max(1, cf["N"] // (s * s)), (cfg, p)
         assert p["num_entries"] == cf["N"]
         # default shifts are >= 0 and at most s - 1: at most a thin band at the top / left
         assert p["band_hi_r"] >= cf["H"] // s - 2 and p["band_hi_c"] >= cf["W"] // s - 2
@@ -140,5 +142,10 @@ def test_zlayout_qualification_of_frame_shards_and_other_models():
     frac = shifts.copy()
     frac[3, 0] += 0.5
     assert srb.plan((16, 1, 64, 64), s, psf, frac)["zlayout"] == 0
+    assert srb.plan((16, 1, 64, 64), s, psf, frac)["zt_frames"] == 0
+    far = np.concatenate([shifts, shifts + np.array([s, 0.0])])            # same phases, different shifts
+    assert srb.plan((32, 1, 64, 64), s, psf, far)["zt_frames"] == 0
+    assert srb.plan((32, 1, 64, 64), s, psf, np.concatenate([shifts, shifts]))["zt_frames"] == 2
+    assert srb.plan((20, 1, 64, 64), s, psf, np.concatenate([shifts, shifts[:4]]))["zt_frames"] == 0   # unequal counts
     assert srb.plan((16, 1, 64, 64), s, None, shifts)["zlayout"] == 0          # no PSF: nothing to gain
     assert srb.plan((4, 1, 64, 64), 2, wl.gaussian_psf(3, 0.8), wl.default_shifts(4, 2))["zlayout"] == 1
