@@ -51,6 +51,7 @@ if ROOT not in sys.path:
 METRIC = "MAP-solver gradient evaluations: HR px*frames*ch per second"
 UNIT = "HRpx*frames*ch/s"
 SOLVE_ITERS = 20
+REG_OVERRIDE = None   # --reg
 
 
 def parse_args():
@@ -67,6 +68,8 @@ def parse_args():
     ap.add_argument("--solve-iters", type=int, default=SOLVE_ITERS,
                     help="CG iterations of the timed device-resident solve (0 = skip)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement")
+    ap.add_argument("--reg", default=None, choices=["tv", "tv3d", "btv", "none"],
+                    help="regularizer instead of the configuration's own (cfg4 is also quoted with 3-D TV)")
     return ap.parse_args()
 
 
@@ -139,6 +142,8 @@ def _cpu_problem(cfg, side):
     cf = wl.CONFIGS[cfg]
     side = min(side, cf["H"])
     w = wl.make(cfg, H=side, W=side, cheap=True)
+    if REG_OVERRIDE is not None:
+        w["reg_kind"] = wl.REG_KIND[REG_OVERRIDE]
     m = sr_oracle.Model(w["s"], w["psf"], w["shifts"])
     obs = sr_oracle.upsample_observations(m, w["lr"])
     return wl, w, m, obs, side
@@ -245,7 +250,9 @@ def run_reference(args):
 
 
 def main():
+    global REG_OVERRIDE
     args = parse_args()
+    REG_OVERRIDE = args.reg
     if args.impl == "reference":
         run_reference(args)
         return
@@ -290,6 +297,8 @@ def main():
         eng = srb.Engine((len(frames), C, H // s, W // s), s, psf, shifts_all[frames], device=local_rank)
         work = wl.make(args.config, forward=lambda k, plane: eng.forward(frames.index(k), plane), N=n_total, frames=frames)
         eng.set_observations(work["lr"])
+        if args.reg is not None:
+            work["reg_kind"] = wl.REG_KIND[args.reg]
         eng.set_regularizer(work["reg_kind"], work["lam"], work["btv_range"], work["btv_decay"])
         eng.set_regularizer_rows(*sharding.row_band(H, rank, world))
         eng.set_path({"auto": srb.PATH_AUTO, "reference_order": srb.PATH_REFERENCE_ORDER,
@@ -397,7 +406,7 @@ def main():
                 full = wl.make(args.config, forward=lambda k, plane: gen.forward(k, plane), N=n_frames)
             with srb.MultiEngine((n_frames, C, H // s, W // s), s, psf, shifts_all, n_gpus=world) as me:
                 me.set_observations(full["lr"])
-                me.set_regularizer(full["reg_kind"], full["lam"], full["btv_range"], full["btv_decay"])
+                me.set_regularizer(work["reg_kind"], full["lam"], full["btv_range"], full["btv_decay"])
                 for _ in range(3):
                     me.eval(h_x.numpy(), out=h_g.numpy()[:n])
                 t0 = time.perf_counter()
@@ -465,7 +474,7 @@ def main():
             "metric": METRIC, "value": units / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cf["name"] + ("" if world == 1 else " -- its %d frames sharded over %d GPUs" % (n_frames, world)),
+            "config": {"workload": cf["name"] + ("" if args.reg is None else " [regularizer: %s]" % args.reg) + ("" if world == 1 else " -- its %d frames sharded over %d GPUs" % (n_frames, world)),
                        "frames_per_gpu": len(frames), "frames_total": n_frames,
                        "partition": partition, "kernel_path": path_name,
                        "l2": "inputs larger than L2 (%.0f MB touched per step vs 126 MB L2)" % (alg_bytes / 1e6),

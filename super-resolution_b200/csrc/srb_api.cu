@@ -97,8 +97,9 @@ srb_status eval_core(srb_ctx* c, const double* d_x, double* d_g, double* tail, b
 
   bool reg_done = false;
   if (resolve_path(c) == SRB_PATH_FUSED && data_term && !accumulate) {
-    // the tile kernel's finishing launch also closes the cost when nothing follows it
-    const bool last = !do_reg || c->reg_kind == SRB_REG_TV;
+    // the tile kernel's finishing launch also closes the cost when nothing follows it: the regularization term
+    // is evaluated inside the tile kernel (2-D TV) or by a tiled kernel right behind it (BTV, 3-D TV)
+    const bool last = !do_reg || fused_reg_covered(c);
     srb_status st = fused_eval(c, d_x, d_g, do_reg, last ? tail : nullptr, &reg_done);
     if (st != SRB_OK) return st;
     if (last) {
@@ -492,6 +493,7 @@ srb_status srb_set_regularizer(srb_ctx* c, int kind, double lambda, int btv_rang
     SRB_CUDA_CHECK(c, cudaMemcpy(c->d_decay, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     c->btv_R = btv_range;
     c->btv_decay = btv_decay;
+    c->decay_h = tab;
   }
   c->reg_kind = kind;
   c->lambda = lambda;
@@ -688,6 +690,7 @@ srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {
 
 // ---- hot path -----------------------------------------------------------------------------------
 static bool units_pipelined(const srb_ctx* c);
+static bool host_slices_ok(const srb_ctx* c);
 // srb_eval, pipelined: the estimate goes to the device in contiguous slices on a copy-in stream, the
 // tile kernel evaluates the units whose rows (and the halo rows of the next slice) have arrived, and
 // every finished gradient slice returns on a copy-out stream -- H2D, compute and D2H overlap, so the
@@ -750,7 +753,7 @@ srb_status srb_eval(srb_ctx* c, const double* x_host, double* g_host, double* co
   if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
   if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
-  if (units_pipelined(c) && c->pipe_chunks > 1) return eval_host_pipelined(c, x_host, g_host, cost);
+  if (units_pipelined(c) && host_slices_ok(c) && c->pipe_chunks > 1) return eval_host_pipelined(c, x_host, g_host, cost);
   const size_t bytes = c->n_active() * sizeof(double);
   cudaEventRecord(c->ev[0], c->stream);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -798,9 +801,12 @@ static bool units_pipelined(const srb_ctx* c) {
   // units need the tile kernel to be the only writer of the gradient: no border band, and a
   // regularizer that is fused (2-D TV) or absent
   const TileState* st = tile_state(c);
-  const bool reg_ok = !reg_active(c) || c->reg_kind == SRB_REG_TV;
+  const bool reg_ok = !reg_active(c) || fused_reg_covered(c);
   return resolve_path(c) == SRB_PATH_FUSED && st && !st->has_band && reg_ok;
 }
+// srb_eval / srb_multi_eval stream x to the device slice by slice in memory order; 3-D TV reads the next
+// channel's plane at the same rows, which has not arrived when a slice is evaluated
+static bool host_slices_ok(const srb_ctx* c) { return !(reg_active(c) && c->reg_kind == SRB_REG_TV3D); }
 
 srb_status srb_num_units(srb_ctx* c, int* num_units, int* rows_per_unit) {
   if (!c || !num_units) return SRB_ERR_INVALID;

@@ -78,6 +78,7 @@ struct srb_ctx {
   int btv_R = 3;
   double btv_decay = 0.5;
   double* d_decay = nullptr;  // [2R+1] std::pow(decay, i+j) computed on the host
+  std::vector<double> decay_h;  // the same table on the host (kernel parameter of k_btv_tile)
   double* d_w = nullptr;      // IRLS weights [Ct][H][W]
   int reg_row0 = 0, reg_row1 = 0;
   int path = SRB_PATH_AUTO;

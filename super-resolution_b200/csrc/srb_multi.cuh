@@ -147,6 +147,7 @@ inline srb_status multi_plan_bands(srb_multi* m) {
     static const int env_groups = getenv("SRB_MULTI_GROUPS") ? atoi(getenv("SRB_MULTI_GROUPS")) : 0;
     int ng = env_groups > 0 ? env_groups : 3;
     ng = std::max(1, std::min(std::min(ng, Ca), (int)srb_multi::kMaxGroups));
+    if (!host_slices_ok(c0)) ng = 1;  // 3-D TV couples the channels: the whole estimate before any evaluation
     m->ngroups = ng;
     auto first_elem = [&](int u) -> long long {
       if (u >= tr * Ca) return n;

@@ -14,6 +14,7 @@
 #include "srb_kernels_band.cuh"
 #include "srb_kernels_tile.cuh"
 #include "srb_kernels_tilez.cuh"
+#include "srb_kernels_regtile.cuh"
 
 namespace srb {
 
@@ -529,6 +530,44 @@ inline int tile_rows_per_channel(const srb_ctx* c) {
   return (c->g.H + TH - 1) / TH;
 }
 
+// Regularizers the fused path evaluates itself: 2-D TV inside the tile kernel, BTV (R <= 4) and 3-D TV by the
+// tiled kernels of srb_kernels_regtile.cuh right behind it.  Anything else runs the reference-order kernels
+// after the tile kernel (eval_core).
+inline bool fused_reg_covered(const srb_ctx* c) {
+  if (c->reg_kind == SRB_REG_TV) return true;
+  if (tile_height(c) != 32) return false;
+  return c->reg_kind == SRB_REG_TV3D || (c->reg_kind == SRB_REG_BTV && c->btv_R >= 1 && c->btv_R <= 4);
+}
+
+// BTV / 3-D TV term of units [unit_begin, unit_end): adds into the gradient rows the tile kernel has written.
+inline srb_status reg_tile_launch(srb_ctx* c, const double* d_x, double* d_g, bool do_reg, int unit_begin, int unit_end,
+                                  double* part_reg, bool* reg_done) {
+  if (!do_reg || c->reg_kind == SRB_REG_TV || !fused_reg_covered(c)) return SRB_OK;
+  const Geometry& G = c->g;
+  RegTileParams R;
+  R.H = G.H; R.W = G.W; R.Ca = c->Ca();
+  R.row0 = c->reg_row0; R.row1 = c->reg_row1;
+  R.unit_begin = unit_begin; R.tile_rows = tile_rows_per_channel(c);
+  R.x = d_x; R.w = c->d_w; R.g = d_g;
+  R.two_lambda = 2.0 * c->lambda;
+  for (int i = 0; i < 9; ++i) R.decay[i] = i < (int)c->decay_h.size() ? c->decay_h[i] : 0.0;
+  R.part_reg = part_reg;
+  const dim3 grid((G.W + FT_W - 1) / FT_W, unit_end - unit_begin, 1);
+  if (c->reg_kind == SRB_REG_TV3D) {
+    k_tv3d_tile<<<grid, 256, 0, c->stream>>>(R);
+  } else {
+    switch (c->btv_R) {
+      case 1: k_btv_tile<1><<<grid, 256, 0, c->stream>>>(R); break;
+      case 2: k_btv_tile<2><<<grid, 256, 0, c->stream>>>(R); break;
+      case 3: k_btv_tile<3><<<grid, 256, 0, c->stream>>>(R); break;
+      default: k_btv_tile<4><<<grid, 256, 0, c->stream>>>(R); break;
+    }
+  }
+  c->timing.kernel_launches += 1;
+  *reg_done = true;
+  return SRB_OK;
+}
+
 struct TileLayout {  // cost-partial slots of one evaluation
   size_t nblocks, nband;
   dim3 bgrid;
@@ -613,7 +652,7 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
     }
     if (zr == SRB_OK) {
       c->timing.kernel_launches += 1;
-      return SRB_OK;
+      return reg_tile_launch(c, d_x, d_g, do_reg, unit_begin, unit_end, P.part_reg, reg_done);
     }
     if (zr != SRB_ERR_STATE) return zr;
   }
@@ -632,7 +671,7 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
     }
     if (zr == SRB_OK) {
       c->timing.kernel_launches += 1;
-      return SRB_OK;
+      return reg_tile_launch(c, d_x, d_g, do_reg, unit_begin, unit_end, P.part_reg, reg_done);
     }
     if (zr != SRB_ERR_STATE) return zr;
   }
@@ -651,7 +690,7 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   }
   if (rc != SRB_OK) return rc;
   c->timing.kernel_launches += 1;
-  return SRB_OK;
+  return reg_tile_launch(c, d_x, d_g, do_reg, unit_begin, unit_end, P.part_reg, reg_done);
 }
 
 // After every unit has been evaluated: the border band (exact, reference order) and the cost.
