@@ -387,6 +387,7 @@ def main():
     # ---- end to end through the host-facing call ----------------------------------------------------------
     e_steps = max(3, min(args.steps, 20))
     cost = 0.0
+    e2e_frames = None
     e2e_api = "srb_eval"
     if world == 1:
         for _ in range(3):
@@ -397,22 +398,33 @@ def main():
             cost, _ = eng.eval(h_x.numpy(), out=h_g.numpy()[:n])
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
     else:
-        # ONE host thread drives all GPUs (srb_multi_eval); the other ranks wait on the CPU
-        e2e_api = "srb_multi_eval (one host thread, %d GPUs)" % world
+        # ONE host thread drives all GPUs (srb_multi_eval); the other ranks wait on the CPU.  Two partitions:
+        # rows (every device evaluates the whole objective on its HR row bands: no exchange, PCIe traffic and
+        # kernel work per device both 1/N) is what a host solver would use and is reported as `e2e`; the
+        # contract's frame shard is timed beside it as `e2e_frame_shard`.
+        e2e_api = "srb_multi_eval (one host thread, %d GPUs, row-band partition)" % world
         e2e_ms = 0.0
         if rank == 0:
             shifts_all = wl.default_shifts(n_frames, s)
             with srb.Engine((n_frames, C, H // s, W // s), s, psf, shifts_all, device=local_rank) as gen:
                 full = wl.make(args.config, forward=lambda k, plane: gen.forward(k, plane), N=n_frames)
-            with srb.MultiEngine((n_frames, C, H // s, W // s), s, psf, shifts_all, n_gpus=world) as me:
-                me.set_observations(full["lr"])
-                me.set_regularizer(work["reg_kind"], full["lam"], full["btv_range"], full["btv_decay"])
-                for _ in range(3):
-                    me.eval(h_x.numpy(), out=h_g.numpy()[:n])
-                t0 = time.perf_counter()
-                for _ in range(e_steps):
-                    cost, _ = me.eval(h_x.numpy(), out=h_g.numpy()[:n])
-                e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+            for part in (srb.PARTITION_FRAMES, srb.PARTITION_ROWS):
+                with srb.MultiEngine((n_frames, C, H // s, W // s), s, psf, shifts_all, n_gpus=world, partition=part) as me:
+                    me.set_observations(full["lr"])
+                    me.set_regularizer(work["reg_kind"], full["lam"], full["btv_range"], full["btv_decay"])
+                    for _ in range(3):
+                        me.eval(h_x.numpy(), out=h_g.numpy()[:n])
+                    t0 = time.perf_counter()
+                    for _ in range(e_steps):
+                        cost_p, _ = me.eval(h_x.numpy(), out=h_g.numpy()[:n])
+                    ms_p = (time.perf_counter() - t0) * 1e3 / e_steps
+                if part == srb.PARTITION_ROWS:
+                    e2e_ms, cost = ms_p, cost_p
+                else:
+                    e2e_frames = {"value": units / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p,
+                                  "api": "srb_multi_eval (one host thread, %d GPUs, frame shard + NVLink "
+                                         "all-gather / reduce-scatter)" % world,
+                                  "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": (n + 1) * 8, "cost_check": cost_p}
             del full
         torch.cuda.set_device(local_rank)   # rank 0 drove every GPU from this thread
         dist.barrier(group=cpu_group)
@@ -505,6 +517,8 @@ def main():
                                     frac_moved=moved / (kernel_ms * 1e-3) / 1e9 / peak)
         if solve is not None:
             line["solve"] = solve
+        if e2e_frames is not None:
+            line["e2e_frame_shard"] = e2e_frames
         if weak is not None:
             line["weak"] = weak
         if not args.no_cpu_baseline and world == 1:

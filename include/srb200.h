@@ -298,9 +298,24 @@ srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, uns
  * bands to their owners (the reduce-scatter), and device r returns its summed band of the gradient to the
  * host: host traffic per PCIe link is 1/G of srb_eval's.  devices = NULL means devices 0 .. n_gpus-1.  Pin
  * the host buffers with srb_pin_host.  Results equal srb_eval's up to fp64 re-association of the
- * cross-device sum (fixed device order: deterministic). */
+ * cross-device sum (fixed device order: deterministic).
+ *
+ * Partition.  SRB_PARTITION_FRAMES is the one described above (the contract partition of SURVEY 8e: the
+ * LR-frame axis).  Its exchange moves the whole gradient (C*H*W doubles) over NVLink per evaluation whatever the
+ * number of devices, and since the fused kernels apply the PSF once per evaluation, not once per frame, a
+ * device's kernel time barely drops with fewer frames.  SRB_PARTITION_ROWS cuts the HR image instead: every
+ * device holds every frame and evaluates the WHOLE objective on its HR row bands; device r fetches only its
+ * bands of x (plus the few halo rows the PSF and regularizer stencils reach) from the host and returns its
+ * bands of the gradient, which are final -- no exchange between the devices at all, and compute, H2D and D2H
+ * per device all drop by n_gpus.  Costs n_gpus copies of the observations in HBM (cfg3 100 MB, cfg5 1.6 GB
+ * per device).  Applies when the tile kernel covers the whole image (no border band of special samples) with
+ * a regularizer other than 3-D TV; otherwise device 0 evaluates alone.  srb_multi_create takes the partition
+ * from SRB_MULTI_PARTITION=frames|rows in the environment (default frames). */
+enum { SRB_PARTITION_FRAMES = 0, SRB_PARTITION_ROWS = 1 };
 typedef struct srb_multi srb_multi;
 srb_status srb_multi_create(const srb_model_desc* desc, int n_gpus, const int* devices, srb_multi** out);
+srb_status srb_multi_create_partitioned(const srb_model_desc* desc, int n_gpus, const int* devices, int partition,
+                                        srb_multi** out);
 void srb_multi_destroy(srb_multi* m);
 const char* srb_multi_last_error(const srb_multi* m);
 int srb_multi_num_gpus(const srb_multi* m);

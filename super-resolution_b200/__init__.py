@@ -10,5 +10,5 @@ the `srb200` alias module at the repository root.
 """
 from . import build, engine  # noqa: F401
 from .engine import (Engine, MultiEngine, SrbError, REG_NONE, REG_TV, REG_TV3D, REG_BTV, PATH_AUTO,  # noqa: F401
-                     PATH_REFERENCE_ORDER, PATH_FUSED, device_count, load_library, pin_host,
+                     PATH_REFERENCE_ORDER, PATH_FUSED, PARTITION_FRAMES, PARTITION_ROWS, device_count, load_library, pin_host,
                      unpin_host, plan, quantize_shift, sample_is_special, dev_alloc, dev_free, ipc_export, ipc_open, ipc_close)

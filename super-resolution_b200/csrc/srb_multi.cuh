@@ -20,6 +20,8 @@
 
 struct srb_multi {
   int G = 0;
+  int partition = SRB_PARTITION_FRAMES;  // SRB_PARTITION_FRAMES | SRB_PARTITION_ROWS
+  bool rows_ok = false;                  // rows partition: the current configuration can be cut into row bands
   std::vector<int> dev;
   std::vector<srb_ctx*> rank;
   std::vector<int> frame_begin;          // [G + 1]
@@ -170,7 +172,94 @@ inline srb_status multi_plan_bands(srb_multi* m) {
       m->band_elem[0][o] = o == G ? n : ((n * o / G) & ~1LL);
     }
   }
+  m->rows_ok = m->pipelined && host_slices_ok(c0);
   m->bands_valid = true;
+  return SRB_OK;
+}
+
+// HR rows of x that the tile kernel and the fused / tiled regularizers read around a gradient row: the PSF
+// twice (forward and adjoint pass), one row for TV, R for BTV.
+inline int multi_halo_rows(const srb_ctx* c) {
+  int reg = 0;
+  if (reg_active(c)) reg = c->reg_kind == SRB_REG_BTV ? c->btv_R : 1;
+  return 2 * c->g.hk + std::max(reg, 1);
+}
+
+// Rows partition (SRB_PARTITION_ROWS): every device holds every frame and evaluates the WHOLE objective on its
+// HR row bands -- the gradient band it produces is final, so there is no exchange between the devices at all:
+// device r fetches its bands of x (plus the halo rows the PSF / regularizer stencils reach) from the host over
+// its own PCIe link, runs the tile kernel on its units and returns its gradient bands; the host adds G partial
+// costs.  Per-device compute, H2D and D2H all drop by the number of devices.
+inline srb_status multi_eval_rows(srb_multi* m, const double* x_host, double* g_host, double* cost) {
+  const int G = m->G, NG = m->ngroups;
+  for (int r = 0; r < G; ++r) {
+    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t0[r], m->rank[r]->s_in));
+  }
+  for (int g = 0; g < NG; ++g) {
+    const long long* be = m->band_elem[g];
+    for (int r = 0; r < G; ++r) {
+      srb_ctx* c = m->rank[r];
+      SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+      const bool have = m->band_unit[g][r + 1] > m->band_unit[g][r];
+      if (have) {
+        // band + halo, clipped to the channels the band touches (no stencil crosses a channel boundary)
+        const long long P = (long long)c->P, W = c->g.W, halo = (long long)multi_halo_rows(c) * W;
+        const long long lo = std::max(be[r] - halo, be[r] / P * P);
+        const long long hi = std::min(be[r + 1] + halo, (be[r + 1] + P - 1) / P * P);
+        SRB_MULTI_CHECK(m, cudaMemcpyAsync(c->d_x + lo, x_host + lo, (size_t)(hi - lo) * sizeof(double),
+                                           cudaMemcpyHostToDevice, c->s_in));
+      }
+      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_h2d[g][r], c->s_in));
+      SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->stream, m->ev_h2d[g][r], 0));
+      if (g == 0) {
+        // only this device's units write their cost slots: the others must read as zero
+        const TileLayout L = tile_layout(c);
+        const size_t need = 2 * L.nblocks + L.nband;
+        if (need > c->partial_capacity) {
+          if (c->d_partial) cudaFree(c->d_partial);
+          c->d_partial = nullptr;
+          c->partial_capacity = 0;
+          SRB_MULTI_CHECK(m, cudaMalloc((void**)&c->d_partial, need * sizeof(double)));
+          c->partial_capacity = need;
+        }
+        SRB_MULTI_CHECK(m, cudaMemsetAsync(c->d_partial, 0, need * sizeof(double), c->stream));
+      }
+      if (have) {
+        const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
+        bool reg_done = false;
+        srb_status st = fused_eval_units(c, c->d_x, g_host ? c->d_grad : nullptr, do_reg, m->band_unit[g][r],
+                                         m->band_unit[g][r + 1], &reg_done);
+        if (st != SRB_OK) return multi_status(m, r, st);
+      }
+      if (g == NG - 1) {
+        srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr);
+        if (st != SRB_OK) return multi_status(m, r, st);
+        c->timing.num_evals += 1;
+        SRB_MULTI_CHECK(m, cudaMemcpyAsync(m->h_cost[r], c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      }
+      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_part[g][r], c->stream));
+      if (g_host && have) {
+        SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->s_out, m->ev_part[g][r], 0));
+        SRB_MULTI_CHECK(m, cudaMemcpyAsync(g_host + be[r], c->d_grad + be[r], (size_t)(be[r + 1] - be[r]) * sizeof(double),
+                                           cudaMemcpyDeviceToHost, c->s_out));
+      }
+      c->x_resident = false;  // only this device's bands of x are here
+    }
+  }
+  double total = 0.0;
+  for (int r = 0; r < G; ++r) {
+    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
+    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t1[r], m->rank[r]->s_out));
+    SRB_MULTI_CHECK(m, cudaStreamSynchronize(m->rank[r]->s_out));
+    SRB_MULTI_CHECK(m, cudaStreamSynchronize(m->rank[r]->stream));
+    total += m->h_cost[r][2];  // fixed device order
+  }
+  if (cost) *cost = total;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, m->ev_t0[0], m->ev_t1[0]) == cudaSuccess) m->last_ms[5] = ms;
+  (void)cudaGetLastError();
+  m->timing.num_evals += 1;
   return SRB_OK;
 }
 
@@ -199,6 +288,13 @@ void srb_multi_destroy(srb_multi* m) {
 }
 
 srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devices, srb_multi** out) {
+  int partition = SRB_PARTITION_FRAMES;
+  if (const char* e = getenv("SRB_MULTI_PARTITION")) partition = (e[0] == 'r' || e[0] == '1') ? SRB_PARTITION_ROWS : SRB_PARTITION_FRAMES;
+  return srb_multi_create_partitioned(d, n_gpus, devices, partition, out);
+}
+
+srb_status srb_multi_create_partitioned(const srb_model_desc* d, int n_gpus, const int* devices, int partition,
+                                        srb_multi** out) {
   if (!out) return SRB_ERR_INVALID;
   srb::DeviceRestore restore_device;
   *out = nullptr;
@@ -208,6 +304,8 @@ srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devi
   if (!d) return m->fail(SRB_ERR_INVALID, "null model description");
   if (n_gpus < 1 || n_gpus > SRB_MAX_PEERS) return m->fail(SRB_ERR_INVALID, "number of GPUs must be 1..8");
   if (d->num_frames <= 0) return m->fail(SRB_ERR_INVALID, "cannot solve with 0 observations");  // map_solver.cpp:56-57
+  if (partition != SRB_PARTITION_FRAMES && partition != SRB_PARTITION_ROWS) return m->fail(SRB_ERR_INVALID, "unknown partition");
+  m->partition = partition;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     (void)cudaGetLastError();
@@ -252,8 +350,10 @@ srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devi
   }
   for (int r = 0; r < n_gpus; ++r) {
     srb_model_desc dr = m->desc;
-    dr.num_frames = m->frame_begin[r + 1] - m->frame_begin[r];
-    dr.shifts = m->desc.shifts ? m->desc.shifts + (size_t)2 * m->frame_begin[r] : nullptr;
+    if (m->partition == SRB_PARTITION_FRAMES) {
+      dr.num_frames = m->frame_begin[r + 1] - m->frame_begin[r];
+      dr.shifts = m->desc.shifts ? m->desc.shifts + (size_t)2 * m->frame_begin[r] : nullptr;
+    }  // rows: every device holds every frame and evaluates its HR row bands of the whole objective
     srb_status st = srb_create_shard(&dr, m->dev[r], &m->rank[r]);
     if (st != SRB_OK) {
       m->err = std::string("device ") + std::to_string(m->dev[r]) + ": " + (m->rank[r] ? m->rank[r]->err : "out of memory");
@@ -261,9 +361,10 @@ srb_status srb_multi_create(const srb_model_desc* d, int n_gpus, const int* devi
     }
     const int H = m->rank[r]->g.H;
     const int band = (H + n_gpus - 1) / n_gpus;
-    srb_set_regularizer_rows(m->rank[r], std::min(H, r * band), std::min(H, (r + 1) * band));
+    if (m->partition == SRB_PARTITION_FRAMES)
+      srb_set_regularizer_rows(m->rank[r], std::min(H, r * band), std::min(H, (r + 1) * band));
     SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-    for (int q = 0; q < n_gpus; ++q) {
+    for (int q = 0; q < n_gpus && m->partition == SRB_PARTITION_FRAMES; ++q) {  // (rows: no device reads another's memory)
       if (q == r) continue;
       int can = 0;
       SRB_MULTI_CHECK(m, cudaDeviceCanAccessPeer(&can, m->dev[r], m->dev[q]));
@@ -293,7 +394,8 @@ srb_status srb_multi_set_observations(srb_multi* m, const double* lr_host) {
   if (!lr_host) return m->fail(SRB_ERR_INVALID, "null observations");
   const size_t per_frame = (size_t)m->desc.num_channels * m->lr_plane;
   for (int r = 0; r < m->G; ++r) {
-    srb_status st = srb_set_observations(m->rank[r], lr_host + (size_t)m->frame_begin[r] * per_frame);
+    const size_t first = m->partition == SRB_PARTITION_FRAMES ? (size_t)m->frame_begin[r] : 0;
+    srb_status st = srb_set_observations(m->rank[r], lr_host + first * per_frame);
     if (st != SRB_OK) return srb::multi_status(m, r, st);
   }
   m->bands_valid = false;
@@ -382,6 +484,12 @@ srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* g_host, do
   if (!m->bands_valid) {
     srb_status st = multi_plan_bands(m);
     if (st != SRB_OK) return st;
+  }
+  if (m->partition == SRB_PARTITION_ROWS) {
+    if (m->rows_ok) return multi_eval_rows(m, x_host, g_host, cost);
+    // a configuration that cannot be cut into row bands (border band of special samples, 3-D TV, a model the
+    // tile kernel does not cover): every device holds the whole model, so device 0 evaluates it alone
+    return multi_status(m, 0, srb_eval(m->rank[0], x_host, g_host, cost));
   }
   const int NG = m->ngroups;
   MultiPtrs X, Gp;

@@ -16,6 +16,7 @@ _ctx_p = C.c_void_p
 
 REG_NONE, REG_TV, REG_TV3D, REG_BTV = -1, 0, 1, 2
 PATH_AUTO, PATH_REFERENCE_ORDER, PATH_FUSED = 0, 1, 2
+PARTITION_FRAMES, PARTITION_ROWS = 0, 1
 _STATUS = {0: "SRB_OK", 1: "SRB_ERR_INVALID", 2: "SRB_ERR_CUDA", 3: "SRB_ERR_GEOMETRY",
            4: "SRB_ERR_STATE", 5: "SRB_ERR_NOMEM"}
 
@@ -82,6 +83,7 @@ SIGNATURES = {
     "srb_get_timing": (C.c_int, [_ctx_p, C.c_void_p]),
     # single-process multi-GPU form
     "srb_multi_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_ctx_p)]),
+    "srb_multi_create_partitioned": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(_ctx_p)]),
     "srb_multi_destroy": (None, [_ctx_p]),
     "srb_multi_last_error": (C.c_char_p, [_ctx_p]),
     "srb_multi_num_gpus": (C.c_int, [_ctx_p]),
@@ -485,7 +487,10 @@ class MultiEngine:
     blocks, x and IRLS weights replicated, regularizer split by row bands) behind the call shape of
     `Engine.eval` -- what the reference's single-threaded solver would hold."""
 
-    def __init__(self, lr_shape, scale, psf=None, shifts=None, n_gpus=1, devices=None, shard_frames=None):
+    def __init__(self, lr_shape, scale, psf=None, shifts=None, n_gpus=1, devices=None, partition=None):
+        """partition: PARTITION_FRAMES (the contract partition: frames sharded, gradient summed over NVLink),
+        PARTITION_ROWS (every device evaluates the whole objective on its HR row bands, no exchange), or None =
+        srb_multi_create's choice (SRB_MULTI_PARTITION in the environment, default frames)."""
         self._lib = load_library()
         self._ctx = _ctx_p()
         N, Cn, h, w = (int(v) for v in lr_shape)
@@ -499,7 +504,10 @@ class MultiEngine:
                          None if self._psf is None else self._psf.ctypes.data_as(_dp),
                          None if self._shifts is None else self._shifts.ctypes.data_as(_dp))
         dev = None if devices is None else (C.c_int * self.n_gpus)(*[int(d) for d in devices])
-        st = self._lib.srb_multi_create(C.byref(desc), self.n_gpus, dev, C.byref(self._ctx))
+        if partition is None:
+            st = self._lib.srb_multi_create(C.byref(desc), self.n_gpus, dev, C.byref(self._ctx))
+        else:
+            st = self._lib.srb_multi_create_partitioned(C.byref(desc), self.n_gpus, dev, int(partition), C.byref(self._ctx))
         if st != 0:
             msg = self._lib.srb_multi_last_error(self._ctx).decode() if self._ctx else "allocation failed"
             if self._ctx:

@@ -43,14 +43,20 @@ CASES = [
     (9, 4, 5, 1.2, 1, 40, 64, "btv", False),    # cfg2's model: BTV is not fused -> unpipelined exchange
     (8, 2, 5, 1.0, 3, 40, 64, "tv3d", False),   # cfg4's model: two frames per phase, 3-D TV
     (6, 2, 3, 0.8, 1, 64, 96, "none", True),    # fractional shifts, no regularizer
+    (16, 4, 7, 1.5, 3, 72, 80, "btv", False),   # no border band + BTV (tiled kernel): pipelined in both partitions
+    (32, 4, 5, 1.2, 2, 64, 64, "tv", False),    # two frames per phase (merged at upload in the rows partition)
 ]
 
 
+@pytest.mark.parametrize("partition", ["frames", "rows"])
 @pytest.mark.parametrize("G", [1, 2, 4, 8])
 @pytest.mark.parametrize("N,s,K,sigma,C,h,w,reg,frac", CASES)
-def test_multi_eval_matches_oracle_and_single_device(srb, oracle, G, N, s, K, sigma, C, h, w, reg, frac):
+def test_multi_eval_matches_oracle_and_single_device(srb, oracle, G, N, s, K, sigma, C, h, w, reg, frac, partition):
+    """partition = rows: every device holds every frame and evaluates the whole objective on its HR row bands
+    (no exchange); configurations that cannot be cut into row bands are evaluated by device 0 alone."""
     if srb.device_count() < G:
         pytest.skip("needs %d GPUs" % G)
+    part = srb.PARTITION_ROWS if partition == "rows" else srb.PARTITION_FRAMES
     psf, shifts, lr, x, wts = _case(N, s, K, sigma, C, h, w, seed=100 + N + K, frac=frac)
     kind = {"tv": srb.REG_TV, "tv3d": srb.REG_TV3D, "btv": srb.REG_BTV, "none": srb.REG_NONE}[reg]
     okind = {"tv": oracle.REG_TV, "tv3d": oracle.REG_TV3D, "btv": oracle.REG_BTV, "none": oracle.REG_TV}[reg]
@@ -58,7 +64,8 @@ def test_multi_eval_matches_oracle_and_single_device(srb, oracle, G, N, s, K, si
     m = oracle.Model(s, psf, shifts)
     obs = oracle.upsample_observations(m, lr)
     cost_ref, g_ref = oracle.evaluate(m, x, obs, okind, lam, wts if lam > 0 else None)
-    with srb.MultiEngine(lr.shape, s, psf, shifts, n_gpus=G) as me, srb.Engine(lr.shape, s, psf, shifts) as e1:
+    with srb.MultiEngine(lr.shape, s, psf, shifts, n_gpus=G, partition=part) as me, \
+            srb.Engine(lr.shape, s, psf, shifts) as e1:
         for e in (me, e1):
             e.set_observations(lr)
             e.set_regularizer(kind, lam)
