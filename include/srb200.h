@@ -363,6 +363,94 @@ srb_status srb_forward_all(srb_ctx* ctx, const double* hr_host, double* lr_out_h
 srb_status srb_transpose(srb_ctx* ctx, int frame, const double* lr_host, int h, int w,
                          double* hr_out_host);
 
+/* ---- the steps either side of the hot path (N2 data generation, N3 initial estimate +
+ * scores, N4 hyperspectral front end) -- on the device, behind the same boundary ----------------------------- */
+
+/* ImageData::ResizeImage(size, INTERPOLATE_LINEAR) (image_data.cpp:310-350: cv::resize INTER_LINEAR per channel)
+ * for a planar image src [C][h][w] -> dst [C][H][W].  OpenCV's sampling geometry (half-pixel centres, clamped at the
+ * borders), rows interpolated horizontally then vertically, every product and sum rounded separately.  OpenCV's
+ * own build evaluates its coefficient tables partly in float; results agree with cv2 to 1 ulp for power-of-two
+ * scale factors and to ~3e-7 otherwise (tests/test_frontend_oracle.py pins the oracle against cv2 fixtures). */
+srb_status srb_resize_linear(srb_ctx* ctx, const double* src_host, int num_channels, int h, int w, int H, int W,
+                             double* dst_host);
+/* The solver's initial estimate (super_resolution.cpp:368-373): LR observation `frame` (0 in the reference) of
+ * the active channel range, upsampled bilinearly to the HR size; needs srb_set_observations.  The _dev form
+ * writes (c1-c0)*H*W doubles on the device, stream-ordered: srb_cg_minimize_dev can follow directly. */
+srb_status srb_initial_estimate(srb_ctx* ctx, int frame, double* x_host_out);
+srb_status srb_initial_estimate_dev(srb_ctx* ctx, int frame, double* x_dev_out);
+/* PeakSignalToNoiseRatioEvaluator::Evaluate (peak_signal_to_noise_ratio.cpp:11-54; peak value 1.0, +inf for
+ * identical images) and StructuralSimilarityEvaluator::Evaluate (structural_similarity.cpp:9-103: the GLOBAL
+ * mean / variance / covariance form; the reference's defaults are k1 = 0.01, k2 = 0.03, image_scale = 1) of
+ * `image` against `truth`, n = channels * pixels doubles each (both must have the same size: the reference's
+ * resize branch resizes an image to its own size, i.e. does nothing).  psnr / ssim may be NULL. */
+srb_status srb_score(srb_ctx* ctx, const double* image_host, const double* truth_host, unsigned long long n,
+                     double k1, double k2, double image_scale, double* psnr, double* ssim);
+srb_status srb_score_dev(srb_ctx* ctx, const double* image_dev, const double* truth_dev, unsigned long long n,
+                         double k1, double k2, double image_scale, double* psnr, double* ssim);
+
+/* AdditiveNoiseModule::ApplyToImage (additive_noise_module.cpp:19-36): data[i] += N(0, (sigma / 255)^2).  The
+ * reference draws from cv::randn on OpenCV's process-global generator, which the program never seeds: its noise
+ * has no values to reproduce, only a distribution.  Here the samples come from Philox4x32-10 (counter = sample
+ * index / 4 and stream_id, key = seed) through Box-Muller: deterministic for a (seed, stream_id) pair and
+ * independent of the launch geometry.  sigma must be positive (additive_noise_module.cpp:15-17). */
+srb_status srb_add_noise(srb_ctx* ctx, double* data_host_inout, unsigned long long n, double sigma,
+                         unsigned long long seed, unsigned long long stream_id);
+srb_status srb_add_noise_dev(srb_ctx* ctx, double* data_dev_inout, unsigned long long n, double sigma,
+                             unsigned long long seed, unsigned long long stream_id);
+/* ImageModel::ApplyToImage(image, k) for every frame k with the noise module last (image_model.cpp:76-84, what
+ * generate_data.cpp:118-127 and super_resolution.cpp:286-311 loop over): the LR stack [num_frames][C][h][w] of the
+ * HR image [C][H][W] given on the host OR on the device (the other pointer NULL); noise_sigma = 0 leaves the
+ * noise module out.  lr_out_host may be NULL; keep_as_observations != 0 makes the stack the context's
+ * observations without a round trip through the host (srb_set_observations_dev is implied). */
+srb_status srb_generate_observations(srb_ctx* ctx, const double* hr_host, const double* hr_dev, double noise_sigma,
+                                     unsigned long long seed, double* lr_out_host, int keep_as_observations);
+
+/* ENVI header / HSI configuration (HSIBinaryDataParameters, hyperspectral_data_loader.h; ReadHeaderFromFile,
+ * hyperspectral_data_loader.cpp:226-270 -- "samples" is stored as the row count and "lines" as the column count,
+ * as the reference does). */
+typedef struct {
+  int interleave_bsq;   /* 1 = band sequential (the only supported interleave) */
+  int data_type;        /* ENVI data type code; 4 = float32 (the only supported type) */
+  int big_endian;       /* "byte order = 1" */
+  int header_offset;    /* bytes before the first sample (ENVI convention).  Every file the reference ships or
+                           writes has 0; for other values the reference's reader scales the offset by the
+                           sample size for the first run and then drops it (:85-101), which is not reproduced */
+  int num_data_rows, num_data_cols, num_data_bands;
+} srb_envi_header;
+srb_status srb_envi_read_header(const char* header_path, srb_envi_header* out);
+/* ReadBinaryFileBSQ<float> (hyperspectral_data_loader.cpp:68-118): rows [r0, r1), columns [c0, c1), bands
+ * [b0, b1) of a float32 BSQ file as planar doubles [b1-b0][r1-r0][c1-c0].  The selected rows are read in one
+ * run per band into pinned memory and copied to the device while the next band is read; byte swap, column
+ * crop and float -> double conversion run on the device.  _dev leaves the image in device memory. */
+srb_status srb_envi_read(srb_ctx* ctx, const char* data_path, const srb_envi_header* header, int r0, int r1, int c0,
+                         int c1, int b0, int b1, double* image_out_host);
+srb_status srb_envi_read_dev(srb_ctx* ctx, const char* data_path, const srb_envi_header* header, int r0, int r1,
+                             int c0, int c1, int b0, int b1, double* image_out_dev);
+/* WriteBinaryFileBSQ<float> (hyperspectral_data_loader.cpp:120-196): float32 BSQ in machine byte order plus
+ * `path`.hdr and `path`.config with the reference's keys.  Host only. */
+srb_status srb_envi_write(const char* data_path, const double* image_host, int num_bands, int num_rows, int num_cols);
+
+/* SpectralPCA (spectral_pca.cpp:155-199): cv::PCA (data as rows) trained on 10 * num_bands pixel vectors
+ * sub-sampled from the images at a fixed stride (GetPCAInputData, :27-96); images_host[i] is [num_bands][num_pixels].
+ * num_pca_bands > 0 keeps that many components; num_pca_bands = 0 applies cv::PCA's retained-variance rule: the
+ * leading components up to, not including, the one whose cumulative eigenvalue share first exceeds
+ * `retained_variance`, and at least 2.  Training is a num_bands x num_bands host problem (mean,
+ * covariance, cyclic Jacobi); eigenvectors are defined up to sign, as with cv::PCA.  Host only. */
+typedef struct srb_pca srb_pca;
+srb_status srb_pca_create(const double* const* images_host, int num_images, int num_bands, unsigned long long num_pixels,
+                          int num_pca_bands, double retained_variance, srb_pca** out);
+void srb_pca_destroy(srb_pca* pca);
+int srb_pca_num_components(const srb_pca* pca);
+int srb_pca_num_bands(const srb_pca* pca);
+/* mean [num_bands], eigenvectors [num_components][num_bands] (rows), eigenvalues [num_components]; any may be NULL */
+srb_status srb_pca_get(const srb_pca* pca, double* mean_out, double* eigenvectors_out, double* eigenvalues_out);
+/* SpectralPCA::GetPCAImage / ReconstructImage (spectral_pca.cpp:98-153, 175-197: pca.project / pca.backProject per
+ * pixel): [num_bands][P] -> [num_components][P] and back, one thread per pixel on the device. */
+srb_status srb_pca_project(srb_ctx* ctx, const srb_pca* pca, const double* image_host, unsigned long long num_pixels,
+                           double* pca_image_out_host);
+srb_status srb_pca_reconstruct(srb_ctx* ctx, const srb_pca* pca, const double* pca_image_host,
+                               unsigned long long num_pixels, double* image_out_host);
+
 /* ---- plumbing --------------------------------------------------------------------------- */
 /* Page-locks a caller buffer (e.g. ALGLIB's x / g arrays) so H2D/D2H run at full PCIe rate. */
 srb_status srb_pin_host(void* ptr, unsigned long long bytes);

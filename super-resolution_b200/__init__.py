@@ -9,6 +9,6 @@ the `srb200` alias module at the repository root.
   build       in-tree nvcc build of that library (sm_100a)
 """
 from . import build, engine  # noqa: F401
-from .engine import (Engine, MultiEngine, SrbError, REG_NONE, REG_TV, REG_TV3D, REG_BTV, PATH_AUTO,  # noqa: F401
+from .engine import (Engine, MultiEngine, SrbError, SpectralPCA, EnviHeader, envi_read_header, envi_write, REG_NONE, REG_TV, REG_TV3D, REG_BTV, PATH_AUTO,  # noqa: F401
                      PATH_REFERENCE_ORDER, PATH_FUSED, PARTITION_FRAMES, PARTITION_ROWS, device_count, load_library, pin_host,
                      unpin_host, plan, quantize_shift, sample_is_special, dev_alloc, dev_free, ipc_export, ipc_open, ipc_close)

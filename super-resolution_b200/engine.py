@@ -81,6 +81,26 @@ SIGNATURES = {
     "srb_dev_gradient": (C.c_void_p, [_ctx_p]),
     "srb_synchronize": (C.c_int, [_ctx_p]),
     "srb_get_timing": (C.c_int, [_ctx_p, C.c_void_p]),
+    # steps either side of the hot path
+    "srb_resize_linear": (C.c_int, [_ctx_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "srb_initial_estimate": (C.c_int, [_ctx_p, C.c_int, C.c_void_p]),
+    "srb_initial_estimate_dev": (C.c_int, [_ctx_p, C.c_int, C.c_void_p]),
+    "srb_score": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_double, C.c_double, C.c_double, _dp, _dp]),
+    "srb_score_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_double, C.c_double, C.c_double, _dp, _dp]),
+    "srb_add_noise": (C.c_int, [_ctx_p, C.c_void_p, C.c_ulonglong, C.c_double, C.c_ulonglong, C.c_ulonglong]),
+    "srb_add_noise_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_ulonglong, C.c_double, C.c_ulonglong, C.c_ulonglong]),
+    "srb_generate_observations": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_double, C.c_ulonglong, C.c_void_p, C.c_int]),
+    "srb_envi_read_header": (C.c_int, [C.c_char_p, C.c_void_p]),
+    "srb_envi_read": (C.c_int, [_ctx_p, C.c_char_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "srb_envi_read_dev": (C.c_int, [_ctx_p, C.c_char_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "srb_envi_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "srb_pca_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_ulonglong, C.c_int, C.c_double, C.POINTER(_ctx_p)]),
+    "srb_pca_destroy": (None, [_ctx_p]),
+    "srb_pca_num_components": (C.c_int, [_ctx_p]),
+    "srb_pca_num_bands": (C.c_int, [_ctx_p]),
+    "srb_pca_get": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_pca_project": (C.c_int, [_ctx_p, _ctx_p, C.c_void_p, C.c_ulonglong, C.c_void_p]),
+    "srb_pca_reconstruct": (C.c_int, [_ctx_p, _ctx_p, C.c_void_p, C.c_ulonglong, C.c_void_p]),
     # single-process multi-GPU form
     "srb_multi_create": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_ctx_p)]),
     "srb_multi_create_partitioned": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(_ctx_p)]),
@@ -103,6 +123,13 @@ class ModelDesc(C.Structure):
     _fields_ = [("lr_height", C.c_int), ("lr_width", C.c_int), ("num_channels", C.c_int),
                 ("num_frames", C.c_int), ("scale", C.c_int), ("psf_size", C.c_int),
                 ("psf", _dp), ("shifts", _dp)]
+
+
+class EnviHeader(C.Structure):
+    """srb_envi_header (HSIBinaryDataParameters, hyperspectral_data_loader.h)."""
+    _fields_ = [("interleave_bsq", C.c_int), ("data_type", C.c_int), ("big_endian", C.c_int),
+                ("header_offset", C.c_int), ("num_data_rows", C.c_int), ("num_data_cols", C.c_int),
+                ("num_data_bands", C.c_int)]
 
 
 class Timing(C.Structure):
@@ -463,6 +490,89 @@ class Engine:
         self._check(self._lib.srb_transpose(self._ctx, int(k), _host_ptr(lr), h, w, _host_ptr(out)))
         return out
 
+    # -- the steps either side of the hot path
+    def resize_linear(self, src, H, W):
+        """ImageData::ResizeImage(size, INTERPOLATE_LINEAR): [C][h][w] -> [C][H][W]."""
+        src = _f64(src)
+        Cn, h, w = src.shape
+        out = np.empty((Cn, int(H), int(W)))
+        self._check(self._lib.srb_resize_linear(self._ctx, _host_ptr(src), Cn, h, w, int(H), int(W), _host_ptr(out)))
+        return out
+
+    def initial_estimate(self, frame=0):
+        """Bilinear upsampling of LR observation `frame` of the active channel range (super_resolution.cpp:368-373)."""
+        out = np.empty((self.c1 - self.c0, self.H, self.W))
+        self._check(self._lib.srb_initial_estimate(self._ctx, int(frame), _host_ptr(out)))
+        return out
+
+    def initial_estimate_dev(self, x_dev, frame=0):
+        self._check(self._lib.srb_initial_estimate_dev(self._ctx, int(frame), _dev_ptr(x_dev)))
+
+    def score(self, image, truth, k1=0.01, k2=0.03, image_scale=1.0):
+        """(PSNR, SSIM) of `image` against `truth` (src/evaluation); host arrays or torch CUDA tensors."""
+        psnr, ssim = C.c_double(), C.c_double()
+        if hasattr(image, "is_cuda"):
+            n = image.numel()
+            assert truth.numel() == n
+            self._check(self._lib.srb_score_dev(self._ctx, _dev_ptr(image), _dev_ptr(truth), n, k1, k2, image_scale,
+                                                C.byref(psnr), C.byref(ssim)))
+        else:
+            a, b = _f64(image).reshape(-1), _f64(truth).reshape(-1)
+            assert a.size == b.size
+            self._check(self._lib.srb_score(self._ctx, _host_ptr(a), _host_ptr(b), a.size, k1, k2, image_scale,
+                                            C.byref(psnr), C.byref(ssim)))
+        return psnr.value, ssim.value
+
+    def add_noise(self, data, sigma, seed=0, stream_id=0):
+        """AdditiveNoiseModule::ApplyToImage: returns data + N(0, (sigma/255)^2), Philox4x32-10 counter-based."""
+        out = np.array(_f64(data), copy=True)
+        self._check(self._lib.srb_add_noise(self._ctx, _host_ptr(out.reshape(-1)), out.size, float(sigma), int(seed),
+                                            int(stream_id)))
+        return out
+
+    def generate_observations(self, hr, noise_sigma=0.0, seed=0, keep=True, want_lr=True):
+        """The whole LR stack of an HR image through the image model (+ noise), optionally kept as the context's
+        observations.  hr: host array [C][H][W] or torch CUDA tensor."""
+        out = np.empty((self.N, self.C, self.h, self.w)) if want_lr else None
+        if hasattr(hr, "is_cuda"):
+            assert tuple(hr.shape) == (self.C, self.H, self.W)
+            hp, dp = None, _dev_ptr(hr)
+        else:
+            hr = _f64(hr)
+            assert hr.shape == (self.C, self.H, self.W), hr.shape
+            hp, dp = _host_ptr(hr), None
+        self._check(self._lib.srb_generate_observations(self._ctx, hp, dp, float(noise_sigma), int(seed), _host_ptr(out),
+                                                        1 if keep else 0))
+        return out
+
+    def envi_read(self, data_path, header, rows=None, cols=None, bands=None):
+        """ReadBinaryFileBSQ<float>: the selected range of a float32 BSQ file as [bands][rows][cols] doubles."""
+        r0, r1 = rows if rows is not None else (0, header.num_data_rows)
+        c0, c1 = cols if cols is not None else (0, header.num_data_cols)
+        b0, b1 = bands if bands is not None else (0, header.num_data_bands)
+        out = np.empty((max(b1 - b0, 0), max(r1 - r0, 0), max(c1 - c0, 0)))
+        self._check(self._lib.srb_envi_read(self._ctx, os.fsencode(data_path), C.byref(header), int(r0), int(r1), int(c0),
+                                            int(c1), int(b0), int(b1), _host_ptr(out)))
+        return out
+
+    def pca_project(self, pca, image):
+        """SpectralPCA::GetPCAImage: [C][...] -> [k][...]."""
+        image = _f64(image)
+        assert image.shape[0] == pca.num_bands
+        P = int(np.prod(image.shape[1:]))
+        out = np.empty((pca.num_components,) + image.shape[1:])
+        self._check(self._lib.srb_pca_project(self._ctx, pca._p, _host_ptr(image), P, _host_ptr(out)))
+        return out
+
+    def pca_reconstruct(self, pca, pca_image):
+        """SpectralPCA::ReconstructImage: [k][...] -> [C][...]."""
+        pca_image = _f64(pca_image)
+        assert pca_image.shape[0] == pca.num_components
+        P = int(np.prod(pca_image.shape[1:]))
+        out = np.empty((pca.num_bands,) + pca_image.shape[1:])
+        self._check(self._lib.srb_pca_reconstruct(self._ctx, pca._p, _host_ptr(pca_image), P, _host_ptr(out)))
+        return out
+
     # -- plumbing
     def stream_handle(self):
         return self._lib.srb_stream(self._ctx)
@@ -583,6 +693,62 @@ class MultiEngine:
         t = Timing()
         self._check(self._lib.srb_multi_get_timing(self._ctx, C.byref(t)))
         return {name: getattr(t, name) for name, _ in Timing._fields_}
+
+
+class SpectralPCA:
+    """srb_pca: SpectralPCA's basis (spectral_pca.cpp:155-173), trained on the host from sub-sampled pixel vectors.
+    images: list of [C][...] arrays of one shape.  num_pca_bands > 0, or retained_variance in (0, 1]."""
+
+    def __init__(self, images, num_pca_bands=0, retained_variance=0.0):
+        self._lib = load_library()
+        imgs = [_f64(im) for im in images]
+        if not imgs:
+            raise SrbError(1, "at least one image is required to compute the PCA basis")
+        Cn = imgs[0].shape[0]
+        P = int(np.prod(imgs[0].shape[1:]))
+        for im in imgs:
+            if im.shape != imgs[0].shape:
+                raise SrbError(1, "inconsistent image shapes")
+        ptrs = (C.c_void_p * len(imgs))(*[im.ctypes.data for im in imgs])
+        self._p = _ctx_p()
+        st = self._lib.srb_pca_create(ptrs, len(imgs), Cn, P, int(num_pca_bands), float(retained_variance), C.byref(self._p))
+        if st != 0:
+            raise SrbError(st, "invalid SpectralPCA arguments")
+        self.num_bands = self._lib.srb_pca_num_bands(self._p)
+        self.num_components = self._lib.srb_pca_num_components(self._p)
+        self.mean = np.empty(self.num_bands)
+        self.eigenvectors = np.empty((self.num_components, self.num_bands))
+        self.eigenvalues = np.empty(self.num_components)
+        self._lib.srb_pca_get(self._p, _host_ptr(self.mean), _host_ptr(self.eigenvectors), _host_ptr(self.eigenvalues))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._lib.srb_pca_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def envi_read_header(path):
+    """HSIBinaryDataParameters::ReadHeaderFromFile: parses an ENVI .hdr (host only)."""
+    h = EnviHeader()
+    st = load_library().srb_envi_read_header(os.fsencode(path), C.byref(h))
+    if st != 0:
+        raise SrbError(st, "could not read ENVI header '%s'" % path)
+    return h
+
+
+def envi_write(path, image):
+    """WriteBinaryFileBSQ<float> + .hdr + .config (host only).  image: [bands][rows][cols]."""
+    image = _f64(image)
+    b, r, c = image.shape
+    st = load_library().srb_envi_write(os.fsencode(path), _host_ptr(image), b, r, c)
+    if st != 0:
+        raise SrbError(st, "could not write ENVI file '%s'" % path)
 
 
 def pin_host(array):
