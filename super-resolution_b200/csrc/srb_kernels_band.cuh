@@ -44,29 +44,42 @@ struct BandGeom {
   }
 };
 
+// Frames with the same shift merged into groups (srb_kernels_tilez.cuh: n ||A x - mean||^2 + constant): the band
+// kernels then walk the groups instead of the frames.  frame[g] = a frame of group g (its warp tables stand for
+// the group), yband = the group means of the band samples [groups][Ct][count], n = frames per group.
+// groups == 0: no merging, group g is frame g and the observations come from the full LR stack.
+struct BandGroups {
+  int groups, n;
+  const int* frame;
+  const double* yband;
+};
+
 // Forward model + residual of the special samples in the reference's operation order
 // (forward_pixel): pooled[(k*Ca + c) * count + i] = s^2-fold sum of r, cost partials s^2 r^2.
-// grid: (ceil(count/256), N*Ca)
+// grid: (ceil(count/256), N*Ca)  (N = number of groups when frames are merged)
 __global__ void __launch_bounds__(256)
-k_band_forward(GenericParams P, BandGeom B, const double* __restrict__ x, const double* __restrict__ y,
+k_band_forward(GenericParams P, BandGeom B, BandGroups M, const double* __restrict__ x, const double* __restrict__ y,
                double* __restrict__ pooled, double* __restrict__ cost_partial) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long cnt = B.count();
   const int kc = blockIdx.y;
-  const int k = kc / P.Ca, c = kc % P.Ca;
+  const int kg = kc / P.Ca, c = kc % P.Ca;
+  const int k = M.groups ? M.frame[kg] : kg;
   double cost = 0.0;
   if (i < cnt) {
     int qr, qc;
     B.sample_of(i, &qr, &qc);
     const size_t HW = (size_t)P.H * P.W, hw = (size_t)P.h * P.w;
     const double pred = forward_pixel(P, x + (size_t)c * HW, k, qr, qc);
-    const double obs = y[((size_t)k * P.Ct + P.c0 + c) * hw + (size_t)qr * P.w + qc];
+    const double obs = M.groups ? M.yband[((size_t)kg * P.Ct + P.c0 + c) * cnt + i]
+                                : y[((size_t)k * P.Ct + P.c0 + c) * hw + (size_t)qr * P.w + qc];
     const double r = __dadd_rn(pred, -obs);
     double acc = 0.0;
     const int reps = P.s * P.s;
     for (int t = 0; t < reps; ++t) acc = __dadd_rn(acc, r);
-    pooled[(size_t)kc * cnt + i] = acc;
-    cost = (double)reps * (r * r);
+    const double nf = M.groups ? (double)M.n : 1.0;
+    pooled[(size_t)kc * cnt + i] = nf * acc;
+    cost = nf * ((double)reps * (r * r));
   }
   const double bs = block_sum(cost);
   if (threadIdx.x == 0) cost_partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = bs;
@@ -74,24 +87,35 @@ k_band_forward(GenericParams P, BandGeom B, const double* __restrict__ x, const 
 
 // B^T D^T restricted to the special samples of one frame, at HR pixel (pr, pc) (cf.
 // backproject_pixel).
-__device__ __forceinline__ double band_backproject(const GenericParams& P, const BandGeom& B,
+//   sshift = log2(s) when s is a power of two (shifts and masks instead of integer divisions), else -1
+__device__ __forceinline__ double band_backproject(const GenericParams& P, const BandGeom& B, int sshift,
                                                    const double* __restrict__ pooled_kc, int pr, int pc) {
   if (pr < 0 || pr >= P.H || pc < 0 || pc >= P.W) return 0.0;
   const int s = P.s, K = P.K, hk = P.hk;
-  int i0 = (hk - pr) % s;
-  if (i0 < 0) i0 += s;
-  int j0 = (hk - pc) % s;
-  if (j0 < 0) j0 += s;
+  int i0, j0;
+  if (sshift >= 0) {
+    i0 = (hk - pr) & (s - 1);
+    j0 = (hk - pc) & (s - 1);
+  } else {
+    i0 = (hk - pr) % s;
+    if (i0 < 0) i0 += s;
+    j0 = (hk - pc) % s;
+    if (j0 < 0) j0 += s;
+  }
   double acc = 0.0;
   for (int i = i0; i < K; i += s) {
     const int zr = pr + i - hk;
     if (zr < 0 || zr >= P.H) continue;
-    const int qr = zr / s;
+    const int qr = sshift >= 0 ? zr >> sshift : zr / s;
+    // rows of regular samples contribute through the column bands only
+    const bool row_regular = qr >= B.lo_r && qr < B.hi_r;
     for (int j = j0; j < K; j += s) {
       const double kv = P.psf[j * K + i];  // transposed kernel
       const int zc = pc + j - hk;
       if (kv == 0.0 || zc < 0 || zc >= P.W) continue;
-      const long long idx = B.index_of(qr, zc / s);
+      const int qcol = sshift >= 0 ? zc >> sshift : zc / s;
+      if (row_regular && qcol >= B.lo_c && qcol < B.hi_c) continue;
+      const long long idx = B.index_of(qr, qcol);
       if (idx < 0) continue;
       acc = __dadd_rn(acc, __dmul_rn(kv, pooled_kc[idx]));
     }
@@ -104,7 +128,7 @@ __device__ __forceinline__ double band_backproject(const GenericParams& P, const
 // and [R.hi_c, W)  (R is the BandGeom of the HR-pixel band, B the one of the LR samples).
 // grid: (ceil(R.count()/256), Ca)
 __global__ void __launch_bounds__(256)
-k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, const double* __restrict__ pooled,
+k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, BandGroups M, int sshift, const double* __restrict__ pooled,
                double* __restrict__ g) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= R.count()) return;
@@ -113,28 +137,91 @@ k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, const double* __restrict
   const int c = blockIdx.y;
   const long long cnt = B.count();
   double acc = 0.0;
-  for (int k = 0; k < P.N; ++k) {
-    const double* __restrict__ pk = pooled + ((size_t)k * P.Ca + c) * cnt;
+  const int ng = M.groups ? M.groups : P.N;
+  for (int kg = 0; kg < ng; ++kg) {
+    const int k = M.groups ? M.frame[kg] : kg;
+    const double* __restrict__ pk = pooled + ((size_t)kg * P.Ca + c) * cnt;
     const int Y = P.rowY[(size_t)k * P.H + pr];
     const int X = 32 * pc + P.nX[k];
     const int sy = Y >> 5, fy = Y & 31, sx = X >> 5, fx = X & 31;
     double back;
     if ((fy | fx) == 0) {
-      back = band_backproject(P, B, pk, sy, sx);
+      back = band_backproject(P, B, sshift, pk, sy, sx);
     } else if (sx >= P.W || sx + 1 < 0 || sy >= P.H || sy + 1 < 0) {
       back = 0.0;
     } else {
       const double wy1 = fy * (1.0 / 32.0), wy0 = (32 - fy) * (1.0 / 32.0);
       const double wx1 = fx * (1.0 / 32.0), wx0 = (32 - fx) * (1.0 / 32.0);
-      back = __dmul_rn(band_backproject(P, B, pk, sy, sx), wy0 * wx0);
-      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, pk, sy, sx + 1), wy0 * wx1));
-      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, pk, sy + 1, sx), wy1 * wx0));
-      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, pk, sy + 1, sx + 1), wy1 * wx1));
+      back = __dmul_rn(band_backproject(P, B, sshift, pk, sy, sx), wy0 * wx0);
+      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, sshift, pk, sy, sx + 1), wy0 * wx1));
+      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, sshift, pk, sy + 1, sx), wy1 * wx0));
+      back = __dadd_rn(back, __dmul_rn(band_backproject(P, B, sshift, pk, sy + 1, sx + 1), wy1 * wx1));
     }
     acc = __dadd_rn(acc, __dmul_rn(2.0, back));
   }
   const size_t o = (size_t)c * P.H * P.W + (size_t)pr * P.W + pc;
   g[o] += acc;
+}
+
+// Group means of the band samples and the constant part of the merged data cost (once per srb_set_observations):
+//   yband[(g * Ct + c) * count + i] = mean over the frames e of group g of y_e(sample i),
+//   var_part[c * var_stride + var_offset + g * gridDim.x + blockIdx.x] = block sum of sum_e (y_e - mean)^2.
+// The frames of group g are the entries of sub-pixel phase group_phase[g] (TEntry::yoff - its sample offset =
+// the frame's base offset in the LR stack).   grid: (ceil(count / 256), groups * Ct)
+struct TEntry;
+template <class Entry>
+__global__ void __launch_bounds__(256)
+k_band_merge(BandGeom B, int Ct, int w, const Entry* __restrict__ entries, const int* __restrict__ phase_begin,
+             const int* __restrict__ group_phase, const double* __restrict__ y, double* __restrict__ yband,
+             double* __restrict__ var_part, size_t var_stride, size_t var_offset) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long cnt = B.count();
+  const int g = blockIdx.y / Ct, c = blockIdx.y % Ct;
+  const int ph = group_phase[g];
+  const int e0 = phase_begin[ph], n = phase_begin[ph + 1] - e0;
+  double var = 0.0;
+  if (i < cnt) {
+    int qr, qc;
+    B.sample_of(i, &qr, &qc);
+    const size_t hw = (size_t)B.h * B.w;
+    const long long at = (long long)c * (long long)hw + (long long)qr * w + qc;
+    double sum = 0.0;
+    for (int e = 0; e < n; ++e) {
+      const Entry en = entries[e0 + e];
+      const long long base = en.yoff - ((long long)(short)(en.qoff & 0xffff) * w + (en.qoff >> 16));
+      sum += y[base + at];
+    }
+    const double m = sum / (double)n;
+    for (int e = 0; e < n; ++e) {
+      const Entry en = entries[e0 + e];
+      const long long base = en.yoff - ((long long)(short)(en.qoff & 0xffff) * w + (en.qoff >> 16));
+      const double d = y[base + at] - m;
+      var = fma(d, d, var);
+    }
+    yband[((size_t)g * Ct + c) * cnt + i] = m;
+  }
+  var = block_sum(var);
+  if (threadIdx.x == 0) var_part[(size_t)c * var_stride + var_offset + (size_t)g * gridDim.x + blockIdx.x] = var;
+}
+
+// First stage of the cost reduction for large tile counts: block b sums a fixed contiguous chunk of the data
+// partials and of the regularization partials into stage[b] / stage[gridDim.x + b] (fixed order: deterministic);
+// k_finish_partials then closes over the 2 * gridDim.x stage values.
+__global__ void __launch_bounds__(1024)
+k_stage_partials(const double* __restrict__ pd, size_t nd, const double* __restrict__ pr, size_t nr,
+                 double* __restrict__ stage) {
+  const size_t cd = (nd + gridDim.x - 1) / gridDim.x, cr = (nr + gridDim.x - 1) / gridDim.x;
+  const size_t d0 = (size_t)blockIdx.x * cd, d1 = d0 + cd < nd ? d0 + cd : nd;
+  const size_t r0 = (size_t)blockIdx.x * cr, r1 = r0 + cr < nr ? r0 + cr : nr;
+  double a = 0.0, b = 0.0;
+  for (size_t i = d0 + threadIdx.x; i < d1; i += blockDim.x) a += pd[i];
+  for (size_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) b += pr[i];
+  a = block_sum(a);
+  b = block_sum(b);
+  if (threadIdx.x == 0) {
+    stage[blockIdx.x] = a;
+    stage[gridDim.x + blockIdx.x] = b;
+  }
 }
 
 // cost[0] = sum(data partials), cost[1] = sum(reg partials), cost[2] = their sum (also written to

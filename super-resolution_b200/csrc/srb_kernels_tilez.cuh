@@ -240,12 +240,12 @@ k_tile_zt(const TileParams P, const __grid_constant__ CUtensorMap map_x, const _
 //   yzt[(c * cols_p + pc + KH) * rows_p + pr + HYR] = mean over the n frames (k, q) of the sub-pixel phase whose
 //   regular sample lands on HR position (pr, pc) -- positions up to the PSF half width outside the image
 //   included -- else NaN.  All frames of a phase have the same shift (planner: zt), hence the same q; n = 1 is
-//   the plain copy.  var_part[c][block] = sum over the block of sum_e (y_e - mean)^2 (0 for n = 1).
+//   the plain copy.  var_part[c * var_stride + block] = sum over the block of sum_e (y_e - mean)^2 (0 for n = 1).
 // grid: (ceil(rows_p / 256), cols_p, Ct)
 __global__ void __launch_bounds__(256)
 k_build_yzt(int h, int w, int s, int rows_p, int cols_p, int pad_r, int pad_c, int lo_r, int hi_r, int lo_c,
             int hi_c, const TEntry* __restrict__ entries, const int* __restrict__ phase_begin,
-            const double* __restrict__ y, double* __restrict__ yzt, double* __restrict__ var_part) {
+            const double* __restrict__ y, double* __restrict__ yzt, double* __restrict__ var_part, size_t var_stride) {
   const int rp = blockIdx.x * 256 + threadIdx.x, cp = blockIdx.y, c = blockIdx.z;
   double var = 0.0;
   if (rp < rows_p) {
@@ -276,7 +276,7 @@ k_build_yzt(int h, int w, int s, int rows_p, int cols_p, int pad_r, int pad_c, i
   }
   if (var_part != nullptr) {
     var = block_sum(var);
-    if (threadIdx.x == 0) var_part[((size_t)c * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = var;
+    if (threadIdx.x == 0) var_part[(size_t)c * var_stride + (size_t)blockIdx.y * gridDim.x + blockIdx.x] = var;
   }
 }
 

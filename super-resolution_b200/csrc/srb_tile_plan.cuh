@@ -45,6 +45,9 @@ struct TilePlan {
   // at upload: cfg4 has 2 per phase, cfg5 4)
   bool zt = false;
   int zt_n = 0;
+  // zt_n > 1: the groups of frames with equal shifts = the non-empty sub-pixel phases: their phase index and one
+  // frame of each (the band kernels walk groups instead of frames, srb_kernels_band.cuh)
+  std::vector<int> group_phase, group_frame;
 };
 
 struct TileState {
@@ -69,7 +72,14 @@ struct TileState {
   double* d_yzt = nullptr; // observations in the transposed, padded Z layout [Ct][cols_p][rows_p] (k_tile_zt)
   int yzt_rows = 0, yzt_cols = 0;
   double* d_yvar = nullptr;      // [Ct] constant part of the merged data cost (zt_n > 1), else NULL
-  double* d_yvar_part = nullptr; // per-block partial sums of k_build_yzt
+  double* d_yvar_part = nullptr; // per-block partial sums of k_build_yzt (+ k_band_merge)
+  size_t yvar_stride = 0, yvar_band_offset = 0;   // slots per channel in d_yvar_part; first slot of the band sums
+  int band_groups = 0;           // > 0: the border-band kernels run on merged groups of frames
+  int* d_group_phase = nullptr;  // [band_groups]
+  int* d_group_frame = nullptr;  // [band_groups]
+  double* d_yband = nullptr;     // [band_groups][Ct][band.count()] group means of the band samples
+  double* d_stage = nullptr;     // [2 * kStageBlocks] first-stage sums of the cost reduction
+  static constexpr int kStageBlocks = 64;
   bool tma_ok = false;
   int tile_h = 32;         // SRB_TILE_H=32|64 overrides (tuning knob; 32 measured faster at cfg3)
   void* encode = nullptr;  // cuTensorMapEncodeTiled
@@ -97,6 +107,10 @@ inline void fused_teardown(srb_ctx* c) {
   if (st->d_yzt) cudaFree(st->d_yzt);
   if (st->d_yvar) cudaFree(st->d_yvar);
   if (st->d_yvar_part) cudaFree(st->d_yvar_part);
+  if (st->d_group_phase) cudaFree(st->d_group_phase);
+  if (st->d_group_frame) cudaFree(st->d_group_frame);
+  if (st->d_yband) cudaFree(st->d_yband);
+  if (st->d_stage) cudaFree(st->d_stage);
   delete st;
   st = nullptr;
 }
@@ -192,6 +206,7 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
   const int HB = hk + FR;
   const int BP = (FT_W + 2 * HB) | 1;
   std::vector<std::vector<TEntry>> lists((size_t)s * s);
+  std::vector<int> first_frame((size_t)s * s, -1);   // a frame of every non-empty phase
   const long long hw = (long long)G.h * G.w;
   bool first = true;
   for (int k = 0; k < G.N; ++k) {
@@ -222,6 +237,7 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
             e.fx = (short)fx;
             e.owner = (a == 0 && b == 0) ? 1 : 0;
             lists[(size_t)pr * s + pc].push_back(e);
+            if (first_frame[(size_t)pr * s + pc] < 0) first_frame[(size_t)pr * s + pc] = k;
             if (first) {
               st->qoff_min_r = st->qoff_max_r = qoff_r;
               st->qoff_min_c = st->qoff_max_c = qoff_c;
@@ -300,6 +316,12 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
     }
     st->zt = mergeable;
     st->zt_n = mergeable ? std::max(n, 1) : 0;
+    if (mergeable && n > 1)
+      for (size_t ph = 0; ph < lists.size(); ++ph)
+        if (!lists[ph].empty()) {
+          st->group_phase.push_back((int)ph);
+          st->group_frame.push_back(first_frame[ph]);
+        }
   }
 
   st->supported = true;
@@ -374,8 +396,22 @@ inline srb_status fused_setup(srb_ctx* c) {
         return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (observations in transposed Z layout)");
       if (plan.zt_n > 1) {
         const size_t per_channel = (size_t)((st->yzt_rows + 255) / 256) * st->yzt_cols;
+        st->yvar_band_offset = per_channel;
+        st->yvar_stride = per_channel;
+        if (st->has_band) {  // the border band walks the merged groups too
+          const int ng = (int)plan.group_phase.size();
+          const size_t bcnt = (size_t)st->band.count();
+          st->band_groups = ng;
+          st->yvar_stride += (size_t)ng * ((bcnt + 255) / 256);
+          if (cudaMalloc((void**)&st->d_group_phase, ng * sizeof(int)) != cudaSuccess ||
+              cudaMalloc((void**)&st->d_group_frame, ng * sizeof(int)) != cudaSuccess ||
+              cudaMalloc((void**)&st->d_yband, (size_t)ng * G.Ct * bcnt * sizeof(double)) != cudaSuccess)
+            return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (merged border band)");
+          SRB_CUDA_CHECK(c, cudaMemcpy(st->d_group_phase, plan.group_phase.data(), ng * sizeof(int), cudaMemcpyHostToDevice));
+          SRB_CUDA_CHECK(c, cudaMemcpy(st->d_group_frame, plan.group_frame.data(), ng * sizeof(int), cudaMemcpyHostToDevice));
+        }
         if (cudaMalloc((void**)&st->d_yvar, (size_t)G.Ct * sizeof(double)) != cudaSuccess ||
-            cudaMalloc((void**)&st->d_yvar_part, (size_t)G.Ct * per_channel * sizeof(double)) != cudaSuccess)
+            cudaMalloc((void**)&st->d_yvar_part, (size_t)G.Ct * st->yvar_stride * sizeof(double)) != cudaSuccess)
           return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (merged-frame cost constants)");
       }
     } else if (take && st->tma_ok && st->tile_h == 32) {
@@ -384,6 +420,8 @@ inline srb_status fused_setup(srb_ctx* c) {
       st->yz_holes = plan.zlayout == 2;
     }
   }
+  if (cudaMalloc((void**)&st->d_stage, 2 * TileState::kStageBlocks * sizeof(double)) != cudaSuccess)
+    return c->fail(SRB_ERR_NOMEM, "cudaMalloc failed (cost reduction stage)");
   st->supported = true;
   return SRB_OK;
 }
@@ -398,10 +436,17 @@ inline srb_status fused_observations_changed(srb_ctx* c) {
     const dim3 grid((unsigned)((st->yzt_rows + 255) / 256), (unsigned)st->yzt_cols, (unsigned)G.Ct);
     k_build_yzt<<<grid, 256, 0, c->stream>>>(G.h, G.w, G.s, st->yzt_rows, st->yzt_cols, (KH + 1) & ~1, KH,
                                              st->band.lo_r, st->band.hi_r, st->band.lo_c, st->band.hi_c,
-                                             st->d_entries, st->d_phase_begin, c->d_y, st->d_yzt, st->d_yvar_part);
+                                             st->d_entries, st->d_phase_begin, c->d_y, st->d_yzt, st->d_yvar_part,
+                                             st->yvar_stride);
     c->timing.kernel_launches += 1;
     if (st->d_yvar) {
-      k_reduce_yvar<<<G.Ct, 1024, 0, c->stream>>>(st->d_yvar_part, (size_t)grid.x * grid.y, (double)G.s * G.s, st->d_yvar);
+      if (st->band_groups > 0) {
+        const dim3 bg((unsigned)((st->band.count() + 255) / 256), (unsigned)(st->band_groups * G.Ct));
+        k_band_merge<TEntry><<<bg, 256, 0, c->stream>>>(st->band, G.Ct, G.w, st->d_entries, st->d_phase_begin, st->d_group_phase,
+                                                        c->d_y, st->d_yband, st->d_yvar_part, st->yvar_stride, st->yvar_band_offset);
+        c->timing.kernel_launches += 1;
+      }
+      k_reduce_yvar<<<G.Ct, 1024, 0, c->stream>>>(st->d_yvar_part, st->yvar_stride, (double)G.s * G.s, st->d_yvar);
       c->timing.kernel_launches += 1;
     }
     SRB_CUDA_CHECK(c, cudaGetLastError());
@@ -578,7 +623,8 @@ inline TileLayout tile_layout(const srb_ctx* c) {
   TileLayout L;
   L.nblocks = (size_t)((G.W + FT_W - 1) / FT_W) * tile_rows_per_channel(c) * c->Ca();
   const long long bcount = st->has_band ? st->band.count() : 0;
-  L.bgrid = dim3((unsigned)((bcount + 255) / 256), (unsigned)(G.N * c->Ca()));
+  const int band_frames = (st->band_groups > 0 && st->yz_valid) ? st->band_groups : G.N;  // merged groups or frames
+  L.bgrid = dim3((unsigned)((bcount + 255) / 256), (unsigned)(band_frames * c->Ca()));
   L.nband = st->has_band ? (size_t)L.bgrid.x * L.bgrid.y : 0;
   return L;
 }
@@ -655,6 +701,8 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
       return reg_tile_launch(c, d_x, d_g, do_reg, unit_begin, unit_end, P.part_reg, reg_done);
     }
     if (zr != SRB_ERR_STATE) return zr;
+    if (st->plan.zt_n > 1)   // the merged observations (and the merged border band) have no other kernel
+      return c->fail(SRB_ERR_STATE, "tile kernel: the tensor maps of the transposed Z layout could not be built");
   }
   if (P.yz != nullptr && TH == 32 && fe == 1 && !st->frac) {  // row-major Z layout (SRB_ZT=0)
     srb_status zr = SRB_ERR_STATE;
@@ -707,19 +755,31 @@ inline srb_status fused_eval_finish(srb_ctx* c, const double* d_x, double* d_g, 
     GP.N = G.N; GP.Ca = Ca; GP.Ct = G.Ct; GP.c0 = c->c0;
     GP.src_r = c->d_src_r; GP.src_c = c->d_src_c; GP.psf = c->d_psf;
     GP.rowY = c->d_rowY_fwd; GP.nX = c->d_nX_fwd;
-    k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, d_x, c->d_y, st->d_pooled,
+    BandGroups M{0, 1, nullptr, nullptr};
+    if (st->band_groups > 0 && st->yz_valid) M = BandGroups{st->band_groups, st->plan.zt_n, st->d_group_frame, st->d_yband};
+    int sshift = -1;
+    for (int b = 0; b < 5; ++b)
+      if ((1 << b) == G.s) sshift = b;
+    k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, M, d_x, c->d_y, st->d_pooled,
                                                    c->d_partial + L.nblocks);
     c->timing.kernel_launches += 1;
     if (d_g) {
       GP.rowY = c->d_rowY_tr; GP.nX = c->d_nX_tr;
       const dim3 rgrid((unsigned)((st->reach.count() + 255) / 256), (unsigned)Ca);
-      k_band_adjoint<<<rgrid, 256, 0, c->stream>>>(GP, st->band, st->reach, st->d_pooled, d_g);
+      k_band_adjoint<<<rgrid, 256, 0, c->stream>>>(GP, st->band, st->reach, M, sshift, st->d_pooled, d_g);
       c->timing.kernel_launches += 1;
     }
   }
-  k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, L.nblocks + L.nband,
-                                               c->d_partial + L.nblocks + L.nband, L.nblocks, c->d_cost, tail);
-  c->timing.kernel_launches += 1;
+  const size_t nd = L.nblocks + L.nband;
+  if (nd + L.nblocks >= 32768) {  // large tile counts: a parallel first stage, then the closing block
+    constexpr int SB = TileState::kStageBlocks;
+    k_stage_partials<<<SB, 1024, 0, c->stream>>>(c->d_partial, nd, c->d_partial + nd, L.nblocks, st->d_stage);
+    k_finish_partials<<<1, 1024, 0, c->stream>>>(st->d_stage, SB, st->d_stage + SB, SB, c->d_cost, tail);
+    c->timing.kernel_launches += 2;
+  } else {
+    k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial, nd, c->d_partial + nd, L.nblocks, c->d_cost, tail);
+    c->timing.kernel_launches += 1;
+  }
   return SRB_OK;
 }
 
