@@ -43,6 +43,23 @@ class CudaObjectiveTerm : public ObjectiveTerm {
   srb_ctx* ctx_;
 };
 
+// The same term with ONE host thread driving several GPUs (srb_multi_eval): what the reference's single-threaded
+// solver holds when more than one B200 is available.  Same contract as CudaObjectiveTerm.
+class CudaMultiObjectiveTerm : public ObjectiveTerm {
+ public:
+  explicit CudaMultiObjectiveTerm(srb_multi* multi) : multi_(multi) { CHECK_NOTNULL(multi); }
+  double Compute(const double* estimated_image_data, double* gradient) const override {
+    CHECK_NOTNULL(estimated_image_data);
+    double cost = 0.0;
+    CHECK(srb_multi_eval(multi_, estimated_image_data, gradient, &cost) == SRB_OK)
+        << "libsrb200: " << srb_multi_last_error(multi_);
+    return cost;
+  }
+
+ private:
+  srb_multi* multi_;
+};
+
 // Only the data term (ObjectiveDataTerm::Compute, objective_data_term.cpp:98-116), ADDING into the
 // gradient like the reference; evaluated in the reference's operation order (bit-identical).
 class CudaObjectiveDataTerm : public ObjectiveTerm {

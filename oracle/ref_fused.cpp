@@ -23,8 +23,6 @@
 
 using namespace super_resolution;  // NOLINT
 
-extern "C" {
-
 // IRLSMapSolver::Solve with the B200 engine behind the reference's seams, the way INTEGRATION.md
 // wires it: ONE CudaObjectiveTerm (srb_eval = data term + IRLS regularization term, fused) replaces
 // the ObjectiveDataTerm built at irls_map_solver.cpp:243-246 and the ObjectiveIRLSRegularizationTerm
@@ -34,8 +32,32 @@ extern "C" {
 // is the reference's own RunCGSolverAnalyticalDiff / RunLBFGSSolverAnalyticalDiff + ALGLIB,
 // unmodified.  `ctx` already holds the model, the observations and the regularizer
 // (srb_create / srb_set_observations / srb_set_regularizer).
-int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has_regularizer,
-                    double lambda_sum, const ref_options* opt, double* out, ref_stats* stats) {
+namespace {
+// The engine behind the loop: one device (srb_ctx) or several driven by this thread (srb_multi).
+struct SingleOps {
+  srb_ctx* ctx;
+  void set_channel_range(int c0, int c1) const { CHECK(srb_set_channel_range(ctx, c0, c1) == SRB_OK) << srb_last_error(ctx); }
+  void reweight(const double* x) const { CHECK(srb_reweight(ctx, x, nullptr) == SRB_OK) << srb_last_error(ctx); }
+  std::shared_ptr<ObjectiveTerm> term() const { return std::make_shared<CudaObjectiveTerm>(ctx); }
+  long evals() const {
+    srb_timing tm;
+    return srb_get_timing(ctx, &tm) == SRB_OK ? (long)tm.num_evals : 0;
+  }
+};
+struct MultiOps {
+  srb_multi* m;
+  void set_channel_range(int c0, int c1) const { CHECK(srb_multi_set_channel_range(m, c0, c1) == SRB_OK) << srb_multi_last_error(m); }
+  void reweight(const double* x) const { CHECK(srb_multi_reweight(m, x, nullptr) == SRB_OK) << srb_multi_last_error(m); }
+  std::shared_ptr<ObjectiveTerm> term() const { return std::make_shared<CudaMultiObjectiveTerm>(m); }
+  long evals() const {
+    srb_timing tm;
+    return srb_multi_get_timing(m, &tm) == SRB_OK ? (long)tm.num_evals : 0;
+  }
+};
+
+template <class Ops>
+int solve_fused_impl(const Ops& eng, int C, int H, int W, const double* x0, int has_regularizer, double lambda_sum,
+                     const ref_options* opt, double* out, ref_stats* stats) {
   const auto t0 = std::chrono::steady_clock::now();
   const size_t P = (size_t)H * W;
   IRLSMapSolverOptions options;
@@ -58,7 +80,7 @@ int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has
   ref_stats st{};
   for (int i = 0; i < rounds; ++i) {
     const int c0 = i * per_split, c1 = c0 + per_split;
-    CHECK(srb_set_channel_range(ctx, c0, c1) == SRB_OK) << srb_last_error(ctx);  // resets weights to 1 (:66-74)
+    eng.set_channel_range(c0, c1);  // resets weights to 1 (:66-74)
     alglib::real_1d_array solver_data;  // :232-239
     solver_data.setlength(num_data_points);
     std::memcpy(solver_data.getcontent(), x0 + (size_t)c0 * P, (size_t)num_data_points * sizeof(double));
@@ -68,13 +90,13 @@ int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has
     int num_iterations_ran = 0;
     while (std::abs(cost_difference) >= options.irls_cost_difference_threshold) {
       ObjectiveFunction objective_function(num_data_points);
-      objective_function.AddTerm(std::make_shared<CudaObjectiveTerm>(ctx));
+      objective_function.AddTerm(eng.term());
       const double final_cost = options.least_squares_solver == CG_SOLVER
                                     ? RunCGSolverAnalyticalDiff(options, objective_function, &solver_data)
                                     : RunLBFGSSolverAnalyticalDiff(options, objective_function, &solver_data);
       if (!has_regularizer) break;  // :118-121
       // :128-143, on the device: w = 1 / max(1e-5, reg(x))
-      CHECK(srb_reweight(ctx, solver_data.getcontent(), nullptr) == SRB_OK) << srb_last_error(ctx);
+      eng.reweight(solver_data.getcontent());
       cost_difference = previous_cost - final_cost;
       previous_cost = final_cost;
       num_iterations_ran++;
@@ -82,11 +104,25 @@ int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has
     }
     std::memcpy(out + (size_t)c0 * P, solver_data.getcontent(), (size_t)num_data_points * sizeof(double));
   }
-  srb_timing tm;
-  if (srb_get_timing(ctx, &tm) == SRB_OK) st.num_data_term_evals = (long)tm.num_evals;
+  st.num_data_term_evals = eng.evals();
   st.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (stats) *stats = st;
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int ref_solve_fused(srb_ctx* ctx, int C, int H, int W, const double* x0, int has_regularizer,
+                    double lambda_sum, const ref_options* opt, double* out, ref_stats* stats) {
+  return solve_fused_impl(SingleOps{ctx}, C, H, W, x0, has_regularizer, lambda_sum, opt, out, stats);
+}
+
+// The same loop with ONE host thread driving several GPUs through CudaMultiObjectiveTerm (srb_multi_eval):
+// `multi` already holds the model, the observations and the regularizer.
+int ref_solve_fused_multi(srb_multi* multi, int C, int H, int W, const double* x0, int has_regularizer,
+                          double lambda_sum, const ref_options* opt, double* out, ref_stats* stats) {
+  return solve_fused_impl(MultiOps{multi}, C, H, W, x0, has_regularizer, lambda_sum, opt, out, stats);
 }
 
 

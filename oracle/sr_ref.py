@@ -89,6 +89,8 @@ def fused_lib():
         L.ref_solve_fused.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_double,
                                       C.POINTER(Options), _dp, C.POINTER(Stats)]
         L.ref_solve_fused.restype = C.c_int
+        L.ref_solve_fused_multi.argtypes = L.ref_solve_fused.argtypes
+        L.ref_solve_fused_multi.restype = C.c_int
         L.ref_solve_adapters.argtypes = [C.c_void_p, C.c_void_p, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
                                          C.c_int, C.c_double, C.POINTER(Options), _dp, C.POINTER(Stats)]
         L.ref_solve_adapters.restype = C.c_int
@@ -172,6 +174,20 @@ def solve_fused(engine, x0, has_regularizer, lambda_sum, options=None):
     opt = options if options is not None else default_options()
     rc = fused_lib().ref_solve_fused(engine._ctx, Cn, H, W, _p(x0), 1 if has_regularizer else 0,
                                float(lambda_sum), C.byref(opt), _p(out), C.byref(st))
+    assert rc == 0
+    return out, st
+
+
+def solve_fused_multi(multi_engine, x0, has_regularizer, lambda_sum, options=None):
+    """solve_fused with ONE host thread driving several GPUs (CudaMultiObjectiveTerm -> srb_multi_eval).
+    `multi_engine` is a configured super-resolution_b200 MultiEngine."""
+    x0 = _f64(x0)
+    Cn, H, W = x0.shape
+    out = np.empty_like(x0)
+    st = Stats()
+    opt = options if options is not None else default_options()
+    rc = fused_lib().ref_solve_fused_multi(multi_engine._ctx, Cn, H, W, _p(x0), 1 if has_regularizer else 0,
+                                           float(lambda_sum), C.byref(opt), _p(out), C.byref(st))
     assert rc == 0
     return out, st
 

@@ -56,6 +56,7 @@ __device__ __forceinline__ void btv_tile_body(const RegTileParams& P, double* __
   const double* __restrict__ xg = P.x + (size_t)ch * HW;
   const double* __restrict__ wg = P.w + (size_t)ch * HW;
   // ---- x tile + halo (zero outside the image: such taps are masked or multiply a zero t) ----------------
+#pragma unroll 5
   for (int id = tid; id < D::XR * D::XC; id += D::NT) {
     const int r = id / D::XC, c = id - r * D::XC;
     const int gr = ty0 - D::A + r, gc = tx0 - D::A + c;
@@ -94,7 +95,13 @@ __device__ __forceinline__ void btv_tile_body(const RegTileParams& P, double* __
   const int ec = tid % D::TW, er0 = (tid / D::TW) * EL;
   const int gc = tx0 + ec;
   double* __restrict__ gp = P.g + (size_t)ch * HW + (size_t)(ty0 + er0) * P.W + gc;
-#pragma unroll 2
+  double g_old[EL];  // the data-term gradient the tile kernel left: all loads in flight before the stencil work
+#pragma unroll
+  for (int l = 0; l < EL; ++l) {
+    const int gr = ty0 + er0 + l;
+    g_old[l] = (!BORDER || (gr < P.H && gc < P.W && gr >= P.row0 && gr < P.row1)) ? gp[(size_t)l * P.W] : 0.0;
+  }
+#pragma unroll
   for (int l = 0; l < EL; ++l) {
     const int gr = ty0 + er0 + l;
     if (BORDER && !(gr < P.H && gc < P.W && gr >= P.row0 && gr < P.row1)) continue;
@@ -111,7 +118,7 @@ __device__ __forceinline__ void btv_tile_body(const RegTileParams& P, double* __
         if (!BORDER || !(gr - i == 0 && gc - j == 0))  // the reference skips image pixel (0, 0) here
           nb += signed_by(x0 - xp[-i * D::XP - j], tp[-i * D::TP - j] * P.decay[i + j]);
       }
-    gp[(size_t)l * P.W] += fma(tp[0], self, nb);
+    gp[(size_t)l * P.W] = g_old[l] + fma(tp[0], self, nb);
   }
 }
 
@@ -215,7 +222,7 @@ __device__ __forceinline__ void tv3d_tile_body(const RegTileParams& P, int ch, i
   cost_out = 0.5 * cost;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_tv3d_tile(const RegTileParams P) {
   const int unit = P.unit_begin + blockIdx.y;
   const int ch = unit / P.tile_rows;

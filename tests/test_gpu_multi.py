@@ -115,3 +115,34 @@ def test_multi_rejects_bad_arguments(srb):
         srb.MultiEngine((4, 1, 16, 16), 2, psf, wl.default_shifts(4, 2), n_gpus=2, devices=[0, 0])
     with pytest.raises(srb.SrbError):
         srb.MultiEngine((0, 1, 16, 16), 2, psf, None, n_gpus=1)
+
+
+@pytest.mark.parametrize("partition", ["frames", "rows"])
+def test_reference_solver_drives_several_gpus_through_the_adapter(srb, oracle, ref, partition):
+    """The reference's IRLS + ALGLIB loop (oracle/_ref, unmodified ALGLIB and RunCGSolverAnalyticalDiff) on top of
+    CudaMultiObjectiveTerm (include/srb200_adapters.hpp -> srb_multi_eval): one host thread, every GPU of the box
+    (at most 8).  Same solve as through CudaObjectiveTerm on one device: the gradients differ by fp64
+    re-association of the cross-device sum only, and a tie-free image keeps the solver from amplifying that."""
+    G = min(srb.device_count(), 8)
+    s, K = 4, 7
+    rng = np.random.default_rng(41)
+    psf, shifts = wl.gaussian_psf(K, 1.5), wl.default_shifts(16, s)
+    truth = wl.box_smooth(rng.random((2, 192, 320)))
+    m = oracle.Model(s, psf, shifts)
+    lr = np.stack([np.stack([oracle.forward(m, k, truth[c]) for c in range(2)]) for k in range(16)])
+    lr += 0.004 * rng.standard_normal(lr.shape)
+    x0 = wl.bilinear_upsample(lr[0], s)
+    opt = ref.default_options()
+    opt.max_num_solver_iterations = 25
+    opt.max_num_irls_iterations = 2
+    part = srb.PARTITION_ROWS if partition == "rows" else srb.PARTITION_FRAMES
+    with srb.Engine(lr.shape, s, psf, shifts) as e1, \
+            srb.MultiEngine(lr.shape, s, psf, shifts, n_gpus=G, partition=part) as me:
+        for e in (e1, me):
+            e.set_observations(lr)
+            e.set_regularizer(srb.REG_TV, 0.01)
+        one, st1 = ref.solve_fused(e1, x0, True, 0.01, options=opt)
+        many, stm = ref.solve_fused_multi(me, x0, True, 0.01, options=opt)
+    assert stm.num_data_term_evals == st1.num_data_term_evals
+    assert rel_l2(many, one) <= 1e-9
+    assert rel_l2(many, truth) < rel_l2(x0, truth)
