@@ -476,6 +476,42 @@ def main():
             peer_w.close()
         del obj_w, peer_w
 
+    # ================= row-band partition (N > 1): every rank holds every frame, no gradient exchange ========
+    rows_block = None
+    if world > 1 and not args.no_weak:
+        eng.close()
+        frames_all = list(range(n_frames))
+        eng = srb.Engine((n_frames, C, H // s, W // s), s, psf, wl.default_shifts(n_frames, s), device=local_rank)
+        work_r = wl.make(args.config, forward=lambda k, plane: eng.forward(k, plane), N=n_frames)
+        eng.set_observations(work_r["lr"])
+        eng.set_regularizer(work["reg_kind"], work_r["lam"], work_r["btv_range"], work_r["btv_decay"])
+        try:
+            stream_r = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
+            with torch.cuda.stream(stream_r):
+                halo = sharding.stencil_halo_rows(cf["K"], work["reg_kind"], work_r["btv_range"])
+                robj = sharding.RowBandObjective(sharding.EngineEvaluator(eng), n, W, halo, dist=dist)
+                cost_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+                for _ in range(warmup):
+                    robj.evaluate(x_dev, gc_dev, cost_dev)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream_r)
+                for _ in range(args.steps):
+                    robj.evaluate(x_dev, gc_dev, cost_dev)
+                e1.record(stream_r)
+                barrier()
+                (ms_r,) = reduce_max(e0.elapsed_time(e1) / args.steps)
+                rows_block = {"scaling": "strong", "frames_per_gpu": n_frames, "frames_total": n_frames,
+                              "value": units / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r,
+                              "cost_check": float(cost_dev.cpu()[0]),
+                              "partition": "row bands of the HR image: every rank holds every frame and evaluates the whole "
+                                           "objective on 1/%d of the (channel, tile row) units; per step %d halo rows of x "
+                                           "to each neighbour (NCCL send/recv) + a scalar allreduce of the cost; no gradient "
+                                           "exchange" % (world, halo)}
+        except Exception as err:    # e.g. a model with a border band (cfg4 / cfg5): unit ranges do not apply
+            rows_block = {"unavailable": str(err)[:200]}
+        del work_r
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
@@ -521,6 +557,8 @@ def main():
             line["e2e_frame_shard"] = e2e_frames
         if weak is not None:
             line["weak"] = weak
+        if rows_block is not None:
+            line["row_bands"] = rows_block
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_reference_run(args.config, args.cpu_sample, 3, 1, cores, also_single_thread=True)

@@ -252,6 +252,15 @@ srb_status srb_eval_units_dev(srb_ctx* ctx, const double* x_dev, double* gradien
                               int unit_begin, int unit_end);
 srb_status srb_eval_finish_dev(srb_ctx* ctx, const double* x_dev, double* gradient_cost_dev);
 
+/* Row-band partition with one process per GPU (the alternative to frame sharding): every
+ * rank's context holds EVERY frame; a rank evaluates units [unit_begin, unit_end) of the whole objective -- the
+ * gradient rows it writes are final, no cross-rank sum of the gradient exists -- and *cost_dev (device, may be
+ * NULL) receives the cost of exactly those units, ready for a scalar allreduce.  x_dev must be current on the
+ * rank's rows plus the halo the stencils reach (2 * PSF half width + 1 rows, + R for BTV), which neighbouring
+ * ranks exchange (sharding.RowBandObjective).  Needs srb_num_units > 1 (fused path, no border band). */
+srb_status srb_eval_unit_range_dev(srb_ctx* ctx, const double* x_dev, double* gradient_dev, int unit_begin,
+                                   int unit_end, double* cost_dev);
+
 /* ---- multi-GPU peer path: reduce-scatter / all-gather over NVLink peer memory ------------------
  * One process per GPU.  Every rank owns a contiguous band of gradient units.  The tile kernel
  * evaluates the gradient band by band; a finished band that belongs to another rank is pushed by a

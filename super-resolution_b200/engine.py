@@ -55,6 +55,7 @@ SIGNATURES = {
     "srb_unit_range": (C.c_int, [_ctx_p, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "srb_eval_units_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "srb_eval_finish_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
+    "srb_eval_unit_range_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "srb_set_profiling": (C.c_int, [_ctx_p, C.c_int]),
     "srb_peer_sizes": (C.c_int, [_ctx_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "srb_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_ulonglong]),
@@ -407,6 +408,11 @@ class Engine:
 
     def eval_finish_dev(self, x_dev, gc_dev):
         self._check(self._lib.srb_eval_finish_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(gc_dev)))
+
+    def eval_unit_range_dev(self, x_dev, g_dev, u0, u1, cost_dev=None):
+        """Units [u0, u1) of the whole objective + their cost (row-band partition, srb_eval_unit_range_dev)."""
+        self._check(self._lib.srb_eval_unit_range_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(g_dev), int(u0), int(u1),
+                                                      _dev_ptr(cost_dev)))
 
     def set_profiling(self, on=True):
         self._check(self._lib.srb_set_profiling(self._ctx, 1 if on else 0))

@@ -39,6 +39,75 @@ def chunk_bounds(num_units, num_chunks):
     return [(edges[i], edges[i + 1]) for i in range(num_chunks) if edges[i + 1] > edges[i]]
 
 
+def stencil_halo_rows(psf_size, reg_kind=-1, btv_range=3):
+    """HR rows of x around a gradient row that the fused kernels read: the PSF twice (forward and adjoint pass) plus
+    one row for TV / 3-D TV or R rows for BTV (csrc/srb_multi.cuh: multi_halo_rows)."""
+    reg = btv_range if reg_kind == 2 else 1
+    return 2 * (int(psf_size) // 2) + max(int(reg), 1)
+
+
+def unit_band(num_units, rank, world):
+    """Contiguous units [u0, u1) of `rank` in the row-band partition (units are (channel, tile row) in memory
+    order, so a rank's gradient rows are one contiguous element range)."""
+    return (rank * num_units) // world, ((rank + 1) * num_units) // world
+
+
+class RowBandObjective:
+    """Row-band partition of the MAP objective over the ranks (the alternative to frame sharding): every rank
+    holds EVERY frame and evaluates the whole objective on its contiguous band of (channel, tile row) units.  The
+    gradient band a rank produces is final -- there is no cross-rank sum of the gradient; what the ranks exchange
+    per evaluation is the halo of the estimate (the few rows next to a band that the PSF / regularizer stencils
+    of the neighbouring band read: `halo_rows` rows of W doubles to each neighbour) and one scalar (the cost).
+
+    In a distributed solver every rank updates its own band of x; `evaluate` therefore first refreshes the halo
+    rows of this rank's replica from the neighbours' bands, then evaluates its units.
+
+    evaluator protocol: num_units(), unit_range(u0, u1) -> element range, eval_unit_range(x, g, u0, u1, cost)
+    with `cost` a 1-element tensor on x's device.
+    """
+
+    def __init__(self, evaluator, n, width, halo_rows, dist=None, group=None):
+        self.ev, self.n, self.dist, self.group = evaluator, int(n), dist, group
+        self.world = 1 if dist is None or not dist.is_initialized() else dist.get_world_size(group)
+        self.rank = 0 if self.world == 1 else dist.get_rank(group)
+        nu = evaluator.num_units()
+        self.u0, self.u1 = unit_band(nu, self.rank, self.world)
+        self.begin, self.end = evaluator.unit_range(self.u0, self.u1)
+        self.halo = int(halo_rows) * int(width)            # elements exchanged with each neighbour
+        # neighbours with a non-empty band (ranks beyond the number of units hold nothing)
+        bands = [unit_band(nu, r, self.world) for r in range(self.world)]
+        self.prev = next((r for r in range(self.rank - 1, -1, -1) if bands[r][1] > bands[r][0]), None)
+        self.next = next((r for r in range(self.rank + 1, self.world) if bands[r][1] > bands[r][0]), None)
+        self.empty = self.u1 <= self.u0
+        for r in range(self.world):
+            b, e = evaluator.unit_range(*bands[r])
+            if bands[r][1] > bands[r][0] and e - b < self.halo and self.world > 1:
+                raise ValueError("a rank's row band is thinner than the stencil halo: use fewer ranks")
+
+    def exchange_halo(self, x):
+        """x[begin - halo, begin) <- previous rank's last rows; x[end, end + halo) <- next rank's first rows."""
+        if self.world == 1 or self.empty:
+            return
+        d = self.dist
+        ops = []
+        h = min(self.halo, self.end - self.begin)
+        if self.prev is not None:
+            ops.append(d.P2POp(d.isend, x[self.begin:self.begin + h], self.prev, self.group))
+            ops.append(d.P2POp(d.irecv, x[max(self.begin - self.halo, 0):self.begin], self.prev, self.group))
+        if self.next is not None:
+            ops.append(d.P2POp(d.isend, x[self.end - h:self.end], self.next, self.group))
+            ops.append(d.P2POp(d.irecv, x[self.end:min(self.end + self.halo, self.n)], self.next, self.group))
+        for w in d.batch_isend_irecv(ops):
+            w.wait()
+
+    def evaluate(self, x, g, cost):
+        """g[begin:end] <- this rank's final gradient band; cost[0] <- the whole objective's cost (all ranks)."""
+        self.exchange_halo(x)
+        self.ev.eval_unit_range(x, g, self.u0, self.u1, cost)
+        if self.world > 1:
+            self.dist.all_reduce(cost, group=self.group)
+
+
 class EngineEvaluator:
     """Adapter of one `Engine` (one rank's srb_ctx) to the evaluator protocol."""
 
@@ -56,6 +125,9 @@ class EngineEvaluator:
 
     def eval_finish(self, x, gc):
         self.e.eval_finish_dev(x, gc)
+
+    def eval_unit_range(self, x, g, u0, u1, cost):
+        self.e.eval_unit_range_dev(x, g, u0, u1, cost)
 
 
 class ShardedObjective:

@@ -60,10 +60,68 @@ class OracleEvaluator:
         self._g = None
 
 
+class OracleRowEvaluator:
+    """Evaluator of the row-band partition on the CPU oracle: units are groups of `rpu` HR rows of one channel; the
+    oracle evaluates the whole objective on the rank's replica of x (NaN wherever the rank has no current data) and
+    the rank keeps its own rows.  The cost split by tiles is the CUDA kernel's business (tests/test_gpu_multi.py);
+    here the rank's cost share is a stand-in, sum of x^2 over its band, which only exercises the scalar exchange."""
+
+    def __init__(self, model, lr, reg_kind, lam, wts, rpu):
+        self.m, self.kind, self.lam, self.wts, self.rpu = model, reg_kind, lam, wts, rpu
+        self.obs = o.upsample_observations(model, lr)
+        self.C, self.H, self.W = wts.shape
+        self.tr = (self.H + rpu - 1) // rpu
+
+    def num_units(self):
+        return self.C * self.tr
+
+    def unit_range(self, u0, u1):
+        def first(u):
+            ch, t = divmod(u, self.tr)
+            return ch * self.H * self.W + min(t * self.rpu, self.H) * self.W
+        return first(u0), first(u1)
+
+    def eval_unit_range(self, x, g, u0, u1, cost):
+        b, e = self.unit_range(u0, u1)
+        xs = x.numpy().reshape(self.C, self.H, self.W)
+        with np.errstate(invalid="ignore"):
+            _, grad = o.evaluate(self.m, xs, self.obs, self.kind, self.lam, self.wts)
+        g[b:e] = torch.from_numpy(grad.reshape(-1)[b:e])
+        cost[0] = float(np.sum(x.numpy()[b:e] ** 2))
+
+
+def main_rows(rank, world, out):
+    """Row-band partition: every rank holds every frame, x is current only on the rank's band; the halo comes
+    from the neighbours (RowBandObjective.exchange_halo).  Output: [gradient band placed in a zero vector, cost]."""
+    rng = np.random.default_rng(7)
+    C, h, w, s, K, N = 2, 18, 10, 2, 3, 5
+    psf = o.gaussian_psf(K, 1.0)
+    shifts = rng.integers(-1, 2, size=(N, 2)).astype(np.float64)
+    x = rng.random((C, h * s, w * s))
+    lr = rng.random((N, C, h, w))
+    wts = 0.5 + rng.random(x.shape)
+    ev = OracleRowEvaluator(o.Model(s, psf, shifts), lr, o.REG_TV, 0.02, wts, rpu=6)
+    n = x.size
+    # reach of a gradient row into x: PSF twice + the shift twice (warp and its transpose) + 1 row of TV
+    halo_rows = 2 * (K // 2) + 2 * 1 + 1
+    obj = sharding.RowBandObjective(ev, n, w * s, halo_rows, dist=dist)
+    x_local = torch.full((n,), float("nan"), dtype=torch.float64)
+    x_local[obj.begin:obj.end] = torch.from_numpy(x.reshape(-1)[obj.begin:obj.end])
+    g = torch.zeros(n, dtype=torch.float64)
+    cost = torch.zeros(1, dtype=torch.float64)
+    obj.evaluate(x_local, g, cost)
+    assert not torch.isnan(g[obj.begin:obj.end]).any()
+    np.save(out, np.concatenate([g.numpy(), cost.numpy()]))
+
+
 def main():
     rank, world, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    if os.environ.get("SRB_TEST_PARTITION") == "rows":
+        main_rows(rank, world, out)
+        dist.destroy_process_group()
+        return
     rng = np.random.default_rng(7)
     C, h, w, s, K, N = 2, 12, 10, 2, 3, 5
     psf = o.gaussian_psf(K, 1.0)

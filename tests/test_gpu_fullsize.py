@@ -139,3 +139,53 @@ def test_cfg5_shaped_many_frames_vs_oracle(srb, oracle):
         assert e.active_path == srb.PATH_FUSED
     assert abs(f - fo) <= 1e-12 * abs(fo)
     assert rel(g, go) <= 1e-12
+
+
+def _crop_check(oracle, w, g_gpu, x, wts, okind, lam, ch, r0, c0, size, margin):
+    """Oracle on an HR crop [r0-margin, r0+size+margin) x [c0-margin, ...) of channel `ch`, all frames (clipped at
+    the image: a crop that touches the image border keeps the real border there).  The data term and the 2-D
+    regularizers are local, so away from the crop's ARTIFICIAL borders the oracle's gradient of the cropped problem
+    is the gradient of the full problem: compared on [r0, r0+size) x [c0, c0+size)."""
+    s = w["s"]
+    H, W = x.shape[1:]
+    R0, R1 = max(r0 - margin, 0), min(r0 + size + margin, H)
+    C0, C1 = max(c0 - margin, 0), min(c0 + size + margin, W)
+    assert R0 % s == 0 and C0 % s == 0 and R1 % s == 0 and C1 % s == 0
+    xc = np.ascontiguousarray(x[ch:ch + 1, R0:R1, C0:C1])
+    wc = np.ascontiguousarray(wts[ch:ch + 1, R0:R1, C0:C1])
+    lrc = np.ascontiguousarray(w["lr"][:, ch:ch + 1, R0 // s:R1 // s, C0 // s:C1 // s])
+    m = oracle.Model(s, w["psf"], w["shifts"])
+    _, gc = oracle.evaluate(m, xc, oracle.upsample_observations(m, lrc), okind, lam, wc, btv_range=w["btv_range"],
+                            btv_decay=w["btv_decay"], threads=8)
+    a = g_gpu[ch, r0:r0 + size, c0:c0 + size]
+    b = gc[0, r0 - R0:r0 - R0 + size, c0 - C0:c0 - C0 + size]
+    return rel(a, b)
+
+
+@pytest.mark.parametrize("cfg", [3, 4, 5])
+def test_full_size_gradient_against_the_oracle_on_crops(srb, oracle, cfg):
+    """BASELINE configurations 3, 4 and 5 at their real sizes (2048^2 x 3 x 16 frames; 1024^2 x 128 bands x 8 frames;
+    4096^2 x 3 x 64 frames, BTV) evaluated on the GPU; the CPU oracle evaluates crops of the same problem -- an
+    interior block, the top-left and the bottom-right image corners (real borders, incl. the border band of special
+    samples) -- in first, middle and last channel.  Fused-path bar: 1e-12 relative L2 per block."""
+    cf, w = _workload(cfg)
+    x = w["x0"]
+    rng = np.random.default_rng(100 + cfg)
+    wts = 0.5 + rng.random(x.shape)
+    okind = {0: oracle.REG_TV, 2: oracle.REG_BTV}[w["reg_kind"]]
+    with srb.Engine(w["lr"].shape, w["s"], w["psf"], w["shifts"]) as e:
+        e.set_observations(w["lr"])
+        e.set_regularizer(w["reg_kind"], w["lam"], w["btv_range"], w["btv_decay"])
+        e.set_irls_weights(wts)
+        assert e.active_path == srb.PATH_FUSED and e.zlayout_active
+        f, g = e.eval(x)
+    assert np.isfinite(f) and f > 0
+    H, W, Cn = cf["H"], cf["W"], cf["C"]
+    size, margin = 96, 32
+    blocks = [(H // 2 + 32, W // 2 - 64), (0, 0), (H - size, W - size), (0, W // 2), (H // 2, 0)]
+    worst = 0.0
+    for ch in sorted({0, Cn // 2, Cn - 1}):
+        for (r0, c0) in blocks:
+            worst = max(worst, _crop_check(oracle, w, g, x, wts, okind, w["lam"], ch, r0, c0, size, margin))
+    print("cfg%d full size: worst block rel L2 vs oracle %.3e" % (cfg, worst))
+    assert worst <= 1e-12

@@ -146,3 +146,42 @@ def test_reference_solver_drives_several_gpus_through_the_adapter(srb, oracle, r
     assert stm.num_data_term_evals == st1.num_data_term_evals
     assert rel_l2(many, one) <= 1e-9
     assert rel_l2(many, truth) < rel_l2(x0, truth)
+
+
+def test_unit_ranges_of_the_whole_objective(srb, oracle):
+    """srb_eval_unit_range_dev (the row-band partition with one process per GPU): a range of (channel, tile row)
+    units evaluated from an estimate that is valid ONLY on the range's rows plus the stencil halo gives exactly the
+    gradient rows of the full evaluation, and the range costs add up to the full cost."""
+    import torch
+    sharding = import_module("super-resolution_b200.sharding")
+    psf, shifts, lr, x, wts = _case(16, 4, 7, 1.5, 2, 72, 80, seed=5)
+    H, W = 288, 320
+    for reg, kind in (("tv", srb.REG_TV), ("btv", srb.REG_BTV)):
+        with srb.Engine(lr.shape, 4, psf, shifts) as e:
+            e.set_observations(lr)
+            e.set_regularizer(kind, 0.01)
+            e.set_irls_weights(wts)
+            f_full, g_full = e.eval(x)
+            nu, rpu = e.num_units()
+            assert nu == 2 * 9 and rpu == 32
+            halo = sharding.stencil_halo_rows(7, kind, 3) * W
+            stream = torch.cuda.ExternalStream(e.stream_handle())
+            with torch.cuda.stream(stream):
+                g_dev = torch.zeros(x.size, dtype=torch.float64, device="cuda")
+                cost_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
+                total = 0.0
+                for world in (1, 3, 4):
+                    total = 0.0
+                    g_dev.zero_()
+                    for r in range(world):
+                        u0, u1 = sharding.unit_band(nu, r, world)
+                        b, en = e.unit_range(u0, u1)
+                        xl = np.full(x.size, np.nan)
+                        lo, hi = max(b - halo, 0), min(en + halo, x.size)
+                        xl[lo:hi] = x.reshape(-1)[lo:hi]
+                        x_dev = torch.from_numpy(xl).cuda()
+                        e.eval_unit_range_dev(x_dev, g_dev, u0, u1, cost_dev)
+                        stream.synchronize()
+                        total += float(cost_dev.cpu()[0])
+                    np.testing.assert_array_equal(g_dev.cpu().numpy().reshape(x.shape), g_full)
+                    assert abs(total - f_full) <= 1e-13 * abs(f_full), (reg, world)
