@@ -488,7 +488,7 @@ def main():
         try:
             stream_r = torch.cuda.ExternalStream(eng.stream_handle(), device=dev)
             with torch.cuda.stream(stream_r):
-                halo = sharding.stencil_halo_rows(cf["K"], work["reg_kind"], work_r["btv_range"])
+                halo = eng.halo_rows()
                 robj = sharding.RowBandObjective(sharding.EngineEvaluator(eng), n, W, halo, dist=dist)
                 cost_dev = torch.zeros(1, dtype=torch.float64, device=dev)
                 for _ in range(warmup):

@@ -256,10 +256,13 @@ srb_status srb_eval_finish_dev(srb_ctx* ctx, const double* x_dev, double* gradie
  * rank's context holds EVERY frame; a rank evaluates units [unit_begin, unit_end) of the whole objective -- the
  * gradient rows it writes are final, no cross-rank sum of the gradient exists -- and *cost_dev (device, may be
  * NULL) receives the cost of exactly those units, ready for a scalar allreduce.  x_dev must be current on the
- * rank's rows plus the halo the stencils reach (2 * PSF half width + 1 rows, + R for BTV), which neighbouring
- * ranks exchange (sharding.RowBandObjective).  Needs srb_num_units > 1 (fused path, no border band). */
+ * rank's rows plus srb_halo_rows() rows either side (what the stencils reach: the PSF twice, + 1 for TV or R for BTV,
+ * + twice the largest shift for models with a border band), which neighbouring ranks exchange
+ * (sharding.RowBandObjective).  Units are (channel, 32-row tile) in memory order, tile_rows = ceil(H / 32) per channel.
+ * Needs the fused path and a regularizer it covers (SRB_ERR_STATE otherwise). */
 srb_status srb_eval_unit_range_dev(srb_ctx* ctx, const double* x_dev, double* gradient_dev, int unit_begin,
                                    int unit_end, double* cost_dev);
+int srb_halo_rows(const srb_ctx* ctx);
 
 /* ---- multi-GPU peer path: reduce-scatter / all-gather over NVLink peer memory ------------------
  * One process per GPU.  Every rank owns a contiguous band of gradient units.  The tile kernel
@@ -317,8 +320,8 @@ srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, uns
  * bands of x (plus the few halo rows the PSF and regularizer stencils reach) from the host and returns its
  * bands of the gradient, which are final -- no exchange between the devices at all, and compute, H2D and D2H
  * per device all drop by n_gpus.  Costs n_gpus copies of the observations in HBM (cfg3 100 MB, cfg5 1.6 GB
- * per device).  Applies when the tile kernel covers the whole image (no border band of special samples) with
- * a regularizer other than 3-D TV; otherwise device 0 evaluates alone.  srb_multi_create takes the partition
+ * per device).  Applies when the fused tile kernel covers the model, with a regularizer other than 3-D TV (which
+ * couples the channels); otherwise device 0 evaluates alone.  srb_multi_create takes the partition
  * from SRB_MULTI_PARTITION=frames|rows in the environment (default frames). */
 enum { SRB_PARTITION_FRAMES = 0, SRB_PARTITION_ROWS = 1 };
 typedef struct srb_multi srb_multi;

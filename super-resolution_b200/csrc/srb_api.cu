@@ -873,36 +873,46 @@ srb_status srb_eval_finish_dev(srb_ctx* c, const double* x_dev, double* gc_dev) 
 
 // Row-band partition, one process per GPU: units [u0, u1) of the WHOLE objective (this context holds every frame)
 // and the cost of exactly those units -- a rank's share; the gradient rows written are final.
+// units of the whole objective can be evaluated range by range: fused path with a regularizer it covers (a border
+// band is evaluated by rows too)
+static bool unit_ranges_ok(const srb_ctx* c) {
+  const bool reg_ok = !reg_active(c) || fused_reg_covered(c);
+  return resolve_path(c) == SRB_PATH_FUSED && tile_state(c) && reg_ok;
+}
+
 srb_status srb_eval_unit_range_dev(srb_ctx* c, const double* x_dev, double* g_dev, int u0, int u1, double* cost_dev) {
   if (!c) return SRB_ERR_INVALID;
   if (!x_dev) return c->fail(SRB_ERR_INVALID, "null buffer");
   if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
-  if (!units_pipelined(c)) return c->fail(SRB_ERR_STATE, "unit ranges need the fused tile kernel without a border band");
-  int nu = 0;
-  srb_num_units(c, &nu, nullptr);
+  if (!unit_ranges_ok(c)) return c->fail(SRB_ERR_STATE, "unit ranges need the fused tile kernel and a regularizer it covers");
+  const int nu = tile_rows_per_channel(c) * c->Ca();
   if (u0 < 0 || u1 > nu || u1 < u0) return c->fail(SRB_ERR_INVALID, "invalid unit range");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
   const TileLayout L = tile_layout(c);
+  {
+    srb_status st = ensure_partials(c, 2 * L.nblocks + L.nband);
+    if (st != SRB_OK) return st;
+  }
+  if (L.nband) SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_partial + L.nblocks, 0, L.nband * sizeof(double), c->stream));
   if (u1 > u0) {
     const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
     bool reg_done = false;
     srb_status st = fused_eval_units(c, x_dev, g_dev, do_reg, u0, u1, &reg_done);
     if (st != SRB_OK) return st;
-  } else {
-    const size_t need = 2 * L.nblocks + L.nband;
-    srb_status st = ensure_partials(c, need);
-    if (st != SRB_OK) return st;
+    if ((st = fused_band_units(c, x_dev, g_dev, u0, u1)) != SRB_OK) return st;
   }
   // the cost slots of units [u0, u1) are contiguous: slot = unit * tiles_per_row + tile column
   const size_t per_unit = L.nblocks / (size_t)nu;
   const size_t first = (size_t)u0 * per_unit, count = (size_t)(u1 - u0) * per_unit;
-  k_finish_partials<<<1, 1024, 0, c->stream>>>(c->d_partial + first, count, c->d_partial + L.nblocks + L.nband + first, count,
-                                               c->d_cost, cost_dev);
+  k_finish_partials3<<<1, 1024, 0, c->stream>>>(c->d_partial + first, count, c->d_partial + L.nblocks, L.nband,
+                                                c->d_partial + L.nblocks + L.nband + first, count, c->d_cost, cost_dev);
   c->timing.kernel_launches += 1;
   SRB_CUDA_CHECK(c, cudaGetLastError());
   c->timing.num_evals += 1;
   return SRB_OK;
 }
+
+int srb_halo_rows(const srb_ctx* c) { return (c && tile_state(c)) ? stencil_halo_rows(c) : 0; }
 
 // ---- multi-GPU peer path ------------------------------------------------------------------------
 srb_status srb_dev_alloc(void** ptr, unsigned long long bytes) {

@@ -54,21 +54,40 @@ struct BandGroups {
   const double* yband;
 };
 
+// Row-band partition (every device evaluates the whole objective on its own gradient rows): the band kernels
+// restricted to the rows of one device.  The device owns, of active channel c, HR rows [lo(c), hi(c)) with
+//   lo(c) = c == ch_first ? row_first : 0,   hi(c) = c == ch_last ? row_last : H     (nothing outside [ch_first, ch_last]).
+// The adjoint kernel adds into those rows only; the forward kernel evaluates the samples those rows can reach
+// (s * qr within `pad` HR rows of them) and counts the cost of the samples whose own HR row s * qr they contain.
+// accumulate = 1: cost slots are added to (several launches per evaluation; the caller zeroes them first).
+struct BandRows {
+  int ch_first, row_first, ch_last, row_last, pad, accumulate;
+  __host__ __device__ bool rows_of(int c, int H, int* lo, int* hi) const {
+    if (c < ch_first || c > ch_last) return false;
+    *lo = c == ch_first ? row_first : 0;
+    *hi = c == ch_last ? row_last : H;
+    return *hi > *lo;
+  }
+};
+
 // Forward model + residual of the special samples in the reference's operation order
 // (forward_pixel): pooled[(k*Ca + c) * count + i] = s^2-fold sum of r, cost partials s^2 r^2.
 // grid: (ceil(count/256), N*Ca)  (N = number of groups when frames are merged)
 __global__ void __launch_bounds__(256)
-k_band_forward(GenericParams P, BandGeom B, BandGroups M, const double* __restrict__ x, const double* __restrict__ y,
-               double* __restrict__ pooled, double* __restrict__ cost_partial) {
+k_band_forward(GenericParams P, BandGeom B, BandGroups M, BandRows RW, const double* __restrict__ x,
+               const double* __restrict__ y, double* __restrict__ pooled, double* __restrict__ cost_partial) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long cnt = B.count();
   const int kc = blockIdx.y;
   const int kg = kc / P.Ca, c = kc % P.Ca;
   const int k = M.groups ? M.frame[kg] : kg;
   double cost = 0.0;
-  if (i < cnt) {
-    int qr, qc;
-    B.sample_of(i, &qr, &qc);
+  int rlo = 0, rhi = P.H;
+  const bool have_rows = RW.rows_of(c, P.H, &rlo, &rhi);
+  int qr = 0, qc = 0;
+  if (i < cnt) B.sample_of(i, &qr, &qc);
+  const int hr = qr * P.s;  // the sample's own HR row
+  if (i < cnt && have_rows && hr >= rlo - RW.pad && hr < rhi + RW.pad) {
     const size_t HW = (size_t)P.H * P.W, hw = (size_t)P.h * P.w;
     const double pred = forward_pixel(P, x + (size_t)c * HW, k, qr, qc);
     const double obs = M.groups ? M.yband[((size_t)kg * P.Ct + P.c0 + c) * cnt + i]
@@ -79,10 +98,13 @@ k_band_forward(GenericParams P, BandGeom B, BandGroups M, const double* __restri
     for (int t = 0; t < reps; ++t) acc = __dadd_rn(acc, r);
     const double nf = M.groups ? (double)M.n : 1.0;
     pooled[(size_t)kc * cnt + i] = nf * acc;
-    cost = nf * ((double)reps * (r * r));
+    if (hr >= rlo && hr < rhi) cost = nf * ((double)reps * (r * r));
   }
   const double bs = block_sum(cost);
-  if (threadIdx.x == 0) cost_partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = bs;
+  if (threadIdx.x == 0) {
+    double* slot = cost_partial + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    *slot = RW.accumulate ? *slot + bs : bs;
+  }
 }
 
 // B^T D^T restricted to the special samples of one frame, at HR pixel (pr, pc) (cf.
@@ -128,13 +150,15 @@ __device__ __forceinline__ double band_backproject(const GenericParams& P, const
 // and [R.hi_c, W)  (R is the BandGeom of the HR-pixel band, B the one of the LR samples).
 // grid: (ceil(R.count()/256), Ca)
 __global__ void __launch_bounds__(256)
-k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, BandGroups M, int sshift, const double* __restrict__ pooled,
-               double* __restrict__ g) {
+k_band_adjoint(GenericParams P, BandGeom B, BandGeom R, BandGroups M, BandRows RW, int sshift,
+               const double* __restrict__ pooled, double* __restrict__ g) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= R.count()) return;
   int pr, pc;
   R.sample_of(i, &pr, &pc);
   const int c = blockIdx.y;
+  int rlo, rhi;
+  if (!RW.rows_of(c, P.H, &rlo, &rhi) || pr < rlo || pr >= rhi) return;
   const long long cnt = B.count();
   double acc = 0.0;
   const int ng = M.groups ? M.groups : P.N;
@@ -221,6 +245,25 @@ k_stage_partials(const double* __restrict__ pd, size_t nd, const double* __restr
   if (threadIdx.x == 0) {
     stage[blockIdx.x] = a;
     stage[gridDim.x + blockIdx.x] = b;
+  }
+}
+
+// k_finish_partials with the data partials in two ranges (a device's own tiles + the border band slots).
+__global__ void __launch_bounds__(1024)
+k_finish_partials3(const double* __restrict__ pd, size_t nd, const double* __restrict__ pb, size_t nb,
+                   const double* __restrict__ pr, size_t nr, double* __restrict__ cost, double* __restrict__ tail) {
+  double a = 0.0, b = 0.0;
+  for (size_t i = threadIdx.x; i < nd; i += blockDim.x) a += pd[i];
+  for (size_t i = threadIdx.x; i < nb; i += blockDim.x) a += pb[i];
+  for (size_t i = threadIdx.x; i < nr; i += blockDim.x) b += pr[i];
+  a = block_sum(a);
+  b = block_sum(b);
+  if (threadIdx.x == 0) {
+    cost[0] = a;
+    cost[1] = b;
+    const double t = a + b;
+    cost[2] = t;
+    if (tail) *tail = t;
   }
 }
 

@@ -141,9 +141,14 @@ inline srb_status multi_plan_bands(srb_multi* m) {
   const int G = m->G;
   srb_ctx* c0 = m->rank[0];
   m->pipelined = true;
-  for (int r = 0; r < G; ++r) m->pipelined = m->pipelined && units_pipelined(m->rank[r]);
+  bool ranges_ok = true;
+  for (int r = 0; r < G; ++r) {
+    m->pipelined = m->pipelined && units_pipelined(m->rank[r]);
+    ranges_ok = ranges_ok && unit_ranges_ok(m->rank[r]);
+  }
   const long long n = (long long)c0->n_active();
-  if (m->pipelined) {
+  // rows partition: unit-aligned bands whenever unit ranges can be evaluated (a border band is cut by rows too)
+  if (m->partition == SRB_PARTITION_ROWS ? ranges_ok : m->pipelined) {
     const int Ca = c0->Ca();
     const int tr = tile_rows_per_channel(c0), TH = tile_height(c0);
     static const int env_groups = getenv("SRB_MULTI_GROUPS") ? atoi(getenv("SRB_MULTI_GROUPS")) : 0;
@@ -172,17 +177,9 @@ inline srb_status multi_plan_bands(srb_multi* m) {
       m->band_elem[0][o] = o == G ? n : ((n * o / G) & ~1LL);
     }
   }
-  m->rows_ok = m->pipelined && host_slices_ok(c0);
+  m->rows_ok = ranges_ok && host_slices_ok(c0);
   m->bands_valid = true;
   return SRB_OK;
-}
-
-// HR rows of x that the tile kernel and the fused / tiled regularizers read around a gradient row: the PSF
-// twice (forward and adjoint pass), one row for TV, R for BTV.
-inline int multi_halo_rows(const srb_ctx* c) {
-  int reg = 0;
-  if (reg_active(c)) reg = c->reg_kind == SRB_REG_BTV ? c->btv_R : 1;
-  return 2 * c->g.hk + std::max(reg, 1);
 }
 
 // Rows partition (SRB_PARTITION_ROWS): every device holds every frame and evaluates the WHOLE objective on its
@@ -204,7 +201,7 @@ inline srb_status multi_eval_rows(srb_multi* m, const double* x_host, double* g_
       const bool have = m->band_unit[g][r + 1] > m->band_unit[g][r];
       if (have) {
         // band + halo, clipped to the channels the band touches (no stencil crosses a channel boundary)
-        const long long P = (long long)c->P, W = c->g.W, halo = (long long)multi_halo_rows(c) * W;
+        const long long P = (long long)c->P, W = c->g.W, halo = (long long)stencil_halo_rows(c) * W;
         const long long lo = std::max(be[r] - halo, be[r] / P * P);
         const long long hi = std::min(be[r + 1] + halo, (be[r + 1] + P - 1) / P * P);
         SRB_MULTI_CHECK(m, cudaMemcpyAsync(c->d_x + lo, x_host + lo, (size_t)(hi - lo) * sizeof(double),
@@ -231,9 +228,11 @@ inline srb_status multi_eval_rows(srb_multi* m, const double* x_host, double* g_
         srb_status st = fused_eval_units(c, c->d_x, g_host ? c->d_grad : nullptr, do_reg, m->band_unit[g][r],
                                          m->band_unit[g][r + 1], &reg_done);
         if (st != SRB_OK) return multi_status(m, r, st);
+        st = fused_band_units(c, c->d_x, g_host ? c->d_grad : nullptr, m->band_unit[g][r], m->band_unit[g][r + 1]);
+        if (st != SRB_OK) return multi_status(m, r, st);
       }
       if (g == NG - 1) {
-        srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr);
+        srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr, /*run_band=*/false);
         if (st != SRB_OK) return multi_status(m, r, st);
         c->timing.num_evals += 1;
         SRB_MULTI_CHECK(m, cudaMemcpyAsync(m->h_cost[r], c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

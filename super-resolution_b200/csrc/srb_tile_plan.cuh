@@ -48,6 +48,7 @@ struct TilePlan {
   // zt_n > 1: the groups of frames with equal shifts = the non-empty sub-pixel phases: their phase index and one
   // frame of each (the band kernels walk groups instead of frames, srb_kernels_band.cuh)
   std::vector<int> group_phase, group_frame;
+  int max_shift = 0;   // largest |shift| over the frames, HR pixels, rounded up (+1 for the bilinear partner)
 };
 
 struct TileState {
@@ -188,6 +189,7 @@ inline void plan_tile_model(const Geometry& G, const std::vector<double>& psf_h,
     }
     if (lo[dim] >= hi[dim]) { st->why = "image too small for the shifts (every sample is a border sample)"; return; }
   }
+  st->max_shift = max_shift;
   st->band = BandGeom{G.h, G.w, lo[0], hi[0], lo[1], hi[1]};
   st->has_band = st->band.count() > 0;
   {
@@ -741,34 +743,72 @@ inline srb_status fused_eval_units(srb_ctx* c, const double* d_x, double* d_g, b
   return reg_tile_launch(c, d_x, d_g, do_reg, unit_begin, unit_end, P.part_reg, reg_done);
 }
 
-// After every unit has been evaluated: the border band (exact, reference order) and the cost.
-// Leaves the data cost in d_cost[0], the fused regularization cost in d_cost[1] and their sum in
-// d_cost[2] (and *tail).
-inline srb_status fused_eval_finish(srb_ctx* c, const double* d_x, double* d_g, double* tail) {
+// The border band (exact, reference order) of the whole image, or -- rows != NULL -- of one device's gradient rows.
+inline srb_status fused_band(srb_ctx* c, const double* d_x, double* d_g, const BandRows* rows) {
   const TileState* st = tile_state(c);
+  if (!st->has_band) return SRB_OK;
   const Geometry& G = c->g;
   const int Ca = c->Ca();
   const TileLayout L = tile_layout(c);
-  if (st->has_band) {
-    GenericParams GP;
-    GP.H = G.H; GP.W = G.W; GP.h = G.h; GP.w = G.w; GP.s = G.s; GP.K = G.K; GP.hk = G.hk;
-    GP.N = G.N; GP.Ca = Ca; GP.Ct = G.Ct; GP.c0 = c->c0;
-    GP.src_r = c->d_src_r; GP.src_c = c->d_src_c; GP.psf = c->d_psf;
-    GP.rowY = c->d_rowY_fwd; GP.nX = c->d_nX_fwd;
-    BandGroups M{0, 1, nullptr, nullptr};
-    if (st->band_groups > 0 && st->yz_valid) M = BandGroups{st->band_groups, st->plan.zt_n, st->d_group_frame, st->d_yband};
-    int sshift = -1;
-    for (int b = 0; b < 5; ++b)
-      if ((1 << b) == G.s) sshift = b;
-    k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, M, d_x, c->d_y, st->d_pooled,
-                                                   c->d_partial + L.nblocks);
+  GenericParams GP;
+  GP.H = G.H; GP.W = G.W; GP.h = G.h; GP.w = G.w; GP.s = G.s; GP.K = G.K; GP.hk = G.hk;
+  GP.N = G.N; GP.Ca = Ca; GP.Ct = G.Ct; GP.c0 = c->c0;
+  GP.src_r = c->d_src_r; GP.src_c = c->d_src_c; GP.psf = c->d_psf;
+  GP.rowY = c->d_rowY_fwd; GP.nX = c->d_nX_fwd;
+  BandGroups M{0, 1, nullptr, nullptr};
+  if (st->band_groups > 0 && st->yz_valid) M = BandGroups{st->band_groups, st->plan.zt_n, st->d_group_frame, st->d_yband};
+  int sshift = -1;
+  for (int b = 0; b < 5; ++b)
+    if ((1 << b) == G.s) sshift = b;
+  const BandRows whole{0, 0, Ca - 1, G.H, 0, 0};
+  const BandRows RW = rows ? *rows : whole;
+  k_band_forward<<<L.bgrid, 256, 0, c->stream>>>(GP, st->band, M, RW, d_x, c->d_y, st->d_pooled, c->d_partial + L.nblocks);
+  c->timing.kernel_launches += 1;
+  if (d_g) {
+    GP.rowY = c->d_rowY_tr; GP.nX = c->d_nX_tr;
+    const dim3 rgrid((unsigned)((st->reach.count() + 255) / 256), (unsigned)Ca);
+    k_band_adjoint<<<rgrid, 256, 0, c->stream>>>(GP, st->band, st->reach, M, RW, sshift, st->d_pooled, d_g);
     c->timing.kernel_launches += 1;
-    if (d_g) {
-      GP.rowY = c->d_rowY_tr; GP.nX = c->d_nX_tr;
-      const dim3 rgrid((unsigned)((st->reach.count() + 255) / 256), (unsigned)Ca);
-      k_band_adjoint<<<rgrid, 256, 0, c->stream>>>(GP, st->band, st->reach, M, sshift, st->d_pooled, d_g);
-      c->timing.kernel_launches += 1;
-    }
+  }
+  return SRB_OK;
+}
+
+// HR rows of x around a gradient row that an evaluation reads: the PSF twice (forward and adjoint pass), one row for
+// TV / R for BTV, and -- for models with a border band, whose samples are evaluated through the full warp -- the
+// largest shift twice.
+inline int stencil_halo_rows(const srb_ctx* c) {
+  const TileState* st = tile_state(c);
+  int reg = 1;
+  if (c->reg_kind == SRB_REG_BTV && c->lambda > 0.0) reg = c->btv_R;
+  int halo = 2 * c->g.hk + reg;
+  if (st && st->has_band) halo += 2 * st->plan.max_shift + 1;
+  return halo;
+}
+
+// The border band restricted to the gradient rows of units [u0, u1) (row-band partition): cost slots accumulate.
+inline srb_status fused_band_units(srb_ctx* c, const double* d_x, double* d_g, int u0, int u1) {
+  const TileState* st = tile_state(c);
+  if (!st->has_band || u1 <= u0) return SRB_OK;
+  const int tr = tile_rows_per_channel(c), TH = tile_height(c), H = c->g.H;
+  BandRows RW;
+  RW.ch_first = u0 / tr;
+  RW.row_first = std::min(H, (u0 - RW.ch_first * tr) * TH);
+  RW.ch_last = (u1 - 1) / tr;
+  RW.row_last = std::min(H, (u1 - RW.ch_last * tr) * TH);
+  RW.pad = c->g.hk + st->plan.max_shift + 1;
+  RW.accumulate = 1;
+  return fused_band(c, d_x, d_g, &RW);
+}
+
+// After every unit has been evaluated: the border band and the cost.
+// Leaves the data cost in d_cost[0], the fused regularization cost in d_cost[1] and their sum in
+// d_cost[2] (and *tail).  run_band = false: the band has been evaluated already (fused_band_units).
+inline srb_status fused_eval_finish(srb_ctx* c, const double* d_x, double* d_g, double* tail, bool run_band = true) {
+  const TileState* st = tile_state(c);
+  const TileLayout L = tile_layout(c);
+  if (run_band) {
+    srb_status bs = fused_band(c, d_x, d_g, nullptr);
+    if (bs != SRB_OK) return bs;
   }
   const size_t nd = L.nblocks + L.nband;
   if (nd + L.nblocks >= 32768) {  // large tile counts: a parallel first stage, then the closing block

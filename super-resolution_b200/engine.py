@@ -56,6 +56,7 @@ SIGNATURES = {
     "srb_eval_units_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "srb_eval_finish_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "srb_eval_unit_range_dev": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "srb_halo_rows": (C.c_int, [_ctx_p]),
     "srb_set_profiling": (C.c_int, [_ctx_p, C.c_int]),
     "srb_peer_sizes": (C.c_int, [_ctx_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "srb_dev_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_ulonglong]),
@@ -413,6 +414,14 @@ class Engine:
         """Units [u0, u1) of the whole objective + their cost (row-band partition, srb_eval_unit_range_dev)."""
         self._check(self._lib.srb_eval_unit_range_dev(self._ctx, _dev_ptr(x_dev), _dev_ptr(g_dev), int(u0), int(u1),
                                                       _dev_ptr(cost_dev)))
+
+    def halo_rows(self):
+        """HR rows of x either side of a gradient row band that its evaluation reads (srb_halo_rows)."""
+        return self._lib.srb_halo_rows(self._ctx)
+
+    def total_units(self):
+        """(channel, 32-row tile) units of the active range, whether or not they can be pipelined."""
+        return (self.c1 - self.c0) * ((self.H + 31) // 32)
 
     def set_profiling(self, on=True):
         self._check(self._lib.srb_set_profiling(self._ctx, 1 if on else 0))

@@ -70,9 +70,10 @@ class RowBandObjective:
         self.ev, self.n, self.dist, self.group = evaluator, int(n), dist, group
         self.world = 1 if dist is None or not dist.is_initialized() else dist.get_world_size(group)
         self.rank = 0 if self.world == 1 else dist.get_rank(group)
-        nu = evaluator.num_units()
+        nu = evaluator.total_units() if hasattr(evaluator, "total_units") else evaluator.num_units()
+        rng = evaluator.row_unit_range if hasattr(evaluator, "row_unit_range") else evaluator.unit_range
         self.u0, self.u1 = unit_band(nu, self.rank, self.world)
-        self.begin, self.end = evaluator.unit_range(self.u0, self.u1)
+        self.begin, self.end = rng(self.u0, self.u1)
         self.halo = int(halo_rows) * int(width)            # elements exchanged with each neighbour
         # neighbours with a non-empty band (ranks beyond the number of units hold nothing)
         bands = [unit_band(nu, r, self.world) for r in range(self.world)]
@@ -80,7 +81,7 @@ class RowBandObjective:
         self.next = next((r for r in range(self.rank + 1, self.world) if bands[r][1] > bands[r][0]), None)
         self.empty = self.u1 <= self.u0
         for r in range(self.world):
-            b, e = evaluator.unit_range(*bands[r])
+            b, e = rng(*bands[r])
             if bands[r][1] > bands[r][0] and e - b < self.halo and self.world > 1:
                 raise ValueError("a rank's row band is thinner than the stencil halo: use fewer ranks")
 
@@ -119,6 +120,19 @@ class EngineEvaluator:
 
     def unit_range(self, u0, u1):
         return self.e.unit_range(u0, u1)
+
+    def total_units(self):
+        return self.e.total_units()
+
+    def row_unit_range(self, u0, u1):
+        """Element range of (channel, 32-row tile) units [u0, u1): valid whether or not the model pipelines."""
+        tr = (self.e.H + 31) // 32
+        P = self.e.H * self.e.W
+
+        def first(u):
+            ch, t = divmod(u, tr)
+            return ch * P + min(t * 32, self.e.H) * self.e.W
+        return first(u0), first(u1)
 
     def eval_units(self, x, gc, u0, u1):
         self.e.eval_units_dev(x, gc, u0, u1)

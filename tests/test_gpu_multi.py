@@ -148,40 +148,51 @@ def test_reference_solver_drives_several_gpus_through_the_adapter(srb, oracle, r
     assert rel_l2(many, truth) < rel_l2(x0, truth)
 
 
-def test_unit_ranges_of_the_whole_objective(srb, oracle):
+@pytest.mark.parametrize("K,reg", [(7, "tv"), (7, "btv"), (9, "tv"), (9, "btv"), (5, "none")])
+def test_unit_ranges_of_the_whole_objective(srb, oracle, K, reg):
     """srb_eval_unit_range_dev (the row-band partition with one process per GPU): a range of (channel, tile row)
-    units evaluated from an estimate that is valid ONLY on the range's rows plus the stencil halo gives exactly the
-    gradient rows of the full evaluation, and the range costs add up to the full cost."""
+    units evaluated from an estimate that is valid ONLY on the range's rows plus srb_halo_rows() rows either side
+    gives exactly the gradient rows of the full evaluation, and the range costs add up to the full cost.  K = 9 and
+    K = 5 models have a border band of special samples (bottom / right image edge), which is cut by rows too."""
     import torch
     sharding = import_module("super-resolution_b200.sharding")
-    psf, shifts, lr, x, wts = _case(16, 4, 7, 1.5, 2, 72, 80, seed=5)
-    H, W = 288, 320
-    for reg, kind in (("tv", srb.REG_TV), ("btv", srb.REG_BTV)):
-        with srb.Engine(lr.shape, 4, psf, shifts) as e:
-            e.set_observations(lr)
-            e.set_regularizer(kind, 0.01)
+    s = 4
+    N = 32 if K == 5 else 16                      # K = 5: two frames per phase, merged at upload
+    psf, shifts, lr, x, wts = _case(N, s, K, 1.5, 2, 72, 80, seed=5 + K)
+    kind = {"tv": srb.REG_TV, "btv": srb.REG_BTV, "none": srb.REG_NONE}[reg]
+    with srb.Engine(lr.shape, s, psf, shifts) as e:
+        e.set_observations(lr)
+        e.set_regularizer(kind, 0.01)
+        if reg != "none":
             e.set_irls_weights(wts)
-            f_full, g_full = e.eval(x)
-            nu, rpu = e.num_units()
-            assert nu == 2 * 9 and rpu == 32
-            halo = sharding.stencil_halo_rows(7, kind, 3) * W
-            stream = torch.cuda.ExternalStream(e.stream_handle())
-            with torch.cuda.stream(stream):
-                g_dev = torch.zeros(x.size, dtype=torch.float64, device="cuda")
-                cost_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
+        f_full, g_full = e.eval(x)
+        p = srb.plan(lr.shape, s, psf, shifts)
+        has_band = p["band_hi_r"] < 72 or p["band_lo_r"] > 0
+        assert has_band == (K != 7)
+        nu = e.total_units()
+        assert nu == 2 * 9
+        ev = sharding.EngineEvaluator(e)
+        halo = e.halo_rows() * e.W
+        stream = torch.cuda.ExternalStream(e.stream_handle())
+        with torch.cuda.stream(stream):
+            g_dev = torch.zeros(x.size, dtype=torch.float64, device="cuda")
+            cost_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
+            for world in (1, 3, 4):
                 total = 0.0
-                for world in (1, 3, 4):
-                    total = 0.0
-                    g_dev.zero_()
-                    for r in range(world):
-                        u0, u1 = sharding.unit_band(nu, r, world)
-                        b, en = e.unit_range(u0, u1)
-                        xl = np.full(x.size, np.nan)
-                        lo, hi = max(b - halo, 0), min(en + halo, x.size)
-                        xl[lo:hi] = x.reshape(-1)[lo:hi]
-                        x_dev = torch.from_numpy(xl).cuda()
-                        e.eval_unit_range_dev(x_dev, g_dev, u0, u1, cost_dev)
-                        stream.synchronize()
-                        total += float(cost_dev.cpu()[0])
-                    np.testing.assert_array_equal(g_dev.cpu().numpy().reshape(x.shape), g_full)
-                    assert abs(total - f_full) <= 1e-13 * abs(f_full), (reg, world)
+                g_dev.zero_()
+                for r in range(world):
+                    u0, u1 = sharding.unit_band(nu, r, world)
+                    b, en = ev.row_unit_range(u0, u1)
+                    xl = np.full(x.size, np.nan)
+                    lo, hi = max(b - halo, 0), min(en + halo, x.size)
+                    xl[lo:hi] = x.reshape(-1)[lo:hi]
+                    x_dev = torch.from_numpy(xl).cuda()
+                    e.eval_unit_range_dev(x_dev, g_dev, u0, u1, cost_dev)
+                    stream.synchronize()
+                    total += float(cost_dev.cpu()[0])
+                got = g_dev.cpu().numpy().reshape(x.shape)
+                if has_band:     # the band adds into the tile kernel's rows: same values, same order
+                    np.testing.assert_allclose(got, g_full, rtol=0, atol=1e-13 * np.abs(g_full).max())
+                else:
+                    np.testing.assert_array_equal(got, g_full)
+                assert abs(total - f_full) <= 1e-13 * abs(f_full), (reg, world)
