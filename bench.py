@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--solve-iters", type=int, default=SOLVE_ITERS,
                     help="CG iterations of the timed device-resident solve (0 = skip)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement")
+    ap.add_argument("--no-rows", action="store_true", help="N > 1: skip the row-band partition measurement")
     ap.add_argument("--reg", default=None, choices=["tv", "tv3d", "btv", "none"],
                     help="regularizer instead of the configuration's own (cfg4 is also quoted with 3-D TV)")
     return ap.parse_args()
@@ -249,10 +250,25 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _watchdog(seconds, code=3):
+    """A bench run must never hang a GPU box (a stuck collective at teardown would): hard exit after `seconds`."""
+    import threading
+
+    def fire():
+        sys.stderr.write("bench.py: watchdog fired after %d s -- exiting with code %d\n" % (seconds, code))
+        sys.stderr.flush()
+        os._exit(code)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     global REG_OVERRIDE
     args = parse_args()
     REG_OVERRIDE = args.reg
+    _watchdog(int(os.environ.get("SRB_BENCH_WATCHDOG_S", "900")))
     if args.impl == "reference":
         run_reference(args)
         return
@@ -478,7 +494,7 @@ def main():
 
     # ================= row-band partition (N > 1): every rank holds every frame, no gradient exchange ========
     rows_block = None
-    if world > 1 and not args.no_weak:
+    if world > 1 and not args.no_rows:
         eng.close()
         frames_all = list(range(n_frames))
         eng = srb.Engine((n_frames, C, H // s, W // s), s, psf, wl.default_shifts(n_frames, s), device=local_rank)
@@ -494,20 +510,47 @@ def main():
                 for _ in range(warmup):
                     robj.evaluate(x_dev, gc_dev, cost_dev)
                 barrier()
+                # one step = halo exchange + this rank's kernels + scalar allreduce; captured once as a CUDA graph
+                # (the launch sequence is identical every step) and replayed: the step is short enough for the CPU
+                # side of five launches and three NCCL calls to show otherwise.  SRB_ROWS_GRAPH=0: eager.
+                graph = None
+                if os.environ.get("SRB_ROWS_GRAPH", "1") == "1":
+                    try:
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph, stream=stream_r, capture_error_mode="thread_local"):
+                            robj.evaluate(x_dev, gc_dev, cost_dev)
+                    except Exception as gerr:
+                        graph = None
+                        if rank == 0:
+                            print("row-band step not captured as a CUDA graph (%s): eager launches" % str(gerr)[:120], file=sys.stderr)
+                ok = torch.tensor([1.0 if graph is not None else 0.0], dtype=torch.float64, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok.cpu()[0]) < 1.0:
+                    graph = None
+                run_step = graph.replay if graph is not None else (lambda: robj.evaluate(x_dev, gc_dev, cost_dev))
+                for _ in range(3):
+                    run_step()
+                barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream_r)
                 for _ in range(args.steps):
-                    robj.evaluate(x_dev, gc_dev, cost_dev)
+                    run_step()
                 e1.record(stream_r)
                 barrier()
                 (ms_r,) = reduce_max(e0.elapsed_time(e1) / args.steps)
+                captured = graph is not None
+                if graph is not None:      # the graph holds NCCL work: release it before the process group goes away
+                    stream_r.synchronize()
+                    graph.reset()
+                    graph = None
+                    run_step = None
                 rows_block = {"scaling": "strong", "frames_per_gpu": n_frames, "frames_total": n_frames,
                               "value": units / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r,
                               "cost_check": float(cost_dev.cpu()[0]),
                               "partition": "row bands of the HR image: every rank holds every frame and evaluates the whole "
                                            "objective on 1/%d of the (channel, tile row) units; per step %d halo rows of x "
                                            "to each neighbour (NCCL send/recv) + a scalar allreduce of the cost; no gradient "
-                                           "exchange" % (world, halo)}
+                                           "exchange; step %s" % (world, halo, "replayed as one CUDA graph" if captured else "launched eagerly")}
         except Exception as err:    # e.g. a model with a border band (cfg4 / cfg5): unit ranges do not apply
             rows_block = {"unavailable": str(err)[:200]}
         del work_r
@@ -562,7 +605,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_reference_run(args.config, args.cpu_sample, 3, 1, cores, also_single_thread=True)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    _watchdog(60, code=0)   # the line is out: nothing below (teardown of streams / process group) may keep the box busy
     # release every tensor that lives on the engine's stream before the stream goes away
     del x_dev, gc_dev, h_x, h_g
     torch.cuda.synchronize()
