@@ -691,6 +691,7 @@ srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {
 // ---- hot path -----------------------------------------------------------------------------------
 static bool units_pipelined(const srb_ctx* c);
 static bool host_slices_ok(const srb_ctx* c);
+static bool unit_ranges_ok(const srb_ctx* c);
 // srb_eval, pipelined: the estimate goes to the device in contiguous slices on a copy-in stream, the
 // tile kernel evaluates the units whose rows (and the halo rows of the next slice) have arrived, and
 // every finished gradient slice returns on a copy-out stream -- H2D, compute and D2H overlap, so the
@@ -698,13 +699,23 @@ static bool host_slices_ok(const srb_ctx* c);
 static srb_status eval_host_pipelined(srb_ctx* c, const double* x_host, double* g_host, double* cost) {
   c->x_resident = true;
   const int nu = tile_rows_per_channel(c) * c->Ca();
+  const TileLayout L0 = tile_layout(c);
+  if (L0.nband) {  // the border band is evaluated slice by slice too: its cost slots accumulate over the slices
+    srb_status pst = ensure_partials(c, 2 * L0.nblocks + L0.nband);
+    if (pst != SRB_OK) return pst;
+    SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_partial + L0.nblocks, 0, L0.nband * sizeof(double), c->stream));
+  }
   const int nch = std::max(1, std::min(c->pipe_chunks, nu));
   unsigned long long b[srb_ctx::kMaxPipe + 1];
   int u[srb_ctx::kMaxPipe + 1];
-  for (int i = 0; i <= nch; ++i) {
-    u[i] = (int)((long long)i * nu / nch);
-    unsigned long long e;
-    if (i < nch) srb_unit_range(c, u[i], u[i] + 1, &b[i], &e);
+  {
+    const int tr = tile_rows_per_channel(c), TH = tile_height(c);
+    for (int i = 0; i <= nch; ++i) {
+      u[i] = (int)((long long)i * nu / nch);
+      const int ch = u[i] / tr, t = u[i] - ch * tr;   // first element of unit u[i] (memory order)
+      const int row = t * TH < c->g.H ? t * TH : c->g.H;
+      b[i] = (unsigned long long)ch * c->P + (unsigned long long)row * c->g.W;
+    }
   }
   b[nch] = c->n_active();
   const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
@@ -722,6 +733,7 @@ static srb_status eval_host_pipelined(srb_ctx* c, const double* x_host, double* 
     bool reg_done = false;
     srb_status st = fused_eval_units(c, c->d_x, g_host ? c->d_grad : nullptr, do_reg, u[i], u[i + 1], &reg_done);
     if (st != SRB_OK) return st;
+    if ((st = fused_band_units(c, c->d_x, g_host ? c->d_grad : nullptr, u[i], u[i + 1])) != SRB_OK) return st;
     if (g_host) {
       cudaEventRecord(c->ev_k[i], c->stream);
       SRB_CUDA_CHECK(c, cudaStreamWaitEvent(c->s_out, c->ev_k[i], 0));
@@ -730,7 +742,7 @@ static srb_status eval_host_pipelined(srb_ctx* c, const double* x_host, double* 
                                         cudaMemcpyDeviceToHost, c->s_out));
     }
   }
-  srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr);
+  srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr, /*run_band=*/false);
   if (st != SRB_OK) return st;
   cudaEventRecord(c->ev[2], c->stream);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->h_cost, c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -753,7 +765,8 @@ srb_status srb_eval(srb_ctx* c, const double* x_host, double* g_host, double* co
   if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
   if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
-  if (units_pipelined(c) && host_slices_ok(c) && c->pipe_chunks > 1) return eval_host_pipelined(c, x_host, g_host, cost);
+  if (unit_ranges_ok(c) && host_slices_ok(c) && c->pipe_chunks > 1 && tile_rows_per_channel(c) * c->Ca() > 1)
+    return eval_host_pipelined(c, x_host, g_host, cost);
   const size_t bytes = c->n_active() * sizeof(double);
   cudaEventRecord(c->ev[0], c->stream);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));

@@ -478,6 +478,7 @@ srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* g_host, do
     if (!m->rank[r]->have_obs) return m->fail(SRB_ERR_STATE, "srb_multi_set_observations has not been called");
   if (G == 1) {
     srb_status st = srb_eval(m->rank[0], x_host, g_host, cost);
+    if (st == SRB_OK) m->timing.num_evals += 1;
     return multi_status(m, 0, st);
   }
   if (!m->bands_valid) {
@@ -488,7 +489,9 @@ srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* g_host, do
     if (m->rows_ok) return multi_eval_rows(m, x_host, g_host, cost);
     // a configuration that cannot be cut into row bands (border band of special samples, 3-D TV, a model the
     // tile kernel does not cover): every device holds the whole model, so device 0 evaluates it alone
-    return multi_status(m, 0, srb_eval(m->rank[0], x_host, g_host, cost));
+    srb_status st = srb_eval(m->rank[0], x_host, g_host, cost);
+    if (st == SRB_OK) m->timing.num_evals += 1;
+    return multi_status(m, 0, st);
   }
   const int NG = m->ngroups;
   MultiPtrs X, Gp;

@@ -39,6 +39,21 @@ def chunk_bounds(num_units, num_chunks):
     return [(edges[i], edges[i + 1]) for i in range(num_chunks) if edges[i + 1] > edges[i]]
 
 
+import contextlib
+
+
+def engine_stream(evaluator, tensor):
+    """Context in which torch's CURRENT stream is the engine's own CUDA stream.  The library launches its kernels on
+    the context's private stream while NCCL orders its collectives against torch's current stream: a collective on
+    a gradient slice may only start once the kernels that write the slice are done, so both must be the same
+    stream.  A no-op for CPU tensors and for evaluators without an engine (the gloo tests)."""
+    eng = getattr(evaluator, "e", evaluator)
+    if not getattr(tensor, "is_cuda", False) or not hasattr(eng, "stream_handle"):
+        return contextlib.nullcontext()
+    import torch
+    return torch.cuda.stream(torch.cuda.ExternalStream(eng.stream_handle(), device=tensor.device))
+
+
 def stencil_halo_rows(psf_size, reg_kind=-1, btv_range=3):
     """HR rows of x around a gradient row that the fused kernels read: the PSF twice (forward and adjoint pass) plus
     one row for TV / 3-D TV or R rows for BTV (csrc/srb_multi.cuh: multi_halo_rows)."""
@@ -102,11 +117,13 @@ class RowBandObjective:
             w.wait()
 
     def evaluate(self, x, g, cost):
-        """g[begin:end] <- this rank's final gradient band; cost[0] <- the whole objective's cost (all ranks)."""
-        self.exchange_halo(x)
-        self.ev.eval_unit_range(x, g, self.u0, self.u1, cost)
-        if self.world > 1:
-            self.dist.all_reduce(cost, group=self.group)
+        """g[begin:end] <- this rank's final gradient band; cost[0] <- the whole objective's cost (all ranks).
+        Runs on the engine's stream (engine_stream): halo, kernels and the scalar sum are ordered on one stream."""
+        with engine_stream(self.ev, x):
+            self.exchange_halo(x)
+            self.ev.eval_unit_range(x, g, self.u0, self.u1, cost)
+            if self.world > 1:
+                self.dist.all_reduce(cost, group=self.group)
 
 
 class EngineEvaluator:
@@ -149,7 +166,9 @@ class ShardedObjective:
 
     evaluate(x, gc): x is the replicated estimate, gc a buffer of n + 1 doubles; on return (after
     `wait()`, or immediately for synchronous backends) gc[:n] is the full gradient and gc[n] the
-    full cost on every rank.
+    full cost on every rank.  With a CUDA engine behind the evaluator the whole evaluation -- kernels and
+    collectives -- is issued with the engine's own stream as torch's current stream (engine_stream), so that every
+    allreduce is ordered behind the kernels that wrote its slice; results are valid on that stream.
     """
 
     def __init__(self, evaluator, n, dist=None, group=None, num_chunks=4):
@@ -183,6 +202,10 @@ class ShardedObjective:
         return self._agreed_units if self._agreed_units == mine else 1
 
     def evaluate(self, x, gc):
+        with engine_stream(self.ev, gc):
+            return self._evaluate(x, gc)
+
+    def _evaluate(self, x, gc):
         world = self._world()
         units = self._units(gc)
         chunks = chunk_bounds(units, self.num_chunks if world > 1 else 1)
@@ -293,12 +316,13 @@ class PeerObjective:
         self.dist.all_reduce(self._flag, group=self.group)
 
     def evaluate(self, x):
-        self.e.peer_scatter_dev(x)
-        if self._nccl_barrier:
-            self._barrier()
-        self.e.peer_gather_dev()
-        if self._nccl_barrier:
-            self._barrier()
+        with engine_stream(self.e, x):   # (only the optional NCCL barriers care: the peer kernels are the engine's)
+            self.e.peer_scatter_dev(x)
+            if self._nccl_barrier:
+                self._barrier()
+            self.e.peer_gather_dev()
+            if self._nccl_barrier:
+                self._barrier()
         return self
 
     def wait(self):
