@@ -692,6 +692,15 @@ srb_status srb_set_regularizer_rows(srb_ctx* c, int row_begin, int row_end) {
 static bool units_pipelined(const srb_ctx* c);
 static bool host_slices_ok(const srb_ctx* c);
 static bool unit_ranges_ok(const srb_ctx* c);
+// Slices of the host <-> device pipeline of srb_eval: at most pipe_chunks (SRB_PIPE_CHUNKS, default 16), at most one
+// per unit, and no slice below 4 MB -- a small problem (cfg2: 2 MB) is faster as one copy, one launch, one copy
+// than as a train of tiny launches.
+static int host_pipe_chunks(const srb_ctx* c) {
+  const int nu = tile_rows_per_channel(c) * c->Ca();
+  const long long by_size = (long long)(c->n_active() * sizeof(double)) / (4ll << 20);
+  return (int)std::max(1ll, std::min<long long>(std::min(c->pipe_chunks, nu), by_size));
+}
+
 // srb_eval, pipelined: the estimate goes to the device in contiguous slices on a copy-in stream, the
 // tile kernel evaluates the units whose rows (and the halo rows of the next slice) have arrived, and
 // every finished gradient slice returns on a copy-out stream -- H2D, compute and D2H overlap, so the
@@ -705,7 +714,7 @@ static srb_status eval_host_pipelined(srb_ctx* c, const double* x_host, double* 
     if (pst != SRB_OK) return pst;
     SRB_CUDA_CHECK(c, cudaMemsetAsync(c->d_partial + L0.nblocks, 0, L0.nband * sizeof(double), c->stream));
   }
-  const int nch = std::max(1, std::min(c->pipe_chunks, nu));
+  const int nch = host_pipe_chunks(c);
   unsigned long long b[srb_ctx::kMaxPipe + 1];
   int u[srb_ctx::kMaxPipe + 1];
   {
@@ -765,8 +774,7 @@ srb_status srb_eval(srb_ctx* c, const double* x_host, double* g_host, double* co
   if (!x_host) return c->fail(SRB_ERR_INVALID, "null estimate");
   if (!c->have_obs) return c->fail(SRB_ERR_STATE, "srb_set_observations has not been called");
   SRB_CUDA_CHECK(c, cudaSetDevice(c->device));
-  if (unit_ranges_ok(c) && host_slices_ok(c) && c->pipe_chunks > 1 && tile_rows_per_channel(c) * c->Ca() > 1)
-    return eval_host_pipelined(c, x_host, g_host, cost);
+  if (unit_ranges_ok(c) && host_slices_ok(c) && host_pipe_chunks(c) > 1) return eval_host_pipelined(c, x_host, g_host, cost);
   const size_t bytes = c->n_active() * sizeof(double);
   cudaEventRecord(c->ev[0], c->stream);
   SRB_CUDA_CHECK(c, cudaMemcpyAsync(c->d_x, x_host, bytes, cudaMemcpyHostToDevice, c->stream));
