@@ -759,7 +759,8 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
   tile_body<KH, FRAC, TH, FE>(P, map_x, map_w);
 }
 
-// ---- "Z layout" variant (opt-in, SRB_ZLAYOUT=1) ---------------------------
+// ---- row-major "Z layout" variant (round 1; kept behind SRB_ZT=0 for A/B runs -- the default Z-layout kernel is
+//      k_tile_zt, srb_kernels_tilez.cuh) ---------------------------------------
 // For models with integer shifts and exactly one frame per sub-pixel phase, every HR pixel receives
 // exactly one regular LR sample, and that sample reads the Bx element under it.  With the
 // observations gathered ONCE (at upload, k_build_yz) onto the HR grid, the residual pass of an
@@ -770,7 +771,7 @@ k_tile(const TileParams P, const __grid_constant__ CUtensorMap map_x,
 //     barrier) | Z = B - A in place in B, cost | adjoint horizontal B -> A | adjoint vertical -> g
 // Shared memory and registers are those of k_tile (4 CTAs / SM); tiles that touch the border band run
 // tile_body unchanged.
-//   HOLES (opt-in, SRB_ZLAYOUT=2): sub-pixel phases without a frame (a frame shard of a multi-GPU run
+//   HOLES: sub-pixel phases without a frame (a frame shard of a multi-GPU run
 //   holds N / G of the s^2 phases) are NaN in yz and contribute Z = 0.
 template <int KH, bool HOLES>
 __global__ void __launch_bounds__(256, KH <= 3 ? 4 : 3)

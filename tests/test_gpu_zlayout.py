@@ -1,5 +1,6 @@
-"""GPU parity of the opt-in "Z layout" variant of the fused tile kernel (k_tile_z, SRB_ZLAYOUT=1):
-observations gathered once onto the HR grid, residual pass elementwise from a TMA box.  Same bar
+"""GPU parity of the Z-layout tile kernel (k_tile_zt, the default for integer shifts with one distinct shift per
+sub-pixel phase; SRB_ZLAYOUT=0 selects k_tile for the A/B comparisons below): observations gathered once onto the HR
+grid -- frames with equal shifts averaged --, residual pass elementwise from a TMA box.  Same bar
 as the default fused path: cost and gradient within 1e-12 (relative L2) of the oracle, and of the
 default path on the same inputs."""
 import os

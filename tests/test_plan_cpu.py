@@ -24,7 +24,8 @@ def test_warp_quantisation_matches_the_oracle(oracle):
 
 
 def test_plans_of_the_baseline_configurations():
-    # z: Z layout (k_tile_z) -- 1 one frame on every phase, 2 at most one (opt-in), 0 does not qualify
+    # z: row-major Z layout (k_tile_z, round 1) -- 1 one frame on every phase, 2 at most one, 0 does not qualify;
+    # zt_frames (below): the transposed Z layout k_tile_zt, the default kernel of all five configurations
     expect = {1: dict(frac=0, kh=1, per_phase=(1, 1), table=1, z=1),
               2: dict(frac=0, kh=2, per_phase=(0, 1), table=0, z=2),     # 9 frames over 16 phases
               3: dict(frac=0, kh=3, per_phase=(1, 1), table=1, z=1),
