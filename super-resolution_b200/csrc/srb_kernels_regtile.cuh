@@ -66,26 +66,50 @@ __device__ __forceinline__ void btv_tile_body(const RegTileParams& P, double* __
   }
   __syncthreads();
   // ---- t_q = 2 lambda w_q r_q over the tile and the A rows / columns above / left of it; cost of the tile ----
+  // thread = (column qc, segment of VL rows): the (R+1) x (R+1) window of x slides down the column in registers, so
+  // a value costs R+1 shared-memory loads instead of (R+1)^2 - 1
   double cost = 0.0;
-  for (int id = tid; id < D::TR * D::TC; id += D::NT) {
-    const int qr = id / D::TC, qc = id - qr * D::TC;
-    const int gr = ty0 - D::A + qr, gc = tx0 - D::A + qc;
-    double t = 0.0;
-    if (!BORDER || (gr >= 0 && gc >= 0 && gr < P.H && gc < P.W)) {
-      const int imax = BORDER ? min(R, P.H - 1 - gr) : R, jmax = BORDER ? min(R, P.W - 1 - gc) : R;
-      const double* __restrict__ xq = xs + qr * D::XP + qc;
-      const double x0 = xq[0];
-      double r = 0.0;
+  constexpr int VSEG = D::NT / D::TC;                    // row segments that fit the CTA (3 for 66 columns)
+  constexpr int VL = (D::TR + VSEG - 1) / VSEG;          // rows per segment
+  static_assert(VSEG >= 1 && VSEG * VL >= D::TR, "value pass covers the region");
+  if (tid < D::TC * VSEG) {
+    const int qc = tid % D::TC, r0 = (tid / D::TC) * VL;
+    const int gc = tx0 - D::A + qc;
+    const int jmax = BORDER ? min(R, P.W - 1 - gc) : R;
+    const bool col_in = !BORDER || (gc >= 0 && gc < P.W);
+    double win[R + 1][R + 1];
 #pragma unroll
-      for (int i = 0; i <= R; ++i)
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j <= R; ++j)
-          if ((i | j) != 0 && (!BORDER || (i <= imax && j <= jmax)))
-            r = fma(P.decay[i + j], fabs(x0 - xq[i * D::XP + j]), r);
-      t = (P.two_lambda * wg[(size_t)gr * P.W + gc]) * r;
-      if (qr >= D::A && qc >= D::A && (!BORDER || (gr >= P.row0 && gr < P.row1))) cost = fma(t, r, cost);
+      for (int j = 0; j <= R; ++j) win[i][j] = (r0 + i < D::XR) ? xs[(r0 + i) * D::XP + qc + j] : 0.0;
+#pragma unroll
+    for (int l = 0; l < VL; ++l) {
+      const int qr = r0 + l;
+      if (qr < D::TR) {   // (qr + R < XR always: XR = TR + R)
+#pragma unroll
+        for (int j = 0; j <= R; ++j) win[R][j] = xs[(qr + R) * D::XP + qc + j];
+        const int gr = ty0 - D::A + qr;
+        double t = 0.0;
+        if (col_in && (!BORDER || (gr >= 0 && gr < P.H))) {
+          const int imax = BORDER ? min(R, P.H - 1 - gr) : R;
+          const double x0 = win[0][0];
+          double r = 0.0;
+#pragma unroll
+          for (int i = 0; i <= R; ++i)
+#pragma unroll
+            for (int j = 0; j <= R; ++j)
+              if ((i | j) != 0 && (!BORDER || (i <= imax && j <= jmax)))
+                r = fma(P.decay[i + j], fabs(x0 - win[i][j]), r);
+          t = (P.two_lambda * wg[(size_t)gr * P.W + gc]) * r;
+          if (qr >= D::A && qc >= D::A && (!BORDER || (gr >= P.row0 && gr < P.row1))) cost = fma(t, r, cost);
+        }
+        ts[qr * D::TP + qc] = t;
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j <= R; ++j) win[i][j] = win[i + 1][j];
     }
-    ts[qr * D::TP + qc] = t;
   }
   __syncthreads();
   cost_out = 0.5 * cost;  // lambda w r^2
