@@ -593,7 +593,9 @@ def main():
             # frames with equal shifts are averaged once at upload (srb_kernels_tilez.cuh): the kernel then reads one
             # observation per HR pixel instead of N / s^2.  `achieved` stays SURVEY 8d's algorithmic bytes (what the
             # reference's algorithm has to touch); the bytes the kernel really moves are stated beside it.
-            moved = wl.algorithmic_bytes(H, W, C, len(frames) // plan["zt_frames"], s, has_reg=True)
+            # (the weights are read by the tile kernel only when the regularizer is evaluated inside it: 2-D TV)
+            moved = wl.algorithmic_bytes(H, W, C, len(frames) // plan["zt_frames"], s,
+                                         has_reg=work["reg_kind"] == wl.REG_KIND["tv"])
             line["roofline"].update(merged_frames_per_phase=plan["zt_frames"], bytes_moved_model=moved,
                                     achieved_moved=moved / (kernel_ms * 1e-3) / 1e9,
                                     frac_moved=moved / (kernel_ms * 1e-3) / 1e9 / peak)
