@@ -404,6 +404,7 @@ def main():
     # ---- end to end through the host-facing call ----------------------------------------------------------
     e_steps = max(3, min(args.steps, 20))
     cost = 0.0
+    solve = None
     e2e_frames = None
     e2e_api = "srb_eval"
     if args.no_e2e:
@@ -437,6 +438,27 @@ def main():
                     for _ in range(e_steps):
                         cost_p, _ = me.eval(h_x.numpy(), out=h_g.numpy()[:n])
                     ms_p = (time.perf_counter() - t0) * 1e3 / e_steps
+                    if part == srb.PARTITION_ROWS and args.solve_iters > 0:
+                        # the device-resident solve on all GPUs: every solver vector cut into the same row bands
+                        try:
+                            xs = h_x.clone().pin_memory()
+                            me.cg_minimize_inplace(xs.numpy(), maxits=2)      # warm-up: workspace allocation
+                            xs.copy_(h_x)
+                            l0 = me.timing()["kernel_launches"]
+                            t0 = time.perf_counter()
+                            rep = me.cg_minimize_inplace(xs.numpy(), maxits=args.solve_iters)
+                            dt = time.perf_counter() - t0
+                            solve = {"api": "srb_multi_cg_minimize (RunCGSolverAnalyticalDiff, solver vectors in HBM cut into "
+                                            "row bands over %d GPUs, one host thread)" % world,
+                                     "iterations": rep["iterations"], "evaluations": rep["num_evaluations"],
+                                     "termination_type": rep["termination_type"], "seconds": dt,
+                                     "value": units * rep["num_evaluations"] / dt, "unit": UNIT,
+                                     "ms_per_iteration": dt * 1e3 / max(rep["iterations"], 1),
+                                     "h2d_bytes": n * 8, "d2h_bytes": n * 8,
+                                     "gpu_launches": int(me.timing()["kernel_launches"] - l0), "final_cost": rep["final_cost"]}
+                            del xs
+                        except Exception as err:
+                            solve = {"unavailable": str(err)[:200]}
                 if part == srb.PARTITION_ROWS:
                     e2e_ms, cost = ms_p, cost_p
                 else:
@@ -450,7 +472,6 @@ def main():
     ms_step, e2e_ms, kernel_ms = reduce_max(ms_step, e2e_ms, kernel_ms)
 
     # ---- a whole inner solve behind one call (N = 1) -----------------------------------------------------
-    solve = None
     if args.solve_iters > 0 and world == 1:
         xs = h_x.clone().pin_memory()
         eng.cg_minimize_inplace(xs.numpy(), maxits=2)          # warm-up: workspace allocation

@@ -340,6 +340,28 @@ srb_status srb_multi_reweight(srb_multi* m, const double* x_host, double* weight
 srb_status srb_multi_set_path(srb_multi* m, int path);
 /* ObjectiveFunction::ComputeAllTerms (objective_function.cpp:5-20) on all devices; gradient_host may be NULL. */
 srb_status srb_multi_eval(srb_multi* m, const double* x_host, double* gradient_host, double* cost);
+/* The device-resident solver (srb_cg_minimize / srb_lbfgs_minimize / srb_solve_irls above: RunCGSolverAnalyticalDiff,
+ * RunLBFGSSolverAnalyticalDiff, alglib_objective.cpp:47-140; IRLSMapSolver::RunIRLSLoop, irls_map_solver.cpp:45-157)
+ * on all devices of a SRB_PARTITION_ROWS context, still one host thread.  The (channel, tile row) units of the
+ * active range are cut into n_gpus contiguous bands; a band of units is a contiguous range of every solver vector,
+ * and device r keeps only that range of x, g, d, ...: every vector pass and every evaluation costs 1/n_gpus per
+ * device, the gradient is never exchanged, and per line-search step only the halo rows of the trial point
+ * (srb_halo_rows() rows each way, pulled from the neighbouring devices over NVLink by copy engines) and eight
+ * scalars per device (summed on the host in fixed device order: deterministic) cross the devices.  x enters and
+ * leaves over n_gpus PCIe links at once.  Same iterates as the single-device solver up to the re-association of
+ * the reductions.  A frame-sharded context (n_gpus > 1) is refused with SRB_ERR_STATE; a configuration the row
+ * bands do not cover (3-D TV, a model outside the fused tile kernel) is solved by device 0 alone.
+ * SRB_MULTI_SHARE_DEVICES=1 in the environment of srb_multi_create lets `devices` name the same GPU more than once
+ * (every entry still gets its own context and streams): the whole multi-device logic then runs on one GPU. */
+srb_status srb_multi_cg_minimize(srb_multi* m, double* x_host_inout, const srb_cg_options* options,
+                                 srb_cg_report* report);
+srb_status srb_multi_lbfgs_minimize(srb_multi* m, double* x_host_inout, const srb_cg_options* options,
+                                    srb_cg_report* report);
+/* The IRLS weights are internal to the loop (a local vector of RunIRLSLoop, irls_map_solver.cpp:66-74): they
+ * start at 1 and are reset to 1 on return (every device has re-weighted only the rows it owns). */
+srb_status srb_multi_solve_irls(srb_multi* m, double* x_host_inout, const srb_cg_options* options,
+                                int max_num_irls_iterations, double irls_cost_difference_threshold,
+                                srb_irls_report* report);
 
 /* ObjectiveDataTerm::Compute (objective_data_term.cpp:98-116): returns the data cost and ADDS the
  * data gradient into gradient_host (may be NULL). */

@@ -1387,4 +1387,5 @@ srb_status srb_get_timing(srb_ctx* c, srb_timing* out) {
 }  // extern "C"
 
 #include "srb_multi.cuh"  // single-process multi-GPU form (needs everything above)
+#include "srb_multi_solver.cuh"  // the device-resident solver on several devices (row bands)
 #include "srb_frontend.cuh"  // data generation, initial estimate, scores, ENVI + spectral PCA

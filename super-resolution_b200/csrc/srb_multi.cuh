@@ -315,7 +315,10 @@ srb_status srb_multi_create_partitioned(const srb_model_desc* d, int n_gpus, con
   for (int r = 0; r < n_gpus; ++r) {
     m->dev[r] = devices ? devices[r] : r;
     if (m->dev[r] < 0 || m->dev[r] >= ndev) return m->fail(SRB_ERR_INVALID, "invalid CUDA device index");
-    for (int q = 0; q < r; ++q)
+    // SRB_MULTI_SHARE_DEVICES=1 (tests, small boxes): the same physical device may appear more than once; every entry
+    // still gets its own context, streams and buffers, so the whole multi-device logic runs on one GPU
+    const bool share = getenv("SRB_MULTI_SHARE_DEVICES") && atoi(getenv("SRB_MULTI_SHARE_DEVICES")) != 0;
+    for (int q = 0; q < r && !share; ++q)
       if (m->dev[q] == m->dev[r]) return m->fail(SRB_ERR_INVALID, "a CUDA device is listed twice");
   }
   m->desc = *d;
@@ -364,7 +367,7 @@ srb_status srb_multi_create_partitioned(const srb_model_desc* d, int n_gpus, con
       srb_set_regularizer_rows(m->rank[r], std::min(H, r * band), std::min(H, (r + 1) * band));
     SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
     for (int q = 0; q < n_gpus && m->partition == SRB_PARTITION_FRAMES; ++q) {  // (rows: no device reads another's memory)
-      if (q == r) continue;
+      if (q == r || m->dev[q] == m->dev[r]) continue;
       int can = 0;
       SRB_MULTI_CHECK(m, cudaDeviceCanAccessPeer(&can, m->dev[r], m->dev[q]));
       if (!can) return m->fail(SRB_ERR_CUDA, "the GPUs cannot access each other's memory (NVLink / PCIe peer access)");

@@ -117,6 +117,9 @@ SIGNATURES = {
     "srb_multi_reweight": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p]),
     "srb_multi_set_path": (C.c_int, [_ctx_p, C.c_int]),
     "srb_multi_eval": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, _dp]),
+    "srb_multi_cg_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_multi_lbfgs_minimize": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srb_multi_solve_irls": (C.c_int, [_ctx_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "srb_multi_get_timing": (C.c_int, [_ctx_p, C.c_void_p]),
 }
 
@@ -703,6 +706,37 @@ class MultiEngine:
         cost = C.c_double()
         self._check(self._lib.srb_multi_eval(self._ctx, _host_ptr(xa), _host_ptr(g), C.byref(cost)))
         return cost.value, (None if g is None else g.reshape(self.c1 - self.c0, self.H, self.W))
+
+    # -- device-resident solver on all devices (row-band partition)
+    def cg_minimize_inplace(self, x, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        """srb_multi_cg_minimize on the caller's buffer (float64, contiguous, num_active elements): the initial
+        estimate on entry, the solution on return.  Returns the report dict."""
+        assert isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous and x.size == self.num_active
+        opt, rep = Engine._cg_options(epsg, epsf, epsx, maxits), CgReport()
+        self._check(self._lib.srb_multi_cg_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
+        return _as_dict(rep)
+
+    def cg_minimize(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        x = np.array(_f64(x0).reshape(-1), copy=True)
+        rep = self.cg_minimize_inplace(x, epsg, epsf, epsx, maxits)
+        return x.reshape(self.c1 - self.c0, self.H, self.W), rep
+
+    def lbfgs_minimize(self, x0, corrections=5, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0):
+        x = np.array(_f64(x0).reshape(-1), copy=True)
+        assert x.size == self.num_active
+        opt, rep = Engine._cg_options(epsg, epsf, epsx, maxits, corrections), CgReport()
+        self._check(self._lib.srb_multi_lbfgs_minimize(self._ctx, _host_ptr(x), C.byref(opt), C.byref(rep)))
+        return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
+
+    def solve_irls(self, x0, epsg=0.0, epsf=0.0, epsx=0.0, maxits=0, max_irls_iterations=20,
+                   irls_cost_difference_threshold=1.0e-5, lbfgs_corrections=0):
+        """IRLSMapSolver::RunIRLSLoop on all devices (defaults as Engine.solve_irls).  Returns (x, report dict)."""
+        x = np.array(_f64(x0).reshape(-1), copy=True)
+        assert x.size == self.num_active
+        opt, rep = Engine._cg_options(epsg, epsf, epsx, maxits, lbfgs_corrections), IrlsReport()
+        self._check(self._lib.srb_multi_solve_irls(self._ctx, _host_ptr(x), C.byref(opt), int(max_irls_iterations),
+                                                   float(irls_cost_difference_threshold), C.byref(rep)))
+        return x.reshape(self.c1 - self.c0, self.H, self.W), _as_dict(rep)
 
     def timing(self):
         t = Timing()
