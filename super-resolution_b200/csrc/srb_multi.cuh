@@ -17,6 +17,7 @@
 // evaluates its frames, and device r returns only its summed band of the gradient -- host traffic per
 // link drops by the number of devices.
 #pragma once
+#include "srb_workers.h"
 
 struct srb_multi {
   int G = 0;
@@ -41,6 +42,7 @@ struct srb_multi {
   std::vector<cudaStream_t> s_gather;
   std::vector<cudaEvent_t> ev_h2d[kMaxGroups], ev_x[kMaxGroups], ev_part[kMaxGroups], ev_t0, ev_t1;
   std::vector<double*> h_cost;           // pinned, [4] per device
+  srb::DeviceWorkers* workers = nullptr; // helper threads of the multi-device solver (srb_multi_solver.cuh), made on first use
   std::string err;
   srb_timing timing{};
   double last_ms[6] = {};                // h2d, all-gather, compute + scatter, sum, d2h, total (device 0's clock)
@@ -282,6 +284,7 @@ void srb_multi_destroy(srb_multi* m) {
     for (int g = 0; g < srb_multi::kMaxGroups; ++g) { kill(m->ev_h2d[g]); kill(m->ev_x[g]); kill(m->ev_part[g]); }
     if (r < (int)m->h_cost.size() && m->h_cost[r]) cudaFreeHost(m->h_cost[r]);
   }
+  delete m->workers;  // joins the helper threads
   for (srb_ctx* c : m->rank) srb_destroy(c);
   delete m;
 }

@@ -17,7 +17,17 @@
 //
 // The scalar logic of the backend (the cached sums, the unit direction formed on the fly) is DeviceCgBackend's,
 // with every sum taken over all devices; the kernels are the same.
+//
+// Issue rate.  A line-search step is about a dozen runtime calls per device; issued device after device from the
+// calling thread they would cost more than the kernels they start.  Every backend operation is therefore one or
+// two fork/join ROUNDS of srb::DeviceWorkers (srb_workers.h): the calling thread issues device 0's work, G - 1 helper
+// threads the other devices', each ending with the copy of its eight scalars and the synchronisation of its own
+// stream; the calling thread then adds the scalars.  The join between two rounds is what orders "every device has
+// recorded the event that marks its rows of x" before "every device waits on its neighbours' events".
+// SRB_MULTI_THREADS=0: no helpers, the calling thread walks over the devices (A/B runs).
 #pragma once
+#include <atomic>
+#include <mutex>
 
 namespace srb {
 
@@ -46,8 +56,10 @@ struct MultiCgBackend {
   int G = 0;
   long long n = 0;
   Part part[SRB_MAX_PEERS];
-  double out[8] = {};  // the scalars of the last fetch, combined over the devices
-  srb_status status = SRB_OK;
+  double out[8] = {};  // the scalars of the last operation, combined over the devices
+  std::atomic<int> status{SRB_OK};  // first failure of any device (helpers report concurrently)
+  std::mutex err_mu;
+  DeviceWorkers* workers = nullptr;
   long long evals = 0;
 
   // (see DeviceCgBackend) the unit direction d = (dk * s1) * s2 is never stored
@@ -59,22 +71,32 @@ struct MultiCgBackend {
   double trial_dy = 0.0, trial_gg = 0.0, trial_gy = 0.0;
 
   long long size() const { return n; }
-  bool ok() const { return status == SRB_OK; }
+  bool ok() const { return status.load(std::memory_order_relaxed) == SRB_OK; }
+  srb_status result() const { return (srb_status)status.load(); }
   void fail_cuda(cudaError_t e, const char* what) {
-    if (e != cudaSuccess && status == SRB_OK)
-      status = m->fail(SRB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    if (e == cudaSuccess) return;
+    std::lock_guard<std::mutex> lk(err_mu);
+    if (ok()) status = m->fail(SRB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
   }
   void fail_rank(int r, srb_status st) {
-    if (st != SRB_OK && status == SRB_OK) status = multi_status(m, r, st);
+    if (st == SRB_OK) return;
+    std::lock_guard<std::mutex> lk(err_mu);
+    if (ok()) status = multi_status(m, r, st);
   }
-  // f(r, part) on every device that owns a non-empty range, with that device current
+  // One round: f(r, part) for every device that owns a non-empty range, with that device current -- device 0 on
+  // the calling thread, the others on the helper threads; returns when all have returned.
   template <class F>
   void each(F f) {
-    for (int r = 0; r < G; ++r) {
+    auto job = [&](int r) {
       Part& p = part[r];
-      if (p.nl <= 0) continue;
+      if (p.nl <= 0) return;
       fail_cuda(cudaSetDevice(p.dev), "cudaSetDevice");
       f(r, p);
+    };
+    if (workers && G > 1) {
+      workers->run(G, job);
+    } else {
+      for (int r = 0; r < G; ++r) job(r);
     }
   }
   static double* at(const Part& p, Vec v) { return p.slot[v] + p.off; }
@@ -83,12 +105,13 @@ struct MultiCgBackend {
     k_cg_finish<<<1, CG_NT, 0, p.c->stream>>>(p.d_part, p.nblk, nsums, max_mask, p.d_out + offset);
     launched(p, 2);
   }
-  // the reductions queued so far -> out[0..8): sums (maxima where max_mask says so) over the devices, fixed order
-  void fetch(int max_mask = 0) {
-    each([&](int, Part& p) {
-      fail_cuda(cudaMemcpyAsync(p.h_out, p.d_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, p.c->stream), "solver fetch");
-    });
-    each([&](int, Part& p) { fail_cuda(cudaStreamSynchronize(p.c->stream), "solver synchronize"); });
+  // end of a device's share of a round: its eight scalars -> its pinned mirror, its stream drained
+  void pull(Part& p) {
+    fail_cuda(cudaMemcpyAsync(p.h_out, p.d_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, p.c->stream), "solver fetch");
+    fail_cuda(cudaStreamSynchronize(p.c->stream), "solver synchronize");
+  }
+  // after the round: out[0..8) = sums (maxima where max_mask says so) over the devices, fixed order
+  void combine(int max_mask = 0) {
     for (int k = 0; k < 8; ++k) {
       double v = 0.0;
       for (int r = 0; r < G; ++r) {
@@ -106,11 +129,14 @@ struct MultiCgBackend {
     if (v == unit_g0) trial_g = unit_g0 = kNone;
   }
 
-  // every device's range of x is complete on its stream: pull the halo rows from their owners
-  void exchange_halo(Vec x) {
-    if (G == 1) return;
-    each([&](int, Part& p) { fail_cuda(cudaEventRecord(p.ev_slice, p.c->stream), "cudaEventRecord"); });
-    each([&](int, Part& p) {
+  // Halo exchange, two halves in two rounds: mark() -- this device's rows of x are complete on its stream (the
+  // last call of a round) -- and halo() -- pull the halo rows from their owners behind THEIR marks (the first call
+  // of the next round; the join in between guarantees that every mark has been recorded).
+  void mark(Part& p) {
+    if (G > 1) fail_cuda(cudaEventRecord(p.ev_slice, p.c->stream), "cudaEventRecord");
+  }
+  void halo(Part& p, Vec x) {
+    {
       for (const Pull& h : p.pulls) {
         const Part& q = part[h.from];
         fail_cuda(cudaStreamWaitEvent(p.c->stream, q.ev_slice, 0), "cudaStreamWaitEvent");
@@ -120,21 +146,23 @@ struct MultiCgBackend {
         else
           fail_cuda(cudaMemcpyPeerAsync(p.slot[x] + h.begin, p.dev, q.slot[x] + h.begin, q.dev, bytes, p.c->stream), "halo copy");
       }
-    });
+    }
   }
   // objective + gradient of this device's units at x -> its range of g, its share of the cost -> d_out[5]
-  void evaluate(Vec x, Vec g) {
-    exchange_halo(x);
-    each([&](int r, Part& p) {
-      if (ok()) fail_rank(r, srb_eval_unit_range_dev(p.c, p.slot[x], p.slot[g], p.u0, p.u1, p.d_out + 5));
-    });
-    ++evals;
+  void evaluate(int r, Part& p, Vec x, Vec g) {
+    halo(p, x);
+    if (ok()) fail_rank(r, srb_eval_unit_range_dev(p.c, p.slot[x], p.slot[g], p.u0, p.u1, p.d_out + 5));
   }
 
   void eval(Vec x, Vec g, double* f) {
     forget(g);
-    evaluate(x, g);
-    fetch();
+    if (G > 1) each([&](int, Part& p) { mark(p); });
+    each([&](int r, Part& p) {
+      evaluate(r, p, x, g);
+      pull(p);
+    });
+    ++evals;
+    combine();
     *f = out[5];
   }
   void copy(Vec dst, Vec src) {
@@ -163,24 +191,27 @@ struct MultiCgBackend {
       else
         k_cg_reduce<0><<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, a), at(p, b), nullptr, p.nl, p.d_part);
       finish(p, 1);
+      pull(p);
     });
-    fetch();
+    combine();
     return out[0];
   }
   double sum_sq(Vec a) {
     each([&](int, Part& p) {
       k_cg_reduce<1><<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, a), nullptr, nullptr, p.nl, p.d_part);
       finish(p, 1);
+      pull(p);
     });
-    fetch();
+    combine();
     return out[0];
   }
   double max_abs(Vec a) {
     each([&](int, Part& p) {
       k_cg_max_abs<<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, a), p.nl, p.d_part);
       finish(p, 1, 1);
+      pull(p);
     });
-    fetch(1);
+    combine(1);
     return out[0];
   }
   void normalize_to(Vec d, Vec dk, double mx, Vec g0, double* stp, double* slope, double* dd) {
@@ -205,8 +236,9 @@ struct MultiCgBackend {
         finish(p, 1);
         k_cg_reduce<0><<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, g0), at(p, dk), nullptr, p.nl, p.d_part);
         finish(p, 1, 0, 1);
+        pull(p);
       });
-      fetch();
+      combine();
       sumsq_scaled = out[0];
       gdk = out[1];
     }
@@ -225,11 +257,12 @@ struct MultiCgBackend {
       if (unit) k_cg_step_scaled<<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, x), at(p, x0), stp, at(p, unit_src), unit_s1, unit_s2, p.nl, p.d_part);
       else k_cg_step<<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, x), at(p, x0), stp, at(p, d), p.nl, p.d_part);
       finish(p, 1, 0, 4);  // moved -> d_out[4]
+      mark(p);
     });
     if (g == trial_g) trial_g = kNone;
-    evaluate(x, g);
     const bool sums = unit && unit_g0 != kNone && g != unit_g0;
-    each([&](int, Part& p) {
+    each([&](int r, Part& p) {
+      evaluate(r, p, x, g);
       if (sums) {
         k_cg_trial_sums<<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, g), at(p, unit_g0), at(p, unit_src), unit_s1, unit_s2, p.nl, p.d_part);
         finish(p, 4);
@@ -240,8 +273,10 @@ struct MultiCgBackend {
         k_cg_reduce<0><<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, g), at(p, d), nullptr, p.nl, p.d_part);
         finish(p, 1);
       }
+      pull(p);
     });
-    fetch();
+    ++evals;
+    combine();
     *f = out[5];
     *dg = out[0];
     *moved = out[4];
@@ -258,8 +293,9 @@ struct MultiCgBackend {
     each([&](int, Part& p) {
       k_cg_reduce<3><<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, gn), at(p, go), at(p, dk), p.nl, p.d_part);
       finish(p, 3);
+      pull(p);
     });
-    fetch();
+    combine();
     *dy = out[0]; *gg = out[1]; *gy = out[2];
   }
   void direction(Vec dk, Vec g, double beta, double* gg, double* mx) {
@@ -267,8 +303,9 @@ struct MultiCgBackend {
     each([&](int, Part& p) {
       k_cg_direction<<<p.nblk, CG_NT, 0, p.c->stream>>>(at(p, dk), at(p, g), beta, p.nl, p.d_part);
       finish(p, 4, 2);
+      pull(p);
     });
-    fetch(2);
+    combine(2);
     *gg = out[0]; *mx = out[1];
     dir_dk = dk; dir_g = g; dir_sumsq = out[2]; dir_gdk = out[3];
   }
@@ -287,8 +324,9 @@ struct MultiCgBackend {
   // w = 1 / max(1e-5, reg(x)) (irls_map_solver.cpp:128-143): regularizer values are local, so every device
   // re-weights from its own rows of x plus the halo -- the weights its units read are exact, the rest unused
   void reweight(Vec x) {
-    exchange_halo(x);
+    if (G > 1) each([&](int, Part& p) { mark(p); });
     each([&](int r, Part& p) {
+      halo(p, x);
       if (ok()) fail_rank(r, reweight_dev(p.c, p.slot[x]));
     });
   }
@@ -302,6 +340,23 @@ inline bool multi_solver_rows_ok(srb_multi* m) {
     if (!unit_ranges_ok(m->rank[r])) return false;
   return host_slices_ok(m->rank[0]);
 }
+
+// The helper threads spin between rounds while a solve is running and sleep otherwise.
+struct MultiSolveScope {
+  DeviceWorkers* w = nullptr;
+  MultiSolveScope(srb_multi* m, MultiCgBackend* be) {
+    const char* e = getenv("SRB_MULTI_THREADS");
+    if (m->G > 1 && !(e && atoi(e) == 0)) {
+      if (!m->workers) m->workers = new (std::nothrow) DeviceWorkers(m->G - 1);
+      w = m->workers;
+    }
+    be->workers = w;
+    if (w) w->set_hot(true);
+  }
+  ~MultiSolveScope() {
+    if (w) w->set_hot(false);
+  }
+};
 
 // Devices, ranges, halos, workspaces of one solve; uploads every device's range (+ halo) of x.
 inline srb_status multi_solver_begin(srb_multi* m, MultiCgBackend* be, const double* x_host, int num_vectors) {
@@ -392,7 +447,7 @@ inline srb_status multi_solver_end(srb_multi* m, MultiCgBackend* be, double* x_h
     SRB_MULTI_CHECK(m, cudaStreamSynchronize(p.c->stream));
     SRB_MULTI_CHECK(m, cudaGetLastError());
   }
-  return be->status;
+  return be->result();
 }
 
 inline std::vector<int> multi_solver_scratch(int num_vectors) {
@@ -426,6 +481,7 @@ srb_status srb_multi_cg_minimize(srb_multi* m, double* x_host, const srb_cg_opti
   if (!multi_solver_rows_ok(m))  // e.g. 3-D TV: every device holds the whole model, device 0 solves alone
     return multi_status(m, 0, srb_cg_minimize(m->rank[0], x_host, options, report));
   MultiCgBackend be;
+  MultiSolveScope scope(m, &be);
   if ((st = multi_solver_begin(m, &be, x_host, kCgScratchVectors)) != SRB_OK) return st;
   std::vector<int> scratch = multi_solver_scratch(kCgScratchVectors);
   const CgReport rep = cg_minimize(be, 0, scratch.data(), cg_options_from(options));
@@ -449,6 +505,7 @@ srb_status srb_multi_lbfgs_minimize(srb_multi* m, double* x_host, const srb_cg_o
   if (!multi_solver_rows_ok(m)) return multi_status(m, 0, srb_lbfgs_minimize(m->rank[0], x_host, options, report));
   const int mm = options->num_lbfgs_hessian_corrections, nvec = lbfgs_scratch_vectors(mm);
   MultiCgBackend be;
+  MultiSolveScope scope(m, &be);
   if ((st = multi_solver_begin(m, &be, x_host, nvec)) != SRB_OK) return st;
   std::vector<int> scratch = multi_solver_scratch(nvec);
   const CgReport rep = lbfgs_minimize(be, 0, scratch.data(), mm, cg_options_from(options));
@@ -481,6 +538,7 @@ srb_status srb_multi_solve_irls(srb_multi* m, double* x_host, const srb_cg_optio
   const int mm = options ? options->num_lbfgs_hessian_corrections : 0;
   const int nvec = mm > 0 ? lbfgs_scratch_vectors(mm) : kCgScratchVectors;
   MultiCgBackend be;
+  MultiSolveScope scope(m, &be);
   if ((st = multi_solver_begin(m, &be, x_host, nvec)) != SRB_OK) return st;
   std::vector<int> scratch = multi_solver_scratch(nvec);
   const IrlsReport rep = irls_solve(be, 0, scratch.data(), cg_options_from(options), max_num_irls_iterations,
