@@ -347,7 +347,13 @@ struct MultiSolveScope {
   MultiSolveScope(srb_multi* m, MultiCgBackend* be) {
     const char* e = getenv("SRB_MULTI_THREADS");
     if (m->G > 1 && !(e && atoi(e) == 0)) {
-      if (!m->workers) m->workers = new (std::nothrow) DeviceWorkers(m->G - 1);
+      if (!m->workers) {
+        try {
+          m->workers = new DeviceWorkers(m->G - 1);
+        } catch (...) {  // no threads to be had: the calling thread issues every device's work itself
+          m->workers = nullptr;
+        }
+      }
       w = m->workers;
     }
     be->workers = w;

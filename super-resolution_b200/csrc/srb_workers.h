@@ -24,16 +24,14 @@ class DeviceWorkers {
  public:
   explicit DeviceWorkers(int helpers) : helpers_(helpers < 0 ? 0 : helpers) {
     threads_.reserve(helpers_);
-    for (int i = 0; i < helpers_; ++i) threads_.emplace_back([this, i] { loop(i + 1); });
-  }
-  ~DeviceWorkers() {
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      stop_.store(true, std::memory_order_release);
+    try {
+      for (int i = 0; i < helpers_; ++i) threads_.emplace_back([this, i] { loop(i + 1); });
+    } catch (...) {  // the system refused a thread: release the ones that started, let the caller fall back
+      shutdown();
+      throw;
     }
-    cv_.notify_all();
-    for (std::thread& t : threads_) t.join();
   }
+  ~DeviceWorkers() { shutdown(); }
   DeviceWorkers(const DeviceWorkers&) = delete;
   DeviceWorkers& operator=(const DeviceWorkers&) = delete;
 
@@ -68,6 +66,15 @@ class DeviceWorkers {
   }
 
  private:
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_.store(true, std::memory_order_release);
+    }
+    cv_.notify_all();
+    for (std::thread& t : threads_) t.join();
+    threads_.clear();
+  }
   static void relax(unsigned spins) {
 #if defined(__x86_64__) || defined(__i386__)
     if (spins < 4096) {
