@@ -131,6 +131,21 @@ k_multi_sum_pull(MultiPtrs Gp, int world, int rank, long long begin, long long e
   }
 }
 
+// The helper threads of a context (G - 1 of them), made on first use; NULL for one device, with SRB_MULTI_THREADS=0,
+// or when the system refuses a thread -- the calling thread then issues every device's work itself.
+inline DeviceWorkers* multi_workers(srb_multi* m) {
+  const char* e = getenv("SRB_MULTI_THREADS");
+  if (m->G <= 1 || (e && atoi(e) == 0)) return nullptr;
+  if (!m->workers) {
+    try {
+      m->workers = new DeviceWorkers(m->G - 1);
+    } catch (...) {
+      m->workers = nullptr;
+    }
+  }
+  return m->workers;
+}
+
 inline srb_status multi_status(srb_multi* m, int r, srb_status st) {
   if (st != SRB_OK) m->err = std::string("device ") + std::to_string(m->dev[r]) + ": " + m->rank[r]->err;
   return st;
@@ -191,74 +206,109 @@ inline srb_status multi_plan_bands(srb_multi* m) {
 // costs.  Per-device compute, H2D and D2H all drop by the number of devices.
 inline srb_status multi_eval_rows(srb_multi* m, const double* x_host, double* g_host, double* cost) {
   const int G = m->G, NG = m->ngroups;
-  for (int r = 0; r < G; ++r) {
-    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t0[r], m->rank[r]->s_in));
-  }
-  for (int g = 0; g < NG; ++g) {
-    const long long* be = m->band_elem[g];
-    for (int r = 0; r < G; ++r) {
-      srb_ctx* c = m->rank[r];
-      SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-      const bool have = m->band_unit[g][r + 1] > m->band_unit[g][r];
-      if (have) {
-        // band + halo, clipped to the channels the band touches (no stencil crosses a channel boundary)
-        const long long P = (long long)c->P, W = c->g.W, halo = (long long)stencil_halo_rows(c) * W;
-        const long long lo = std::max(be[r] - halo, be[r] / P * P);
-        const long long hi = std::min(be[r + 1] + halo, (be[r + 1] + P - 1) / P * P);
-        SRB_MULTI_CHECK(m, cudaMemcpyAsync(c->d_x + lo, x_host + lo, (size_t)(hi - lo) * sizeof(double),
-                                           cudaMemcpyHostToDevice, c->s_in));
+  // The devices do not depend on each other here, so with helper threads (srb_workers.h; one fork/join round per
+  // call, the helpers sleep in between -- a host solver computes for milliseconds between two evaluations) every
+  // device's ~10 runtime calls per group are issued by its own thread; without them the calling thread issues
+  // group by group so that every device's pipeline starts early.  Failures are recorded per device.
+  struct DevErr {
+    srb_status st = SRB_OK;
+    std::string msg;
+    srb_status fail(srb_status s, const std::string& t) {
+      if (st == SRB_OK) {
+        st = s;
+        msg = t;
       }
-      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_h2d[g][r], c->s_in));
-      SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->stream, m->ev_h2d[g][r], 0));
-      if (g == 0) {
-        // only this device's units write their cost slots: the others must read as zero
-        const TileLayout L = tile_layout(c);
-        const size_t need = 2 * L.nblocks + L.nband;
-        if (need > c->partial_capacity) {
-          if (c->d_partial) cudaFree(c->d_partial);
-          c->d_partial = nullptr;
-          c->partial_capacity = 0;
-          SRB_MULTI_CHECK(m, cudaMalloc((void**)&c->d_partial, need * sizeof(double)));
-          c->partial_capacity = need;
-        }
-        SRB_MULTI_CHECK(m, cudaMemsetAsync(c->d_partial, 0, need * sizeof(double), c->stream));
-      }
-      if (have) {
-        const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
-        bool reg_done = false;
-        srb_status st = fused_eval_units(c, c->d_x, g_host ? c->d_grad : nullptr, do_reg, m->band_unit[g][r],
-                                         m->band_unit[g][r + 1], &reg_done);
-        if (st != SRB_OK) return multi_status(m, r, st);
-        st = fused_band_units(c, c->d_x, g_host ? c->d_grad : nullptr, m->band_unit[g][r], m->band_unit[g][r + 1]);
-        if (st != SRB_OK) return multi_status(m, r, st);
-      }
-      if (g == NG - 1) {
-        srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr, /*run_band=*/false);
-        if (st != SRB_OK) return multi_status(m, r, st);
-        c->timing.num_evals += 1;
-        SRB_MULTI_CHECK(m, cudaMemcpyAsync(m->h_cost[r], c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      }
-      SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_part[g][r], c->stream));
-      if (g_host && have) {
-        SRB_MULTI_CHECK(m, cudaStreamWaitEvent(c->s_out, m->ev_part[g][r], 0));
-        SRB_MULTI_CHECK(m, cudaMemcpyAsync(g_host + be[r], c->d_grad + be[r], (size_t)(be[r + 1] - be[r]) * sizeof(double),
-                                           cudaMemcpyDeviceToHost, c->s_out));
-      }
-      c->x_resident = false;  // only this device's bands of x are here
+      return s;
     }
+  };
+  DevErr err[SRB_MAX_PEERS];
+  auto begin = [&](int r) -> srb_status {
+    SRB_MULTI_CHECK(&err[r], cudaSetDevice(m->dev[r]));
+    SRB_MULTI_CHECK(&err[r], cudaEventRecord(m->ev_t0[r], m->rank[r]->s_in));
+    return SRB_OK;
+  };
+  auto issue = [&](int r, int g) -> srb_status {
+    DevErr* e = &err[r];
+    const long long* be = m->band_elem[g];
+    srb_ctx* c = m->rank[r];
+    SRB_MULTI_CHECK(e, cudaSetDevice(m->dev[r]));
+    const bool have = m->band_unit[g][r + 1] > m->band_unit[g][r];
+    if (have) {
+      // band + halo, clipped to the channels the band touches (no stencil crosses a channel boundary)
+      const long long P = (long long)c->P, W = c->g.W, halo = (long long)stencil_halo_rows(c) * W;
+      const long long lo = std::max(be[r] - halo, be[r] / P * P);
+      const long long hi = std::min(be[r + 1] + halo, (be[r + 1] + P - 1) / P * P);
+      SRB_MULTI_CHECK(e, cudaMemcpyAsync(c->d_x + lo, x_host + lo, (size_t)(hi - lo) * sizeof(double),
+                                         cudaMemcpyHostToDevice, c->s_in));
+    }
+    SRB_MULTI_CHECK(e, cudaEventRecord(m->ev_h2d[g][r], c->s_in));
+    SRB_MULTI_CHECK(e, cudaStreamWaitEvent(c->stream, m->ev_h2d[g][r], 0));
+    if (g == 0) {
+      // only this device's units write their cost slots: the others must read as zero
+      const TileLayout L = tile_layout(c);
+      const size_t need = 2 * L.nblocks + L.nband;
+      if (need > c->partial_capacity) {
+        if (c->d_partial) cudaFree(c->d_partial);
+        c->d_partial = nullptr;
+        c->partial_capacity = 0;
+        SRB_MULTI_CHECK(e, cudaMalloc((void**)&c->d_partial, need * sizeof(double)));
+        c->partial_capacity = need;
+      }
+      SRB_MULTI_CHECK(e, cudaMemsetAsync(c->d_partial, 0, need * sizeof(double), c->stream));
+    }
+    if (have) {
+      const bool do_reg = reg_active(c) && c->reg_row1 > c->reg_row0;
+      bool reg_done = false;
+      srb_status st = fused_eval_units(c, c->d_x, g_host ? c->d_grad : nullptr, do_reg, m->band_unit[g][r],
+                                       m->band_unit[g][r + 1], &reg_done);
+      if (st == SRB_OK)
+        st = fused_band_units(c, c->d_x, g_host ? c->d_grad : nullptr, m->band_unit[g][r], m->band_unit[g][r + 1]);
+      if (st != SRB_OK) return e->fail(st, std::string("device ") + std::to_string(m->dev[r]) + ": " + c->err);
+    }
+    if (g == NG - 1) {
+      srb_status st = fused_eval_finish(c, c->d_x, g_host ? c->d_grad : nullptr, nullptr, /*run_band=*/false);
+      if (st != SRB_OK) return e->fail(st, std::string("device ") + std::to_string(m->dev[r]) + ": " + c->err);
+      c->timing.num_evals += 1;
+      SRB_MULTI_CHECK(e, cudaMemcpyAsync(m->h_cost[r], c->d_cost, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    SRB_MULTI_CHECK(e, cudaEventRecord(m->ev_part[g][r], c->stream));
+    if (g_host && have) {
+      SRB_MULTI_CHECK(e, cudaStreamWaitEvent(c->s_out, m->ev_part[g][r], 0));
+      SRB_MULTI_CHECK(e, cudaMemcpyAsync(g_host + be[r], c->d_grad + be[r], (size_t)(be[r + 1] - be[r]) * sizeof(double),
+                                         cudaMemcpyDeviceToHost, c->s_out));
+    }
+    c->x_resident = false;  // only this device's bands of x are here
+    return SRB_OK;
+  };
+  auto drain = [&](int r) -> srb_status {
+    SRB_MULTI_CHECK(&err[r], cudaSetDevice(m->dev[r]));
+    SRB_MULTI_CHECK(&err[r], cudaEventRecord(m->ev_t1[r], m->rank[r]->s_out));
+    SRB_MULTI_CHECK(&err[r], cudaStreamSynchronize(m->rank[r]->s_out));
+    SRB_MULTI_CHECK(&err[r], cudaStreamSynchronize(m->rank[r]->stream));
+    return SRB_OK;
+  };
+  DeviceWorkers* workers = multi_workers(m);
+  if (workers) {
+    workers->run(G, [&](int r) {
+      bool ok = begin(r) == SRB_OK;
+      for (int g = 0; g < NG && ok; ++g) ok = issue(r, g) == SRB_OK;
+      (void)drain(r);  // whatever was issued has to finish before the buffers are touched again
+    });
+  } else {
+    bool ok = true;
+    for (int r = 0; r < G && ok; ++r) ok = begin(r) == SRB_OK;
+    for (int g = 0; g < NG && ok; ++g)
+      for (int r = 0; r < G && ok; ++r) ok = issue(r, g) == SRB_OK;
+    for (int r = 0; r < G; ++r) (void)drain(r);
   }
+  for (int r = 0; r < G; ++r)
+    if (err[r].st != SRB_OK) return m->fail(err[r].st, err[r].msg);
   double total = 0.0;
-  for (int r = 0; r < G; ++r) {
-    SRB_MULTI_CHECK(m, cudaSetDevice(m->dev[r]));
-    SRB_MULTI_CHECK(m, cudaEventRecord(m->ev_t1[r], m->rank[r]->s_out));
-    SRB_MULTI_CHECK(m, cudaStreamSynchronize(m->rank[r]->s_out));
-    SRB_MULTI_CHECK(m, cudaStreamSynchronize(m->rank[r]->stream));
-    total += m->h_cost[r][2];  // fixed device order
-  }
+  for (int r = 0; r < G; ++r) total += m->h_cost[r][2];  // fixed device order
   if (cost) *cost = total;
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, m->ev_t0[0], m->ev_t1[0]) == cudaSuccess) m->last_ms[5] = ms;
+  if (cudaSetDevice(m->dev[0]) == cudaSuccess && cudaEventElapsedTime(&ms, m->ev_t0[0], m->ev_t1[0]) == cudaSuccess)
+    m->last_ms[5] = ms;
   (void)cudaGetLastError();
   m->timing.num_evals += 1;
   return SRB_OK;

@@ -345,17 +345,7 @@ inline bool multi_solver_rows_ok(srb_multi* m) {
 struct MultiSolveScope {
   DeviceWorkers* w = nullptr;
   MultiSolveScope(srb_multi* m, MultiCgBackend* be) {
-    const char* e = getenv("SRB_MULTI_THREADS");
-    if (m->G > 1 && !(e && atoi(e) == 0)) {
-      if (!m->workers) {
-        try {
-          m->workers = new DeviceWorkers(m->G - 1);
-        } catch (...) {  // no threads to be had: the calling thread issues every device's work itself
-          m->workers = nullptr;
-        }
-      }
-      w = m->workers;
-    }
+    w = multi_workers(m);
     be->workers = w;
     if (w) w->set_hot(true);
   }
