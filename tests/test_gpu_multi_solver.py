@@ -179,3 +179,26 @@ def test_multi_solver_channel_range_and_fallbacks(srb, oracle, monkeypatch):
         _configure(srb, me, lr, "tv")
         with pytest.raises(srb.SrbError):               # mincgsetcond asserts non-negative thresholds
             me.cg_minimize(x0, epsg=-1.0)
+
+
+def test_irls_map_solver_solve_on_several_devices(srb, oracle, monkeypatch):
+    """IRLSMapSolver::Solve (irls_map_solver.cpp:192-265; solver.solve: threshold scaling, one round per channel with
+    split_channels) on a multi-device context: the same rounds as on one device, every round one srb_multi_solve_irls."""
+    solver = import_module("super-resolution_b200.solver")
+    N, s, K, sigma, C, h, w, reg, frac = CASES["cfg3_tv"]
+    psf, shifts, lr, x0 = _problem(oracle, N, s, K, sigma, 3, h, w, seed=33)
+    lam = 0.01
+    for split in (False, True):
+        opt = solver.IrlsMapSolverOptions(max_num_solver_iterations=5, max_num_irls_iterations=2, split_channels=split)
+        with srb.Engine(lr.shape, s, psf, shifts) as e1:
+            _configure(srb, e1, lr, reg, lam)
+            x1, rep1 = solver.solve(e1, x0, opt, regularization_parameter_sum=lam)
+        with _multi(srb, monkeypatch, lr.shape, s, psf, shifts, 3, "shared") as me:
+            _configure(srb, me, lr, reg, lam)
+            xm, repm = solver.solve(me, x0, opt, regularization_parameter_sum=lam)
+        assert len(repm) == len(rep1) == (3 if split else 1)
+        for a, b in zip(repm, rep1):
+            assert a["num_irls_iterations"] == b["num_irls_iterations"]
+            assert a["num_solver_iterations"] == b["num_solver_iterations"]
+        print("IRLSMapSolver::Solve split_channels=%s on 3 contexts: rel L2 vs one device %.3e" % (split, rel_l2(xm, x1)))
+        assert rel_l2(xm, x1) <= 1e-7
