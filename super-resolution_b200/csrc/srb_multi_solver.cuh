@@ -29,6 +29,8 @@
 #include <atomic>
 #include <mutex>
 
+#include "srb_row_bands.h"
+
 namespace srb {
 
 struct MultiCgBackend {
@@ -361,23 +363,16 @@ inline srb_status multi_solver_begin(srb_multi* m, MultiCgBackend* be, const dou
   be->m = m;
   be->G = G;
   be->n = (long long)c0->n_active();
-  const int Ca = c0->Ca(), tr = tile_rows_per_channel(c0), TH = tile_height(c0);
-  const int nu = tr * Ca;
-  const long long P = (long long)c0->P, W = c0->g.W;
-  auto first_elem = [&](int u) -> long long {
-    if (u >= nu) return be->n;
-    const int ch = u / tr, t = u - ch * tr;
-    const int row = t * TH < c0->g.H ? t * TH : c0->g.H;
-    return (long long)ch * P + (long long)row * W;
-  };
+  // the partition is host arithmetic (srb_row_bands.h; tests/test_row_bands.py); the halo is the same on every device
+  const std::vector<RowBand> bands = plan_row_bands(G, c0->Ca(), c0->g.H, c0->g.W, tile_height(c0), stencil_halo_rows(c0));
   for (int r = 0; r < G; ++r) {
     MultiCgBackend::Part& p = be->part[r];
     p.c = m->rank[r];
     p.dev = m->dev[r];
-    p.u0 = (int)((long long)nu * r / G);
-    p.u1 = (int)((long long)nu * (r + 1) / G);
-    p.off = first_elem(p.u0);
-    p.nl = first_elem(p.u1) - p.off;
+    p.u0 = bands[r].u0;
+    p.u1 = bands[r].u1;
+    p.off = bands[r].begin;
+    p.nl = bands[r].end - bands[r].begin;
     p.ev_slice = m->ev_x[0][r];
   }
   for (int r = 0; r < G; ++r) {
@@ -396,18 +391,8 @@ inline srb_status multi_solver_begin(srb_multi* m, MultiCgBackend* be, const dou
     for (int k = 0; k < 8; ++k) p.h_out[k] = 0.0;
     p.pulls.clear();
     if (p.nl <= 0) continue;
-    // halo rows of the estimate, clipped to the channels the range touches (no stencil crosses a channel)
-    const long long halo = (long long)stencil_halo_rows(p.c) * W;
-    const long long b0 = p.off, b1 = p.off + p.nl;
-    const long long lo = std::max(b0 - halo, b0 / P * P), hi = std::min(b1 + halo, (b1 + P - 1) / P * P);
-    for (int q = 0; q < G; ++q) {
-      if (q == r || be->part[q].nl <= 0) continue;
-      const long long q0 = be->part[q].off, q1 = q0 + be->part[q].nl;
-      const long long a0 = std::max(lo, q0), a1 = std::min(b0, q1);   // below the range
-      if (a1 > a0) p.pulls.push_back({q, a0, a1});
-      const long long c0e = std::max(b1, q0), c1e = std::min(hi, q1);  // above it
-      if (c1e > c0e) p.pulls.push_back({q, c0e, c1e});
-    }
+    const long long lo = bands[r].halo_begin, hi = bands[r].halo_end;
+    for (const RowBandPull& h : bands[r].pulls) p.pulls.push_back({h.from, h.begin, h.end});
     // direct NVLink copies where the devices can reach each other (a staged copy otherwise: still correct)
     for (const MultiCgBackend::Pull& h : p.pulls) {
       const int qd = be->part[h.from].dev;
