@@ -322,7 +322,13 @@ srb_status srb_memcpy_d2h(srb_ctx* ctx, void* dst_host, const void* src_dev, uns
  * per device all drop by n_gpus.  Costs n_gpus copies of the observations in HBM (cfg3 100 MB, cfg5 1.6 GB
  * per device).  Applies when the fused tile kernel covers the model, with a regularizer other than 3-D TV (which
  * couples the channels); otherwise device 0 evaluates alone.  srb_multi_create takes the partition
- * from SRB_MULTI_PARTITION=frames|rows in the environment (default frames). */
+ * from SRB_MULTI_PARTITION=frames|rows in the environment (default frames).
+ *
+ * Threads.  The entry points are called from one thread and are not re-entrant per context.  For the row-band
+ * evaluation and the multi-device solver below the library keeps n_gpus - 1 helper threads per context (made on
+ * first use, joined by srb_multi_destroy) that issue the other devices' runtime calls beside the calling thread;
+ * they sleep between calls and spin only while a srb_multi_*_minimize / srb_multi_solve_irls call is running.
+ * SRB_MULTI_THREADS=0 in the environment keeps everything on the calling thread. */
 enum { SRB_PARTITION_FRAMES = 0, SRB_PARTITION_ROWS = 1 };
 typedef struct srb_multi srb_multi;
 srb_status srb_multi_create(const srb_model_desc* desc, int n_gpus, const int* devices, srb_multi** out);
