@@ -75,3 +75,21 @@ def test_invalid_arguments_are_rejected_before_touching_cuda():
     st = lib.srb_create(ctypes.byref(desc), 0, ctypes.byref(ctx))
     assert st == 1
     lib.srb_destroy(ctx)
+
+
+def test_multi_device_entry_points_fail_loudly_without_a_device_or_context():
+    """The multi-GPU forms behind the same boundary: a NULL context is SRB_ERR_INVALID, and without a CUDA device
+    srb_multi_create fails with SRB_ERR_CUDA (there is no CPU path to fall back to)."""
+    import srb200
+    lib = srb200.load_library()
+    x = np.zeros(4)
+    xp = x.ctypes.data_as(ctypes.c_void_p)
+    assert lib.srb_multi_eval(None, xp, None, None) == 1
+    assert lib.srb_multi_cg_minimize(None, xp, None, None) == 1
+    assert lib.srb_multi_lbfgs_minimize(None, xp, None, None) == 1
+    assert lib.srb_multi_solve_irls(None, xp, None, 20, 1e-5, None) == 1
+    if srb200.device_count() > 0:
+        return
+    with pytest.raises(srb200.SrbError) as ei:
+        srb200.MultiEngine((4, 1, 8, 8), 2, n_gpus=2, partition=srb200.PARTITION_ROWS)
+    assert "no CPU fallback" in str(ei.value)
